@@ -1,0 +1,79 @@
+// devdefs.cuh — compiler shims shared by all code of the engine.
+//
+// The games and the search body are written once as inline functions.  Under
+// nvcc they are __host__ __device__: the kernels (engine.cu) run them on the
+// GPU, and the host game helpers of the C ABI (games_host.cu: deal / legal /
+// apply / result, no search) run the very same rules on the host.  The same
+// headers also compile with plain g++; tests/emu uses that to check the device
+// logic against the oracle on a machine without a GPU (test infrastructure, not
+// part of the product library — the search itself has no host path).
+#pragma once
+
+#include <stdint.h>
+#include <chrono>
+
+#if defined(__CUDACC__)
+#define ISMCTS_DEV __host__ __device__ __forceinline__
+#define ISMCTS_HDI __host__ __device__ __forceinline__
+#else
+#define ISMCTS_DEV inline
+#define ISMCTS_HDI inline
+#endif
+
+#include "../../include/ismcts_detmath.h"
+
+namespace ismcts {
+
+#if defined(__CUDA_ARCH__)
+ISMCTS_DEV uint32_t popc32(uint32_t x) { return (uint32_t)__popc(x); }
+ISMCTS_DEV uint32_t popc64(uint64_t x) { return (uint32_t)__popcll(x); }
+ISMCTS_DEV uint32_t ctz32(uint32_t x) { return (uint32_t)(__ffs((int)x) - 1); }
+ISMCTS_DEV uint32_t ctz64(uint64_t x) { return (uint32_t)(__ffsll((long long)x) - 1); }
+ISMCTS_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+ISMCTS_DEV uint64_t global_timer_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+// Fire-and-forget 64-bit reduction (SASS RED.E.ADD.64): no return value, no scoreboard wait.
+ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+#else
+ISMCTS_DEV uint32_t popc32(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+ISMCTS_DEV uint32_t popc64(uint64_t x) { return (uint32_t)__builtin_popcountll(x); }
+ISMCTS_DEV uint32_t ctz32(uint32_t x) { return (uint32_t)__builtin_ctz(x); }
+ISMCTS_DEV uint32_t ctz64(uint64_t x) { return (uint32_t)__builtin_ctzll(x); }
+ISMCTS_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+ISMCTS_DEV uint64_t global_timer_ns()
+{
+    return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+               std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
+ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v) { *p += v; }
+#endif
+
+// Index of the k-th (0-based) set bit of w; k < popc(w).
+ISMCTS_DEV uint32_t kth_bit32(uint32_t w, uint32_t k)
+{
+    uint32_t pos = 0, c;
+    c = popc32(w & 0xFFFFu); if (k >= c) { k -= c; pos = 16; w >>= 16; }
+    c = popc32(w & 0xFFu);   if (k >= c) { k -= c; pos += 8; w >>= 8; }
+    c = popc32(w & 0xFu);    if (k >= c) { k -= c; pos += 4; w >>= 4; }
+    c = popc32(w & 0x3u);    if (k >= c) { k -= c; pos += 2; w >>= 2; }
+    c = w & 1u;              if (k >= c) { pos += 1; }
+    return pos;
+}
+
+ISMCTS_DEV uint32_t kth_bit64(uint64_t m, uint32_t k)
+{
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    const uint32_t c = popc32(lo);
+    return (k >= c) ? 32u + kth_bit32(hi, k - c) : kth_bit32(lo, k);
+}
+
+} // namespace ismcts

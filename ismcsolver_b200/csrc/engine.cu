@@ -1,0 +1,387 @@
+// engine.cu — CUDA kernels (sm_100a) and the C ABI of include/ismcts_b200.h.
+//
+// Kernel map (reference symbols in SURVEY.md section 8a):
+//   so_root_parallel_kernel<Game>  a1,a3-a10,a12-a15  one thread = one SO-ISMCTS tree
+//   playout_kernel<Game>           a3-a6,a8           determinise + rollout only
+// No tensor cores are involved: the path has no dense contraction; it is
+// bound by SM instruction issue.
+#include "so_search.cuh"
+#include "kw_game.cuh"
+#include "mnk_game.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace ismcts {
+
+constexpr int kBlock = 128;
+
+template <class Game>
+__global__ void __launch_bounds__(kBlock) so_root_parallel_kernel(SearchParams P)
+{
+    extern __shared__ uint64_t scratch[];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid >= P.n_positions * P.trees) return;
+    so_tree_search<Game>(P, gtid, scratch + threadIdx.x, blockDim.x);
+}
+
+template <class Game>
+__global__ void __launch_bounds__(kBlock) playout_kernel(const typename Game::Root* roots, uint32_t n_positions,
+                                                         uint32_t per_position, uint64_t seed, uint32_t* out)
+{
+    extern __shared__ uint64_t scratch[];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid >= n_positions * per_position) return;
+    const uint32_t pos = gtid / per_position, j = gtid % per_position;
+    out[gtid] = playout_only<Game>(roots + pos, seed, pos, j, scratch + threadIdx.x, blockDim.x);
+}
+
+} // namespace ismcts
+
+using namespace ismcts;
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+
+struct ismcts_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+
+    // device buffers, grown on demand
+    void* pool = nullptr;        size_t pool_bytes = 0;
+    double* ln_table = nullptr;  uint32_t ln_count = 0;
+    void* roots = nullptr;       size_t roots_bytes = 0;
+    uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
+    uint32_t* play_out = nullptr; size_t play_bytes = 0;
+
+    // geometry of the last search (for ismcts_dump_tree)
+    uint32_t last_log2cap = 0;
+    uint32_t last_trees_launched = 0;
+    uint32_t last_game = 0;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(ismcts_ctx* ctx, int code, const std::string& what)
+{
+    if (ctx) ctx->error = what; else g_create_error = what;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                     \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(ctx, ISMCTS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+static int ensure(ismcts_ctx* ctx, T*& ptr, size_t& have, size_t need)
+{
+    if (need <= have) return ISMCTS_OK;
+    if (ptr) { CUDA_TRY(ctx, cudaFree(ptr)); ptr = nullptr; have = 0; }
+    CUDA_TRY(ctx, cudaMalloc((void**)&ptr, need));
+    have = need;
+    return ISMCTS_OK;
+}
+
+extern "C" {
+
+const char* ismcts_version(void) { return "ismcsolver_b200 0.1 (sm_100a)"; }
+
+size_t ismcts_state_size(uint32_t game)
+{
+    return game == ISMCTS_GAME_KW ? sizeof(ismcts_kw_state) : game == ISMCTS_GAME_MNK ? sizeof(ismcts_mnk_state) : 0;
+}
+
+uint32_t ismcts_move_stride(uint32_t game)
+{
+    return game == ISMCTS_GAME_KW ? KwGame::kMoveStride : game == ISMCTS_GAME_MNK ? MnkGame::kMoveStride : 0;
+}
+
+int ismcts_create(int device, ismcts_ctx** out)
+{
+    if (!out) return fail(nullptr, ISMCTS_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, ISMCTS_ERR_NO_DEVICE,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (this engine has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, ISMCTS_ERR_INVALID, "device index out of range");
+    ismcts_ctx* ctx = new (std::nothrow) ismcts_ctx;
+    if (!ctx) return fail(nullptr, ISMCTS_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, ISMCTS_ERR_NO_DEVICE, std::string("cannot initialise device: ") +
+                                                      cudaGetErrorString(cudaGetLastError()));
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return ISMCTS_OK;
+}
+
+void ismcts_destroy(ismcts_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->out); cudaFree(ctx->play_out);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* ismcts_last_error(const ismcts_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int ismcts_set_stream(ismcts_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return ISMCTS_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ISMCTS_OK;
+}
+
+uint64_t ismcts_launch_count(const ismcts_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ismcts_synchronize(ismcts_ctx* ctx)
+{
+    if (!ctx) return ISMCTS_ERR_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISMCTS_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------
+
+static size_t slot_bytes(uint32_t game)
+{
+    return game == ISMCTS_GAME_KW ? sizeof(SlotT<KwGame::Mask>) : sizeof(SlotT<MnkGame::Mask>);
+}
+
+static uint32_t ceil_log2(uint64_t x)
+{
+    uint32_t l = 0;
+    while (((uint64_t)1 << l) < x) ++l;
+    return l;
+}
+
+static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
+{
+    if (!ctx || !d) return ISMCTS_ERR_INVALID;
+    if (d->game != ISMCTS_GAME_KW && d->game != ISMCTS_GAME_MNK) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    if (d->solver != ISMCTS_SOLVER_SO) return fail(ctx, ISMCTS_ERR_INVALID, "solver kind not available in this build");
+    if (d->policy != ISMCTS_POLICY_UCB1) return fail(ctx, ISMCTS_ERR_INVALID, "policy not available in this build");
+    if (d->n_positions == 0 || d->trees == 0) return fail(ctx, ISMCTS_ERR_INVALID, "n_positions and trees must be > 0");
+    if ((uint64_t)d->n_positions * d->trees > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many trees");
+    if (d->trees_total < d->tree_base + d->trees) return fail(ctx, ISMCTS_ERR_INVALID, "trees_total < tree_base + trees");
+    if (d->iterations == 0 && d->time_ns == 0) return fail(ctx, ISMCTS_ERR_INVALID, "iterations or time_ns must be > 0");
+    return ISMCTS_OK;
+}
+
+// Builds ln(i), i < count, with the host libm (the oracle uses the same libm, so
+// UCB values agree bit for bit; CUDA's log() does not).
+static int ensure_ln_table(ismcts_ctx* ctx, uint32_t count)
+{
+    if (count <= ctx->ln_count) return ISMCTS_OK;
+    count = std::max<uint32_t>(count, 4096);
+    std::vector<double> host(count);
+    host[0] = 0.0;
+    for (uint32_t i = 1; i < count; ++i) host[i] = std::log((double)i);
+    if (ctx->ln_table) { CUDA_TRY(ctx, cudaFree(ctx->ln_table)); ctx->ln_table = nullptr; ctx->ln_count = 0; }
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->ln_table, (size_t)count * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->ln_table, host.data(), (size_t)count * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->ln_count = count;
+    return ISMCTS_OK;
+}
+
+template <class Game>
+static int launch_so(ismcts_ctx* ctx, const SearchParams& P, uint32_t n_threads)
+{
+    const uint32_t grid = (n_threads + kBlock - 1) / kBlock;
+    const size_t smem = (size_t)Game::kHandWords * sizeof(uint64_t) * kBlock;
+    so_root_parallel_kernel<Game><<<grid, kBlock, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return ISMCTS_OK;
+}
+
+extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d, const void* d_roots,
+                                    uint64_t* d_visits, uint64_t* d_score2, uint64_t* d_avail, uint64_t* d_iters)
+{
+    int rc = validate(ctx, d);
+    if (rc) return rc;
+    if (!d_roots || !d_visits || !d_score2 || !d_avail || !d_iters) return fail(ctx, ISMCTS_ERR_INVALID, "null device pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+    const uint32_t n_threads = d->n_positions * d->trees;
+    const uint32_t stride = ismcts_move_stride(d->game);
+
+    // nodes per tree: one per iteration plus the root
+    uint64_t max_it;
+    uint32_t log2cap;
+    if (d->iterations > 0) {
+        max_it = d->iterations / d->trees_total + 1;
+        log2cap = std::max<uint32_t>(4, ceil_log2(2 * (max_it + 1)));
+        if (log2cap > kMaxSlotsLog2) return fail(ctx, ISMCTS_ERR_CAPACITY, "too many iterations per tree for the node pool");
+    } else {
+        // time mode: the iteration count is unknown; give every tree an equal share of the free memory
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = (free_b + ctx->pool_bytes) / 2;
+        log2cap = 4;
+        while (log2cap < 21 && ((size_t)n_threads << (log2cap + 1)) * slot_bytes(d->game) <= budget) ++log2cap;
+        max_it = ((uint64_t)1 << (log2cap - 1)) - 1;
+    }
+    const size_t pool_need = ((size_t)n_threads << log2cap) * slot_bytes(d->game);
+    {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        if (pool_need > ctx->pool_bytes && pool_need > free_b + ctx->pool_bytes)
+            return fail(ctx, ISMCTS_ERR_CAPACITY, "node pool does not fit device memory: need " + std::to_string(pool_need) + " bytes");
+    }
+    rc = ensure(ctx, ctx->pool, ctx->pool_bytes, pool_need);
+    if (rc) return rc;
+    rc = ensure_ln_table(ctx, (uint32_t)std::min<uint64_t>(max_it + 3, 0x7FFFFFFFull));
+    if (rc) return rc;
+
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, pool_need, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_visits, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_score2, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
+
+    SearchParams P;
+    P.roots = d_roots;
+    P.n_positions = d->n_positions; P.trees = d->trees; P.trees_total = d->trees_total;
+    P.tree_base = d->tree_base; P.pos_base = d->pos_base;
+    P.iterations = d->iterations; P.time_ns = d->time_ns; P.seed = d->seed;
+    P.exploration = d->exploration < 0.0 ? 0.0 : d->exploration; // UCB1 ctor clamps, ucb1.h:65-67
+    P.pool = ctx->pool; P.log2cap = log2cap;
+    P.max_nodes = (uint32_t)std::min<uint64_t>(((uint64_t)1 << (log2cap - 1)), ctx->ln_count - 2);
+    P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
+    P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
+
+    ctx->last_log2cap = log2cap; ctx->last_trees_launched = n_threads; ctx->last_game = d->game;
+
+    if (d->game == ISMCTS_GAME_KW) return launch_so<KwGame>(ctx, P, n_threads);
+    return launch_so<MnkGame>(ctx, P, n_threads);
+}
+
+template <class Mask>
+static int dump_tree_t(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count)
+{
+    using Slot = SlotT<Mask>;
+    const size_t cap = (size_t)1 << ctx->last_log2cap;
+    std::vector<Slot> table(cap);
+    CUDA_TRY(ctx, cudaMemcpy(table.data(), (const Slot*)ctx->pool + (size_t)dump_index * cap, cap * sizeof(Slot),
+                             cudaMemcpyDeviceToHost));
+    // slots -> creation order
+    uint32_t n = 0;
+    for (const Slot& s : table) if (s.key != 0) ++n;
+    *count = n;
+    if (n > capacity) return fail(ctx, ISMCTS_ERR_CAPACITY, "dump buffer too small");
+    for (size_t i = 0; i < cap; ++i) {
+        const Slot& s = table[i];
+        if (s.key == 0) continue;
+        if (s.created >= n) return fail(ctx, ISMCTS_ERR_CUDA, "corrupt node pool");
+        ismcts_node_rec& r = nodes[s.created];
+        if (s.key == kRootKey) { r.parent = 0; r.move = 0; }
+        else { r.parent = table[slot_parent_of(s.key)].created; r.move = slot_move_of(s.key); }
+        r.player = s.player; r.visits = s.visits; r.score2 = s.score2; r.avail = s.avail;
+        r.score = 0.5 * (double)s.score2; r.prob = 1.0;
+    }
+    return ISMCTS_OK;
+}
+
+extern "C" int ismcts_dump_tree(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes, uint32_t capacity,
+                                uint32_t* count)
+{
+    if (!ctx || !nodes || !count) return ISMCTS_ERR_INVALID;
+    if (dump_index >= ctx->last_trees_launched) return fail(ctx, ISMCTS_ERR_INVALID, "dump index out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->last_game == ISMCTS_GAME_KW) return dump_tree_t<KwGame::Mask>(ctx, dump_index, nodes, capacity, count);
+    return dump_tree_t<MnkGame::Mask>(ctx, dump_index, nodes, capacity, count);
+}
+
+extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const void* roots, ismcts_search_out* out)
+{
+    int rc = validate(ctx, d);
+    if (rc) return rc;
+    if (!roots || !out || !out->visits) return fail(ctx, ISMCTS_ERR_INVALID, "null host pointer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t stride = ismcts_move_stride(d->game);
+    const size_t root_bytes = (size_t)d->n_positions * ismcts_state_size(d->game);
+    const size_t per_arr = (size_t)d->n_positions * stride;
+    const size_t n_trees = (size_t)d->n_positions * d->trees;
+    rc = ensure(ctx, ctx->roots, ctx->roots_bytes, root_bytes);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->out, ctx->out_bytes, (3 * per_arr + n_trees) * sizeof(uint64_t));
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->roots, roots, root_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t* dv = ctx->out; uint64_t* ds = dv + per_arr; uint64_t* da = ds + per_arr; uint64_t* di = da + per_arr;
+    rc = ismcts_search_device(ctx, d, ctx->roots, dv, ds, da, di);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->visits, dv, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->score2) CUDA_TRY(ctx, cudaMemcpyAsync(out->score2, ds, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->avail) CUDA_TRY(ctx, cudaMemcpyAsync(out->avail, da, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->iterations_done) CUDA_TRY(ctx, cudaMemcpyAsync(out->iterations_done, di, n_trees * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out->best_move) {
+        // RootParallel::bestMove, execution.h:209-216: first maximum in ascending move order
+        for (uint32_t p = 0; p < d->n_positions; ++p) {
+            uint32_t best = 0xFFFFFFFFu; uint64_t best_v = 0;
+            for (uint32_t m = 0; m < stride; ++m)
+                if (out->visits[(size_t)p * stride + m] > best_v) { best_v = out->visits[(size_t)p * stride + m]; best = m; }
+            out->best_move[p] = best;
+        }
+    }
+    out->dump_count = 0;
+    if (d->dump_tree != 0xFFFFFFFFu && out->dump_nodes)
+        return ismcts_dump_tree(ctx, d->dump_tree, out->dump_nodes, out->dump_capacity, &out->dump_count);
+    return ISMCTS_OK;
+}
+
+extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots, uint32_t n_positions,
+                               uint32_t per_position, uint64_t seed, uint32_t* out_result)
+{
+    if (!ctx || !roots || !out_result || n_positions == 0 || per_position == 0) return ISMCTS_ERR_INVALID;
+    if (game != ISMCTS_GAME_KW && game != ISMCTS_GAME_MNK) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t root_bytes = (size_t)n_positions * ismcts_state_size(game);
+    const size_t n = (size_t)n_positions * per_position;
+    int rc = ensure(ctx, ctx->roots, ctx->roots_bytes, root_bytes);
+    if (rc) return rc;
+    rc = ensure(ctx, ctx->play_out, ctx->play_bytes, n * sizeof(uint32_t));
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->roots, roots, root_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t grid = (uint32_t)((n + kBlock - 1) / kBlock);
+    if (game == ISMCTS_GAME_KW) {
+        const size_t smem = (size_t)KwGame::kHandWords * sizeof(uint64_t) * kBlock;
+        playout_kernel<KwGame><<<grid, kBlock, smem, ctx->stream>>>((const ismcts_kw_state*)ctx->roots, n_positions, per_position, seed, ctx->play_out);
+    } else {
+        const size_t smem = (size_t)MnkGame::kHandWords * sizeof(uint64_t) * kBlock;
+        playout_kernel<MnkGame><<<grid, kBlock, smem, ctx->stream>>>((const ismcts_mnk_state*)ctx->roots, n_positions, per_position, seed, ctx->play_out);
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_result, ctx->play_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ISMCTS_OK;
+}

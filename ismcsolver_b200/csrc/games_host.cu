@@ -1,0 +1,165 @@
+// games_host.cu — host game helpers of the C ABI (include/ismcts_b200.h).
+//
+// The reference's games are host objects that callers construct and advance
+// between searches (KnockoutWhist / MnkGame in test/common, driven by
+// test/benchmark.cpp:73-89).  These helpers do the same on the POD position
+// records, with the SAME rule code the kernels run (kw_game.cuh, mnk_game.cuh
+// are __host__ __device__).  They contain no search: the search has no host path.
+#include "kw_game.cuh"
+#include "mnk_game.cuh"
+
+#include <cstring>
+
+using namespace ismcts;
+
+namespace {
+
+// Streams of the position generators (never used by a search: tree ids of a
+// search are < 2^31).
+constexpr uint32_t kDealTree = 0xFFFFFFFFu, kDealIteration = 0xFFFFFFFFu;
+constexpr uint32_t kApplyTree = 0xFFFFFFFEu;
+
+void kw_store(const KwGame& g, const uint64_t* hands, uint64_t unknown, ismcts_kw_state* s)
+{
+    for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) s->hands[p] = hands[p];
+    s->unknown = unknown;
+    s->player = (uint8_t)g.player; s->dealer = (uint8_t)g.dealer; s->trump = (uint8_t)g.trump;
+    s->tricks_left = (uint8_t)g.tricks_left; s->request_trump = (uint8_t)g.request_trump;
+    s->alive_mask = (uint8_t)g.alive;
+    s->trick_len = (uint8_t)g.trick_len;
+    for (uint32_t p = 0; p < 8; ++p) s->tricks_taken[p] = p < 7 ? (uint8_t)((g.tricks >> (4 * p)) & 15u) : 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_kw_state* out)
+{
+    if (!out) return ISMCTS_ERR_INVALID;
+    // KnockoutWhist::KnockoutWhist, knockoutwhist.cpp:36-54 (player count clamped to 2..7, :38)
+    const uint32_t np = num_players < 2 ? 2 : num_players > 7 ? 7 : num_players;
+    std::memset(out, 0, sizeof *out);
+    out->num_players = (uint8_t)np;
+    uint64_t hands[ISMCTS_KW_MAX_PLAYERS] = {0};
+    KwGame g;
+    g.bind(hands, 1);
+    ismcts_kw_state blank;
+    std::memset(&blank, 0, sizeof blank);
+    blank.num_players = (uint8_t)np; blank.alive_mask = (uint8_t)((1u << np) - 1u);
+    blank.tricks_left = 7; blank.dealer = (uint8_t)(np - 1);
+    g.load(&blank);
+    Philox rng;
+    rng.init(seed, stream, kDealTree);
+    rng.begin_iteration(kDealIteration);
+    g.start_deal();
+    while (g.chance_pending()) {
+        const KwGame::Mask c = g.choices();
+        g.step(c.kth(rng.below(c.count())));
+    }
+    // one of the remaining cards is turned up for trumps and leaves the unknown set (:50-53)
+    uint64_t unknown = g.pool;
+    const uint32_t up = kth_bit64(unknown, rng.below(popc64(unknown)));
+    unknown &= ~((uint64_t)1 << up);
+    g.trump = up / 13u;
+    kw_store(g, hands, unknown, out);
+    return ISMCTS_OK;
+}
+
+uint64_t ismcts_kw_legal(const ismcts_kw_state* s)
+{
+    if (!s) return 0;
+    uint64_t hands[ISMCTS_KW_MAX_PLAYERS];
+    KwGame g;
+    g.bind(hands, 1);
+    g.load(s);
+    return g.legal().w;
+}
+
+int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t stream, uint32_t* draw_counter)
+{
+    if (!s) return ISMCTS_ERR_INVALID;
+    if (move >= ISMCTS_KW_CARDS) return ISMCTS_ERR_ILLEGAL_MOVE;
+    uint64_t hands[ISMCTS_KW_MAX_PLAYERS];
+    KwGame g;
+    g.bind(hands, 1);
+    g.load(s);
+    // doMove accepts any card while trumps are requested (knockoutwhist.cpp:97-102); otherwise
+    // the card must be in the mover's hand or std::out_of_range is thrown (:105-109)
+    const bool play = !g.request_trump;
+    if (play && !((hands[g.player] >> move) & 1u)) return ISMCTS_ERR_ILLEGAL_MOVE;
+    const uint32_t mover = g.player;
+    Philox rng;
+    rng.init(seed, stream, kApplyTree);
+    rng.begin_iteration(0);
+    rng.seek(draw_counter ? *draw_counter : 0);
+    g.step(move);
+    uint64_t unknown = s->unknown;
+    bool dealt = false;
+    while (g.chance_pending()) {
+        const KwGame::Mask c = g.choices();
+        g.step(c.kth(rng.below(c.count())));
+        dealt = true;
+    }
+    if (dealt) unknown = g.pool; // deal, :138-152: the undealt rest of the deck is unknown to everyone
+    if (draw_counter) *draw_counter = rng.d;
+    // the cards of the trick in progress (m_currentTrick)
+    if (play) {
+        if (g.trick_len == 0) {
+            std::memset(s->trick_player, 0, sizeof s->trick_player);
+            std::memset(s->trick_card, 0, sizeof s->trick_card);
+        } else {
+            s->trick_player[g.trick_len - 1] = (uint8_t)mover;
+            s->trick_card[g.trick_len - 1] = (uint8_t)move;
+        }
+    }
+    kw_store(g, hands, unknown, s);
+    return ISMCTS_OK;
+}
+
+int ismcts_kw_result2(const ismcts_kw_state* s, uint32_t player)
+{
+    if (!s || s->alive_mask == 0) return 0;
+    return player == ctz32(s->alive_mask) ? 2 : 0; // getResult, knockoutwhist.cpp:117-120
+}
+
+int ismcts_mnk_init(uint32_t m, uint32_t n, uint32_t k, ismcts_mnk_state* out)
+{
+    if (!out || m == 0 || n == 0 || m * n > ISMCTS_MNK_MAX_CELLS || m > 255 || n > 255 || k > 255) return ISMCTS_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->m = (uint8_t)m; out->n = (uint8_t)n; out->k = (uint8_t)k; out->player = 0; out->result2 = -1;
+    return ISMCTS_OK;
+}
+
+void ismcts_mnk_legal(const ismcts_mnk_state* s, uint64_t legal[4])
+{
+    uint64_t stones[8];
+    MnkGame g;
+    g.bind(stones, 1);
+    g.load(s);
+    const MnkGame::Mask l = g.legal();
+    for (int i = 0; i < 4; ++i) legal[i] = l.w[i];
+}
+
+int ismcts_mnk_apply(ismcts_mnk_state* s, uint32_t move)
+{
+    if (!s) return ISMCTS_ERR_INVALID;
+    uint64_t stones[8];
+    MnkGame g;
+    g.bind(stones, 1);
+    g.load(s);
+    // mnkgame.cpp:41-43: the move must be one of the remaining cells
+    if (move >= (uint32_t)s->m * s->n || g.occupied_by(0, move) || g.occupied_by(1, move)) return ISMCTS_ERR_ILLEGAL_MOVE;
+    g.step(move);
+    for (uint32_t i = 0; i < 8; ++i) s->stones[i >> 2][i & 3] = stones[i];
+    s->player = (uint8_t)g.player; s->result2 = (int8_t)g.res2;
+    return ISMCTS_OK;
+}
+
+int ismcts_mnk_result2(const ismcts_mnk_state* s, uint32_t player)
+{
+    if (!s) return 0;
+    return player == 0 ? s->result2 : 2 - s->result2; // getResult, mnkgame.cpp:56-59
+}
+
+} // extern "C"

@@ -1,0 +1,165 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle (bit-exact).
+
+The oracle (oracle/oracle.c) restates the reference's algorithm with different data structures
+(membership arrays and child lists instead of bit masks and a hash pool) and is driven by the same
+Philox streams, so every integer the search produces must agree.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from ismcsolver_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("parent", "move", "player", "visits", "score2", "avail")
+
+
+def _okw(s):
+    return O.KwState.from_buffer_copy(bytes(s))
+
+
+def _omnk(s):
+    return O.MnkState.from_buffer_copy(bytes(s))
+
+
+def _midgame(seed, stream, plies):
+    """Position stream: `plies` uniformly random legal moves from deal `stream`."""
+    rng = np.random.default_rng(seed * 1000003 + stream)
+    s = capi.kw_deal(seed, stream, 4)
+    ctr = [0]
+    for _ in range(plies):
+        mask = capi.kw_legal_mask(s)
+        legal = [c for c in range(52) if mask >> c & 1]
+        if not legal:
+            break
+        assert capi.kw_apply(s, int(rng.choice(legal)), seed, stream, ctr) == 0
+    return s
+
+
+def test_playouts_kw_bit_exact(engine):
+    """Determinise + rollout outcomes (winner, plies, draws) for 20k (position, iteration) pairs."""
+    n_pos, per = 40, 512
+    states = [_midgame(11, i, (i * 7) % 50) for i in range(n_pos)]
+    states = [s for s in states if capi.kw_legal_mask(s)]
+    got = engine.playouts(capi.GAME_KW, capi.pack_states(states), len(states), per, seed=4242)
+    for i, s in enumerate(states):
+        os_ = _okw(s)
+        want = np.array([O.playout(O.GAME_KW, os_, 4242, i, 0, j) for j in range(per)], dtype=np.uint32)
+        assert (got[i] == want).all(), f"position {i}"
+    # every playout ends with exactly one survivor (getResult sums to 1)
+    assert ((got & 0xFF) < 4).all()
+
+
+@pytest.mark.parametrize("mnk", [(3, 3, 3), (5, 4, 3), (9, 9, 5), (15, 15, 5)])
+def test_playouts_mnk_bit_exact(engine, mnk):
+    s = capi.mnk_init(*mnk)
+    got = engine.playouts(capi.GAME_MNK, capi.pack_states([s]), 1, 1024, seed=9)
+    want = np.array([O.playout(O.GAME_MNK, _omnk(s), 9, 0, 0, j) for j in range(1024)], dtype=np.uint32)
+    assert (got[0] == want).all()
+
+
+def test_so_tree_kw_every_node_bit_exact(engine):
+    """visits / score / available / parent / move / player of EVERY node of several trees."""
+    n_pos, trees, per_tree = 3, 4, 1500
+    states = [_midgame(5, i, i * 9) for i in range(n_pos)]
+    desc = engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=trees * per_tree, seed=77)
+    res = engine.search(desc, capi.pack_states(states))
+    assert (res["iterations_done"] == per_tree).all()
+    for i, s in enumerate(states):
+        for t in range(trees):
+            got = engine.dump_tree(i * trees + t, per_tree + 2)
+            want = O.so_search(O.GAME_KW, _okw(s), per_tree, seed=77, pos=i, tree=t)
+            assert len(got) == len(want)
+            for f in FIELDS:
+                assert (got[f] == want[f]).all(), (i, t, f)
+
+
+@pytest.mark.parametrize("mnk,iters", [((3, 3, 3), 4000), ((6, 5, 4), 2000), ((15, 15, 5), 1000)])
+def test_so_tree_mnk_every_node_bit_exact(engine, mnk, iters):
+    s = capi.mnk_init(*mnk)
+    desc = engine.make_desc(capi.GAME_MNK, 1, 2, iterations=2 * iters, seed=3)
+    engine.search(desc, capi.pack_states([s]))
+    for t in range(2):
+        got = engine.dump_tree(t, iters + 2)
+        want = O.so_search(O.GAME_MNK, _omnk(s), iters, seed=3, pos=0, tree=t)
+        assert len(got) == len(want)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), (t, f)
+
+
+def test_root_parallel_sums_and_best_move(engine):
+    """RootParallel::compileVisitCounts + bestMove (execution.h:208-231) over 64 trees, uneven split."""
+    n_pos, trees, iterations = 6, 64, 64 * 100 + 17
+    states = [_midgame(21, i, i * 5) for i in range(n_pos)]
+    desc = engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=123, pos_base=1000)
+    res = engine.search(desc, capi.pack_states(states))
+    assert int(res["iterations_done"].sum()) == n_pos * iterations
+    for i, s in enumerate(states):
+        v, sc, av, best = O.root_parallel(O.GAME_KW, _okw(s), iterations, trees, seed=123, pos=1000 + i)
+        assert (res["visits"][i] == v).all()
+        assert (res["score2"][i] == sc).all()
+        assert (res["avail"][i] == av).all()
+        assert int(res["best_move"][i]) == best
+        assert int(res["visits"][i].sum()) == iterations  # every iteration passes through one root child
+        assert capi.kw_legal_mask(s) >> best & 1           # solvertest.cpp:109-111: a valid move
+
+
+def test_tree_sharding_is_invariant(engine):
+    """Splitting the tree range over several calls (as over several GPUs) gives identical sums."""
+    s = capi.kw_deal(8, 0, 4)
+    roots = capi.pack_states([s])
+    total_trees, iterations = 32, 32 * 64 + 5
+    whole = engine.search(engine.make_desc(capi.GAME_KW, 1, total_trees, iterations=iterations, seed=9), roots)
+    acc = {k: np.zeros_like(whole[k]) for k in ("visits", "score2", "avail")}
+    for base in range(0, total_trees, 8):
+        part = engine.search(engine.make_desc(capi.GAME_KW, 1, 8, iterations=iterations, seed=9,
+                                              trees_total=total_trees, tree_base=base), roots)
+        for k in acc:
+            acc[k] += part[k]
+    for k in acc:
+        assert (acc[k] == whole[k]).all()
+
+
+def test_p1_draw_or_lose(engine):
+    """solvertest.cpp:45-60,131-138: from P1DrawOrLose every solver must play move 2 with 16 iterations."""
+    s = capi.mnk_init(3, 3, 3)
+    for mv in (4, 1, 5, 3, 6, 8, 7):  # X: 4,5,6,7  O: 1,3,8 -> board [[-,O,-],[O,X,X],[X,X,O]]
+        assert capi.mnk_apply(s, mv) == 0
+    assert capi.mnk_legal(s) == [0, 2] and s.player == 1
+    for seed in range(20):
+        res = engine.search(engine.make_desc(capi.GAME_MNK, 1, 1, iterations=16, seed=seed), capi.pack_states([s]))
+        assert int(res["best_move"][0]) == 2
+
+
+def test_terminal_root_and_errors(engine):
+    # a finished game has no legal move: best_move is the sentinel and no iteration adds a node
+    s = capi.mnk_init(3, 3, 3)
+    for mv in (0, 3, 1, 4, 2):
+        assert capi.mnk_apply(s, mv) == 0
+    assert capi.mnk_legal(s) == []
+    res = engine.search(engine.make_desc(capi.GAME_MNK, 1, 2, iterations=10, seed=1), capi.pack_states([s]))
+    assert int(res["best_move"][0]) == 0xFFFFFFFF and int(res["visits"].sum()) == 0
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(7, 1, 1, iterations=10), capi.pack_states([s]))
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(capi.GAME_MNK, 1, 0, iterations=10), capi.pack_states([s]))
+
+
+def test_time_mode_runs_and_replays(engine):
+    """Time-limited search (execution.h:188, utility.h:51-60): iterations done are reported per tree
+    and the oracle replays exactly those counts."""
+    s = capi.kw_deal(3, 1, 4)
+    trees = 8
+    res = engine.search(engine.make_desc(capi.GAME_KW, 1, trees, time_ns=5_000_000, seed=55), capi.pack_states([s]))
+    done = res["iterations_done"][0]
+    assert (done > 0).all()
+    v = np.zeros(64, dtype=np.uint64)
+    for t in range(trees):
+        nodes = O.so_search(O.GAME_KW, _okw(s), int(done[t]), seed=55, pos=0, tree=t)
+        for nrec in nodes[1:]:
+            if nrec["parent"] == 0:
+                v[nrec["move"]] += nrec["visits"]
+    assert (v == res["visits"][0]).all()
