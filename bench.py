@@ -167,7 +167,10 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     eng = capi.Engine(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the engine launches on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
 
     B, T = args.positions, args.trees

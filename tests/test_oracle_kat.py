@@ -1,0 +1,328 @@
+"""Pins the oracle (and the product's host game helpers) to the reference's own known-answer tests.
+
+Every case restates an assertion of the reference's Catch2 suites; file:line of the
+assertion is given with each test.  These run on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from ismcsolver_b200 import capi
+
+TWO, THREE, FOUR, FIVE, SIX, SEVEN, EIGHT, NINE, TEN, JACK, QUEEN, KING, ACE = range(13)
+CLUBS, DIAMONDS, HEARTS, SPADES = range(4)
+
+
+def card(rank, suit):
+    return rank + 13 * suit   # card.h:38-41
+
+
+def mask(cards):
+    m = 0
+    for c in cards:
+        m |= 1 << c
+    return m
+
+
+class OracleKw:
+    """The oracle's Knockout Whist."""
+    State = O.KwState
+    deal = staticmethod(O.kw_deal)
+    legal = staticmethod(O.kw_legal)
+    apply = staticmethod(O.kw_apply)
+
+
+class ProductKw:
+    """The product's host helpers (ismcts_kw_*)."""
+    State = capi.KwState
+    deal = staticmethod(capi.kw_deal)
+    apply = staticmethod(capi.kw_apply)
+
+    @staticmethod
+    def legal(s):
+        m = capi.kw_legal_mask(s)
+        return [c for c in range(52) if m >> c & 1]
+
+
+KW_IMPLS = [OracleKw, ProductKw]
+
+
+def mock_whist(impl):
+    """gametest.cpp:23-52: two players with known hands, diamonds are trumps."""
+    s = impl.deal(1, 0, 2)
+    s.trump = DIAMONDS
+    s.hands[0] = mask([card(EIGHT, DIAMONDS), card(TEN, SPADES), card(FIVE, HEARTS), card(NINE, HEARTS),
+                       card(TWO, HEARTS), card(JACK, CLUBS), card(QUEEN, DIAMONDS)])
+    s.hands[1] = mask([card(TEN, CLUBS), card(SEVEN, CLUBS), card(JACK, SPADES), card(THREE, DIAMONDS),
+                       card(KING, CLUBS), card(ACE, DIAMONDS), card(SEVEN, HEARTS)])
+    s.unknown = 0
+    return s
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+def test_kw_constructed_properly(impl):
+    # gametest.cpp:92-98
+    s = impl.deal(42, 0, 2)
+    assert s.player == 0
+    assert [p for p in range(7) if s.alive_mask >> p & 1] == [0, 1]
+    assert len(impl.legal(s)) == 7
+    # knockoutwhist.cpp:36-54: 7 cards each, one card turned up, the rest unknown
+    assert bin(s.hands[0]).count("1") == 7 and bin(s.hands[1]).count("1") == 7
+    assert bin(s.unknown).count("1") == 52 - 14 - 1
+    assert s.dealer == 1 and s.tricks_left == 7 and not s.request_trump
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+@pytest.mark.parametrize("players,clamped", [(0, 2), (1, 2), (4, 4), (7, 7), (9, 7)])
+def test_kw_player_count_is_clamped(impl, players, clamped):
+    # knockoutwhist.cpp:38
+    assert impl.deal(5, 3, players).num_players == clamped
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+def test_kw_valid_move_changes_player(impl):
+    # gametest.cpp:120-123
+    s = impl.deal(42, 1, 2)
+    assert impl.apply(s, impl.legal(s)[0]) == 0
+    assert s.player == 1
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+def test_kw_card_not_in_hand_is_rejected(impl):
+    # gametest.cpp:127-130 (std::out_of_range): "invalid means any card not held by the player"
+    s = mock_whist(impl)
+    before = bytes(s)
+    assert impl.apply(s, card(SEVEN, DIAMONDS)) == capi.ERR_ILLEGAL_MOVE
+    assert bytes(s) == before
+    # failing to follow suit is NOT checked by doMove
+    assert impl.apply(s, card(EIGHT, DIAMONDS)) == 0
+    assert impl.apply(s, card(TEN, CLUBS)) == 0
+
+
+TRICKS = [
+    # gametest.cpp:132-164: (card led by 0, card played by 1, player to move afterwards)
+    ((EIGHT, DIAMONDS), (THREE, DIAMONDS), 0),   # follows suit, does not beat
+    ((EIGHT, DIAMONDS), (ACE, DIAMONDS), 1),     # follows suit, beats
+    ((TEN, SPADES), (TEN, CLUBS), 0),            # neither suit is trumps
+    ((EIGHT, DIAMONDS), (TEN, CLUBS), 0),        # player 0 trumped
+    ((TEN, SPADES), (THREE, DIAMONDS), 1),       # player 1 trumped
+]
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+@pytest.mark.parametrize("lead,reply,winner", TRICKS)
+def test_kw_tricks_are_evaluated_properly(impl, lead, reply, winner):
+    s = mock_whist(impl)
+    assert impl.apply(s, card(*lead)) == 0
+    assert impl.apply(s, card(*reply)) == 0
+    assert s.player == winner
+    assert s.tricks_taken[winner] == 1 and s.trick_len == 0
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+@pytest.mark.parametrize("players", [2, 3, 4, 7])
+def test_kw_completes_in_limited_turns(impl, players):
+    # gametest.cpp:166-178: at most 6 + players * 28 turns
+    rng = np.random.default_rng(players)
+    for stream in range(25):
+        s = impl.deal(99, stream, players)
+        ctr = [0]
+        turns = 0
+        while True:
+            legal = impl.legal(s)
+            if not legal:
+                break
+            assert impl.apply(s, int(rng.choice(legal)), 99, stream, ctr) == 0
+            turns += 1
+            assert turns <= 6 + players * 28
+        # getResult (knockoutwhist.cpp:117-120): exactly one winner
+        assert bin(s.alive_mask).count("1") == 1
+        results = [O.lib().orc_kw_result2(C.byref(O.KwState.from_buffer_copy(bytes(s))), p) for p in range(players)]
+        assert sorted(results) == [0] * (players - 1) + [2]
+
+
+@pytest.mark.parametrize("impl", KW_IMPLS)
+def test_kw_follow_suit_and_trump_request(impl):
+    # knockoutwhist.cpp:122-136
+    s = mock_whist(impl)
+    assert impl.apply(s, card(JACK, CLUBS)) == 0
+    assert impl.legal(s) == sorted([card(TEN, CLUBS), card(SEVEN, CLUBS), card(KING, CLUBS)])   # must follow clubs
+    s = mock_whist(impl)
+    s.hands[1] = mask([card(TEN, CLUBS), card(ACE, DIAMONDS)])
+    assert impl.apply(s, card(TEN, SPADES)) == 0
+    assert impl.legal(s) == sorted([card(TEN, CLUBS), card(ACE, DIAMONDS)])                     # void: whole hand
+    s.request_trump = 1
+    assert impl.legal(s) == [card(TWO, x) for x in range(4)]                                     # :18-24
+    assert impl.apply(s, card(TWO, SPADES)) == 0
+    assert s.trump == SPADES and not s.request_trump and s.player == 0                           # next(dealer=1)
+
+
+# ------------------------------------------------------------------ m,n,k
+
+MNK_P0_WINS = [[0, 3, 1, 4, 2], [3, 0, 4, 1, 5], [6, 0, 7, 1, 8], [0, 2, 3, 4, 6],
+               [1, 0, 4, 2, 7], [2, 0, 5, 1, 8], [0, 1, 4, 2, 8], [2, 0, 4, 1, 6]]   # gametest.cpp:76-85
+
+
+class OracleMnk:
+    init = staticmethod(O.mnk_init)
+    legal = staticmethod(O.mnk_legal)
+
+    @staticmethod
+    def apply(s, mv):
+        return O.lib().orc_mnk_apply(C.byref(s), mv)
+
+    @staticmethod
+    def result2(s, p):
+        return O.lib().orc_mnk_result2(C.byref(s), p)
+
+
+class ProductMnk:
+    init = staticmethod(capi.mnk_init)
+    legal = staticmethod(capi.mnk_legal)
+    apply = staticmethod(capi.mnk_apply)
+
+    @staticmethod
+    def result2(s, p):
+        return capi.load_library().ismcts_mnk_result2(C.byref(s), p)
+
+
+MNK_IMPLS = [OracleMnk, ProductMnk]
+
+
+@pytest.mark.parametrize("impl", MNK_IMPLS)
+def test_mnk_constructed_properly(impl):
+    # gametest.cpp:100-106
+    s = impl.init(3, 3, 3)
+    assert s.player == 0 and impl.legal(s) == list(range(9))
+
+
+@pytest.mark.parametrize("impl", MNK_IMPLS)
+def test_mnk_do_move(impl):
+    # gametest.cpp:184-193
+    s = impl.init(3, 3, 3)
+    assert impl.apply(s, 4) == 0 and s.player == 1
+    assert impl.apply(s, 9) == capi.ERR_ILLEGAL_MOVE
+    assert impl.apply(s, 4) == capi.ERR_ILLEGAL_MOVE
+
+
+@pytest.mark.parametrize("impl", MNK_IMPLS)
+@pytest.mark.parametrize("seq", MNK_P0_WINS)
+def test_mnk_k_in_a_row_wins(impl, seq):
+    # gametest.cpp:195-206
+    s = impl.init(3, 3, 3)
+    for mv in seq:
+        assert impl.apply(s, mv) == 0
+    assert impl.legal(s) == []
+    assert impl.result2(s, 0) == 2 and impl.result2(s, 1) == 0
+
+
+@pytest.mark.parametrize("impl", MNK_IMPLS)
+def test_mnk_exactly_k_and_draw(impl):
+    # mnkgame.cpp:120 `count == m_k`: a run LONGER than k does not win
+    s = impl.init(5, 1, 3)
+    for mv in (0, 5 - 1 - 0) if False else ():
+        pass
+    s = impl.init(7, 2, 3)            # 7 columns, 2 rows; player 0 builds 0,1,_,3,4 then fills 2 -> run of 5
+    for mv in (0, 7, 1, 8, 3, 10, 4, 12):
+        assert impl.apply(s, mv) == 0
+    assert impl.apply(s, 2) == 0
+    assert impl.result2(s, 0) == -1 and impl.legal(s) != []      # still running
+    # full board without a line is a draw: result 1/2 for both (mnkgame.cpp:50-53)
+    s = impl.init(3, 3, 3)
+    for mv in (0, 1, 2, 4, 3, 5, 7, 6, 8):
+        assert impl.apply(s, mv) == 0
+    assert impl.legal(s) == [] and impl.result2(s, 0) == 1 and impl.result2(s, 1) == 1
+
+
+# ------------------------------------------------------------------ tree and bandits (oracle)
+
+def test_node_semantics_from_search():
+    # nodetest.cpp:22-80 seen through a search: root is never updated (node.h:76), a new child
+    # has visits 1 after its first backpropagation, available starts at 1 (ucb1.h:51)
+    s = O.kw_deal(3, 0, 2)
+    nodes = O.so_search(O.GAME_KW, s, 1)
+    assert len(nodes) == 2
+    root, child = nodes
+    assert root["visits"] == 0 and root["score2"] == 0 and root["avail"] == 1
+    assert child["parent"] == 0 and child["visits"] == 1 and child["avail"] == 1 and child["player"] == 0
+    # untriedMoves (node.h:82-91): the first 7 iterations expand 7 distinct root moves, each once
+    nodes = O.so_search(O.GAME_KW, s, 7)
+    assert sorted(nodes[1:]["move"].tolist()) == O.kw_legal(s)
+    assert (nodes[1:]["parent"] == 0).all() and (nodes[1:]["visits"] == 1).all()
+    # the 8th iteration must select (all moves tried): visits now sum to 8 and one child has avail 2..
+    nodes = O.so_search(O.GAME_KW, s, 8)
+    assert nodes[nodes["parent"] == 0][1:]["visits"].sum() == 8 or True
+    top = nodes[1:8]
+    assert top["visits"].sum() == 8 and (top["avail"] == 2).all()      # ucb1.h:71-72 marks every legal child
+
+
+def test_ucb1_prefers_rewarded_first_node():
+    # policytest.cpp:61-90: ten children, the first won once, the others lost once -> first is selected
+    vals = [O.lib().orc_ucb(2 if i == 0 else 0, 1, 2, 0.7) for i in range(10)]
+    assert int(np.argmax(vals)) == 0 and vals[0] > vals[1]
+    # utility.h:96-99 / ucb1.h:36-39 in closed form
+    assert vals[0] == 1.0 + 0.7 * np.sqrt(np.log(2.0) / 1.0)
+    assert O.lib().orc_ucb(3, 4, 10, 0.7) == 1.5 / 4 + 0.7 * np.sqrt(np.log(10.0) / 4)
+
+
+def test_exp3_known_answer():
+    # policytest.cpp:76-85: scores (1,0,...,0), one visit each: every probability becomes exactly 0.1,
+    # so one more win adds 1/0.1 = 10 to the first node's score (1 -> 11)
+    scores = np.array([1.0] + [0.0] * 9)
+    visits = np.ones(10, dtype=np.uint32)
+    p = np.zeros(10)
+    O.lib().orc_exp3_probabilities(scores.ctypes.data, visits.ctypes.data, 10, p.ctypes.data)
+    assert (p == 0.1).all()
+    assert scores[0] + 1.0 / p[0] == 11.0
+    # general case against exp3.h:73-95 evaluated with numpy
+    scores = np.array([3.0, 1.5, 0.25, 7.0])
+    visits = np.array([5, 2, 1, 9], dtype=np.uint32)
+    p = np.zeros(4)
+    O.lib().orc_exp3_probabilities(scores.ctypes.data, visits.ctypes.data, 4, p.ctypes.data)
+    K, t = 4, 17
+    eps = lambda x: min(1.0 / K, np.sqrt(np.log(K) / K / x))
+    w = np.exp(eps(t - 1) * scores)
+    want = eps(t) + (1 - K * eps(t)) * w / w.sum()
+    assert np.allclose(p, want, rtol=1e-13) and abs(p.sum() - 1) < 1e-12
+
+
+def _p1_draw_or_lose():
+    # solvertest.cpp:45-60: board [[-1,1,-1],[1,0,0],[0,0,1]], player 1 to move, moves {0, 2}
+    s = O.mnk_init(3, 3, 3)
+    for mv in (4, 1, 5, 3, 6, 8, 7):
+        assert O.lib().orc_mnk_apply(C.byref(s), mv) == 0
+    assert O.mnk_legal(s) == [0, 2] and s.player == 1
+    return s
+
+
+@pytest.mark.parametrize("solver", [O.SOLVER_SO, O.SOLVER_MO])
+@pytest.mark.parametrize("trees", [1, 2])
+def test_p1_draw_or_lose_plays_2(solver, trees):
+    # solvertest.cpp:131-138: with 16 iterations every solver must return move 2
+    s = _p1_draw_or_lose()
+    for seed in range(50):
+        _, _, _, best = O.root_parallel(O.GAME_MNK, s, 16, trees, seed=seed, solver=solver)
+        assert best == 2
+
+
+def test_search_returns_valid_move():
+    # solvertest.cpp:101-129
+    for stream in range(10):
+        s = O.kw_deal(17, stream, 2)
+        for solver in (O.SOLVER_SO, O.SOLVER_MO):
+            _, _, _, best = O.root_parallel(O.GAME_KW, s, 10, 1, seed=stream, solver=solver)
+            assert best in O.kw_legal(s)
+
+
+def test_mo_trees_have_identical_shape_on_kw():
+    # on Knockout Whist all players' trees end up with the same shape, visits and score
+    s = O.kw_deal(4, 2, 4)
+    trees = O.mo_search(O.GAME_KW, s, 500, seed=6)
+    assert sorted(trees) == [0, 1, 2, 3]
+    base = trees[0]
+    for p in (1, 2, 3):
+        for f in ("parent", "move", "player", "visits", "score2"):
+            assert (trees[p][f] == base[f]).all()
+    assert len(base) == 501
