@@ -1,0 +1,95 @@
+"""Device logic on the CPU: the kernels' per-thread search body (ismcsolver_b200/csrc/*.cuh), compiled
+as plain C++ by tests/emu, against the oracle — so that the bit masks, the hash node pool and the
+micro-step game loop are checked here, where there is no GPU.  The real kernels are compared with the
+oracle by the `-m gpu` tests; this build is test infrastructure and not part of the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+FIELDS = ("parent", "move", "player", "visits", "score2", "avail")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
+    E = C.CDLL(os.path.join(EMU_DIR, "libemu.so"))
+    E.emu_playout.restype = C.c_uint32
+    E.emu_playout.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
+    E.emu_so_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double,
+                                C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    return E
+
+
+def emu_search(E, game, root, iters, seed, pos, tree, exploration=0.7):
+    nodes = np.zeros(iters + 2, dtype=O.NODE_DTYPE)
+    n = C.c_uint32()
+    assert E.emu_so_search(game, C.byref(root), iters, seed, pos, tree, exploration, nodes.ctypes.data, iters + 2,
+                           C.byref(n)) == 0
+    return nodes[:n.value]
+
+
+@pytest.mark.parametrize("players", [2, 4, 7])
+def test_kw_playouts(emu, players):
+    for pos in range(12):
+        s = O.kw_deal(1234, pos, players)
+        for it in range(100):
+            assert O.playout(O.GAME_KW, s, 99, pos, 0, it) == emu.emu_playout(O.GAME_KW, C.byref(s), 99, pos, it)
+
+
+def test_kw_playouts_midgame(emu):
+    rng = np.random.default_rng(0)
+    for pos in range(30):
+        s = O.kw_deal(8, pos, 4)
+        ctr = [0]
+        for _ in range(int(rng.integers(0, 60))):
+            legal = O.kw_legal(s)
+            if not legal:
+                break
+            O.kw_apply(s, int(rng.choice(legal)), 8, pos, ctr)
+        if not O.kw_legal(s):
+            continue
+        for it in range(50):
+            assert O.playout(O.GAME_KW, s, 5, pos, 0, it) == emu.emu_playout(O.GAME_KW, C.byref(s), 5, pos, it)
+
+
+@pytest.mark.parametrize("mnk", [(3, 3, 3), (4, 7, 4), (15, 15, 5), (16, 16, 5)])
+def test_mnk_playouts(emu, mnk):
+    s = O.mnk_init(*mnk)
+    for it in range(150):
+        assert O.playout(O.GAME_MNK, s, 7, 0, 0, it) == emu.emu_playout(O.GAME_MNK, C.byref(s), 7, 0, it)
+
+
+@pytest.mark.parametrize("players,iters", [(2, 3000), (4, 3000), (7, 1500)])
+def test_kw_search_every_node(emu, players, iters):
+    for pos in range(3):
+        s = O.kw_deal(77, pos, players)
+        want = O.so_search(O.GAME_KW, s, iters, seed=5, pos=pos, tree=pos + 1)
+        got = emu_search(emu, O.GAME_KW, s, iters, 5, pos, pos + 1)
+        assert len(got) == len(want)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), f
+
+
+@pytest.mark.parametrize("mnk,iters", [((3, 3, 3), 5000), ((7, 7, 4), 3000), ((15, 15, 5), 1500)])
+def test_mnk_search_every_node(emu, mnk, iters):
+    s = O.mnk_init(*mnk)
+    want = O.so_search(O.GAME_MNK, s, iters, seed=5)
+    got = emu_search(emu, O.GAME_MNK, s, iters, 5, 0, 0)
+    assert len(got) == len(want)
+    for f in FIELDS:
+        assert (got[f] == want[f]).all(), f
+
+
+def test_exploration_constant_is_used(emu):
+    s = O.kw_deal(1, 1, 4)
+    for c in (0.0, 0.35, 2.0):
+        want = O.so_search(O.GAME_KW, s, 1500, seed=2, exploration=c)
+        got = emu_search(emu, O.GAME_KW, s, 1500, 2, 0, 0, exploration=c)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), (c, f)
