@@ -37,6 +37,9 @@ ISMCTS_DEV uint64_t global_timer_ns()
     return t;
 }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+// Warp votes over all 32 lanes (every lane of a warp runs the search loop, see lane_search.cuh).
+ISMCTS_DEV uint32_t warp_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+ISMCTS_DEV bool warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 // Fire-and-forget 64-bit reduction (SASS RED.E.ADD.64): no return value, no scoreboard wait.
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v)
 {
@@ -53,6 +56,8 @@ ISMCTS_DEV uint64_t global_timer_ns()
     return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+ISMCTS_DEV uint32_t warp_ballot(bool p) { return p ? 1u : 0u; } // host build: a "warp" of one lane
+ISMCTS_DEV bool warp_any(bool p) { return p; }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 #endif

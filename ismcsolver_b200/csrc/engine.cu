@@ -5,7 +5,7 @@
 //   playout_kernel<Game>           a3-a6,a8           determinise + rollout only
 // No tensor cores are involved: the path has no dense contraction; it is
 // bound by SM instruction issue.
-#include "so_search.cuh"
+#include "lane_search.cuh"
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
 
@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -23,24 +24,34 @@ namespace ismcts {
 
 constexpr int kBlock = 128;
 
+// Shared memory of a block: the per-thread game scratch (hands / stones, one
+// 8-byte column per thread) followed by the per-thread Philox rings (one 4-byte
+// column per thread): column layouts are bank-conflict free.
 template <class Game>
-__global__ void __launch_bounds__(kBlock) so_root_parallel_kernel(SearchParams P)
+constexpr size_t block_smem()
 {
-    extern __shared__ uint64_t scratch[];
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gtid >= P.n_positions * P.trees) return;
-    so_tree_search<Game>(P, gtid, scratch + threadIdx.x, blockDim.x);
+    return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + LaneRng::kRingWords * sizeof(uint32_t));
 }
 
 template <class Game>
-__global__ void __launch_bounds__(kBlock) playout_kernel(const typename Game::Root* roots, uint32_t n_positions,
-                                                         uint32_t per_position, uint64_t seed, uint32_t* out)
+__global__ void __launch_bounds__(kBlock) so_root_parallel_kernel(SearchParams P)
 {
-    extern __shared__ uint64_t scratch[];
+    extern __shared__ uint64_t smem[];
+    uint64_t* scratch = smem + threadIdx.x;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
+    uint32_t path[Game::kMaxDepth];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gtid >= n_positions * per_position) return;
-    const uint32_t pos = gtid / per_position, j = gtid % per_position;
-    out[gtid] = playout_only<Game>(roots + pos, seed, pos, j, scratch + threadIdx.x, blockDim.x);
+    lane_tree_search<Game>(P, gtid, gtid < P.n_positions * P.trees, scratch, kBlock, ring, kBlock, path);
+}
+
+template <class Game>
+__global__ void __launch_bounds__(kBlock) playout_kernel(SearchParams P, uint32_t per_position)
+{
+    extern __shared__ uint64_t smem[];
+    uint64_t* scratch = smem + threadIdx.x;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    lane_playout<Game>(P, gtid, gtid < P.n_positions * per_position, per_position, scratch, kBlock, ring, kBlock);
 }
 
 } // namespace ismcts
@@ -64,6 +75,9 @@ struct ismcts_ctx {
     void* roots = nullptr;       size_t roots_bytes = 0;
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
+
+    // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD override
+    uint32_t tree_thresh = 8, tree_period = 8;
 
     // geometry of the last search (for ismcts_dump_tree)
     uint32_t last_log2cap = 0;
@@ -131,6 +145,8 @@ int ismcts_create(int device, ismcts_ctx** out)
                                                       cudaGetErrorString(cudaGetLastError()));
     }
     ctx->stream = ctx->own_stream;
+    if (const char* e = std::getenv("ISMCTS_TREE_THRESH")) ctx->tree_thresh = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("ISMCTS_TREE_PERIOD")) ctx->tree_period = std::max(1, std::atoi(e));
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -215,8 +231,7 @@ template <class Game>
 static int launch_so(ismcts_ctx* ctx, const SearchParams& P, uint32_t n_threads)
 {
     const uint32_t grid = (n_threads + kBlock - 1) / kBlock;
-    const size_t smem = (size_t)Game::kHandWords * sizeof(uint64_t) * kBlock;
-    so_root_parallel_kernel<Game><<<grid, kBlock, smem, ctx->stream>>>(P);
+    so_root_parallel_kernel<Game><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return ISMCTS_OK;
@@ -276,6 +291,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.max_nodes = (uint32_t)std::min<uint64_t>(((uint64_t)1 << (log2cap - 1)), ctx->ln_count - 2);
     P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
+    P.playout_out = nullptr; P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
 
     ctx->last_log2cap = log2cap; ctx->last_trees_launched = n_threads; ctx->last_game = d->game;
 
@@ -372,13 +388,12 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->roots, roots, root_bytes, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t grid = (uint32_t)((n + kBlock - 1) / kBlock);
-    if (game == ISMCTS_GAME_KW) {
-        const size_t smem = (size_t)KwGame::kHandWords * sizeof(uint64_t) * kBlock;
-        playout_kernel<KwGame><<<grid, kBlock, smem, ctx->stream>>>((const ismcts_kw_state*)ctx->roots, n_positions, per_position, seed, ctx->play_out);
-    } else {
-        const size_t smem = (size_t)MnkGame::kHandWords * sizeof(uint64_t) * kBlock;
-        playout_kernel<MnkGame><<<grid, kBlock, smem, ctx->stream>>>((const ismcts_mnk_state*)ctx->roots, n_positions, per_position, seed, ctx->play_out);
-    }
+    SearchParams P;
+    std::memset(&P, 0, sizeof P);
+    P.roots = ctx->roots; P.n_positions = n_positions; P.seed = seed; P.playout_out = ctx->play_out;
+    P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
+    if (game == ISMCTS_GAME_KW) playout_kernel<KwGame><<<grid, kBlock, block_smem<KwGame>(), ctx->stream>>>(P, per_position);
+    else playout_kernel<MnkGame><<<grid, kBlock, block_smem<MnkGame>(), ctx->stream>>>(P, per_position);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out_result, ctx->play_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

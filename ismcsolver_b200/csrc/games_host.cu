@@ -5,6 +5,7 @@
 // test/benchmark.cpp:73-89).  These helpers do the same on the POD position
 // records, with the SAME rule code the kernels run (kw_game.cuh, mnk_game.cuh
 // are __host__ __device__).  They contain no search: the search has no host path.
+#include "philox.cuh"
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
 
@@ -49,13 +50,15 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     blank.num_players = (uint8_t)np; blank.alive_mask = (uint8_t)((1u << np) - 1u);
     blank.tricks_left = 7; blank.dealer = (uint8_t)(np - 1);
     g.load(&blank);
-    Philox rng;
-    rng.init(seed, stream, kDealTree);
+    uint32_t ring[LaneRng::kRingWords];
+    LaneRng rng;
+    rng.init(seed, stream, kDealTree, ring, 1);
     rng.begin_iteration(kDealIteration);
     g.start_deal();
     while (g.chance_pending()) {
-        const KwGame::Mask c = g.choices();
+        const KwGame::Mask c = g.chance_set();
         g.step(c.kth(rng.below(c.count())));
+        if (rng.low()) rng.refill();
     }
     // one of the remaining cards is turned up for trumps and leaves the unknown set (:50-53)
     uint64_t unknown = g.pool;
@@ -89,20 +92,21 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
     const bool play = !g.request_trump;
     if (play && !((hands[g.player] >> move) & 1u)) return ISMCTS_ERR_ILLEGAL_MOVE;
     const uint32_t mover = g.player;
-    Philox rng;
-    rng.init(seed, stream, kApplyTree);
-    rng.begin_iteration(0);
-    rng.seek(draw_counter ? *draw_counter : 0);
+    uint32_t ring[LaneRng::kRingWords];
+    LaneRng rng;
+    rng.init(seed, stream, kApplyTree, ring, 1);
+    rng.begin_iteration(0, draw_counter ? *draw_counter : 0);
     g.step(move);
     uint64_t unknown = s->unknown;
     bool dealt = false;
     while (g.chance_pending()) {
-        const KwGame::Mask c = g.choices();
+        const KwGame::Mask c = g.chance_set();
         g.step(c.kth(rng.below(c.count())));
+        if (rng.low()) rng.refill();
         dealt = true;
     }
     if (dealt) unknown = g.pool; // deal, :138-152: the undealt rest of the deck is unknown to everyone
-    if (draw_counter) *draw_counter = rng.d;
+    if (draw_counter) *draw_counter = rng.consumed();
     // the cards of the trick in progress (m_currentTrick)
     if (play) {
         if (g.trick_len == 0) {

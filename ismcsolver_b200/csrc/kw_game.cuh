@@ -7,18 +7,18 @@
 // 8-byte column per thread, everything else in registers.
 //
 // Every random event of the reference — the determinisation shuffle
-// (knockoutwhist.cpp:56-76), the re-deal shuffle (:138-152), the round-winner
-// tie-break (:198-210) and the uniformly random move of the default policy
-// (utility.h:69-83) — is expressed as ONE kind of micro-step: "remove a
-// uniformly random member from a bit set".  A step draws exactly one Philox
-// word.  Chance events that the reference resolves inside doMove become
-// pending steps (mode != kPlay) that the caller drains before the next
-// decision, in the same order the reference draws them (tie-break, then the
-// deal player by player in ascending id).
+// (cloneAndRandomise, knockoutwhist.cpp:56-76), the re-deal shuffle (deal,
+// :138-152), the round-winner tie-break (roundWinner, :198-210) and the
+// uniformly random move of the default policy (utility.h:69-83) — is expressed
+// as ONE kind of micro-step: "remove a uniformly random member from a bit set".
+// A micro-step draws exactly one Philox word.  Chance events that the reference
+// resolves inside doMove become pending micro-steps (mode != kPlay) which are
+// drained before the next decision, in the order the reference draws them
+// (tie-break, then the deal player by player in ascending id).  That is what lets
+// the 32 lanes of a warp, each in its own game and phase, run one loop body.
 #pragma once
 
 #include "devdefs.cuh"
-#include "philox.cuh"
 #include "bitset.cuh"
 #include "../../include/ismcts_b200.h"
 
@@ -50,8 +50,9 @@ struct KwGame {
     uint32_t win_card;   // card currently winning it
     uint32_t win_player; // who played that card
     uint32_t mode;       // pending chance event, if any
-    uint64_t pool;       // kDeal: undealt deck; kTie: tied players
-    uint32_t deal_player, deal_left;
+    uint64_t pool;       // kDeal: cards not dealt yet; kTie: tied players
+    uint32_t deal_player, deal_left; // kDeal: who is being dealt to and how many more cards
+    uint32_t need;       // kDeal: 4 bits per player, cards the players after deal_player still get
 
     ISMCTS_DEV uint64_t hand(uint32_t p) const { return hands[p * stride]; }
     ISMCTS_DEV void set_hand(uint32_t p, uint64_t v) { hands[p * stride] = v; }
@@ -71,7 +72,7 @@ struct KwGame {
         lead_suit = 0; win_card = 0; win_player = 0;
         // fold the trick so far into its running winner (trickWinner, knockoutwhist.cpp:182-196)
         for (uint32_t i = 0; i < trick_len; ++i) fold_trick(i, r->trick_player[i], r->trick_card[i]);
-        mode = kPlay; pool = 0; deal_player = 0; deal_left = 0;
+        mode = kPlay; pool = 0; deal_player = 0; deal_left = 0; need = 0;
     }
 
     ISMCTS_DEV void fold_trick(uint32_t index, uint32_t who, uint32_t card)
@@ -93,7 +94,8 @@ struct KwGame {
         return ctz32(above ? above : alive);
     }
 
-    // validMoves, knockoutwhist.cpp:122-136 (empty <=> the game is over).
+    // validMoves, knockoutwhist.cpp:122-136 (empty <=> the game is over).  Only
+    // meaningful while no chance event is pending.
     ISMCTS_DEV Mask legal() const
     {
         if (request_trump) return Mask{kTrumpChoices};
@@ -103,20 +105,50 @@ struct KwGame {
         return Mask{follow ? follow : h};
     }
 
-    // The set the next micro-step chooses from.
-    ISMCTS_DEV Mask choices() const { return mode == kPlay ? legal() : Mask{pool}; }
+    // The set a pending chance micro-step draws from.
+    ISMCTS_DEV Mask chance_set() const { return Mask{pool}; }
 
     // getResult * 2, knockoutwhist.cpp:117-120: the first remaining player has won.
     ISMCTS_DEV uint32_t result2(uint32_t who) const { return who == ctz32(alive) ? 2u : 0u; }
     ISMCTS_DEV uint32_t outcome() const { return ctz32(alive); }
 
+    // Starts dealing from `pool`: `sizes` holds 4 bits per player, the number of
+    // cards each gets, ascending id.
+    ISMCTS_DEV void begin_deal(uint64_t from, uint32_t sizes)
+    {
+        if (sizes == 0) { mode = kPlay; return; }
+        pool = from;
+        const uint32_t first = ctz32(sizes) >> 2;
+        deal_player = first;
+        deal_left = (sizes >> (4 * first)) & 15u;
+        need = sizes & ~(15u << (4 * first));
+        mode = kDeal;
+    }
+
+    // deal, knockoutwhist.cpp:138-152: a fresh deck, tricks_left cards to each remaining player.
     ISMCTS_DEV void start_deal()
     {
-        // deal, knockoutwhist.cpp:138-152: tricks_left cards to each remaining player, ascending id
-        pool = kFullDeck;
-        deal_player = ctz32(alive);
-        deal_left = tricks_left;
-        mode = kDeal;
+        uint32_t sizes = 0;
+        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p)
+            if ((alive >> p) & 1u) sizes |= tricks_left << (4 * p);
+        begin_deal(kFullDeck, sizes);
+    }
+
+    // cloneAndRandomise, knockoutwhist.cpp:56-76: what the observer cannot see (the
+    // unknown cards and the other players' hands) is pooled and dealt back to the
+    // other players, ascending id, keeping their hand sizes.
+    ISMCTS_DEV void begin_determinise(uint32_t observer, const Root* r)
+    {
+        uint64_t unseen = r->unknown;
+        uint32_t sizes = 0;
+        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) {
+            if (!((alive >> p) & 1u) || p == observer) continue;
+            const uint64_t h = hand(p);
+            unseen |= h;
+            sizes |= popc64(h) << (4 * p);
+            set_hand(p, 0);
+        }
+        begin_deal(unseen, sizes);
     }
 
     // finishRound, knockoutwhist.cpp:163-180
@@ -141,7 +173,7 @@ struct KwGame {
         }
     }
 
-    // One micro-step: `b` is the member of choices() that was drawn.
+    // One micro-step: `b` is the drawn member of chance_set() (chance pending) or the move played.
     ISMCTS_DEV void step(uint32_t b)
     {
         if (mode == kDeal) {
@@ -149,9 +181,14 @@ struct KwGame {
             pool &= ~bit;
             set_hand(deal_player, hand(deal_player) | bit);
             if (--deal_left == 0) {
-                const uint32_t above = alive & ~((2u << deal_player) - 1u);
-                if (above) { deal_player = ctz32(above); deal_left = tricks_left; }
-                else mode = kPlay;
+                if (need) {
+                    const uint32_t next = ctz32(need) >> 2;
+                    deal_player = next;
+                    deal_left = (need >> (4 * next)) & 15u;
+                    need &= ~(15u << (4 * next));
+                } else {
+                    mode = kPlay;
+                }
             }
             return;
         }
@@ -179,38 +216,6 @@ struct KwGame {
             player = win_player;
         }
         if (hand(player) == 0) finish_round();
-    }
-
-    // Applies a decision (a tree move or a rollout move) and drains the chance
-    // events it triggers, as doMove does internally.
-    ISMCTS_DEV void apply(uint32_t move, Philox& rng)
-    {
-        step(move);
-        while (mode != kPlay) {
-            const Mask c{pool};
-            step(c.kth(rng.below(c.count())));
-        }
-    }
-
-    // cloneAndRandomise, knockoutwhist.cpp:56-76: pool what the observer cannot
-    // see and redeal it to the other players, ascending id, keeping hand sizes.
-    ISMCTS_DEV void determinise(uint32_t observer, Philox& rng, const Root* r)
-    {
-        uint64_t unseen = r->unknown;
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p)
-            if (((alive >> p) & 1u) && p != observer) unseen |= hand(p);
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) {
-            if (!((alive >> p) & 1u) || p == observer) continue;
-            const uint32_t size = popc64(hand(p));
-            uint64_t h = 0;
-            for (uint32_t j = 0; j < size; ++j) {
-                const uint32_t b = kth_bit64(unseen, rng.below(popc64(unseen)));
-                const uint64_t bit = (uint64_t)1 << b;
-                unseen &= ~bit;
-                h |= bit;
-            }
-            set_hand(p, h);
-        }
     }
 };
 

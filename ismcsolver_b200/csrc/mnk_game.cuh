@@ -8,7 +8,6 @@
 #pragma once
 
 #include "devdefs.cuh"
-#include "philox.cuh"
 #include "bitset.cuh"
 #include "../../include/ismcts_b200.h"
 
@@ -36,8 +35,9 @@ struct MnkGame {
     }
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
-    ISMCTS_DEV bool chance_pending() const { return false; }
-    ISMCTS_DEV void determinise(uint32_t, Philox&, const Root*) {} // plain copy, mnkgame.cpp:34-37
+    ISMCTS_DEV bool chance_pending() const { return false; }    // perfect information, no chance events
+    ISMCTS_DEV void begin_determinise(uint32_t, const Root*) {} // cloneAndRandomise is a plain copy, mnkgame.cpp:34-37
+    ISMCTS_DEV Mask chance_set() const { return Mask::none(); }
 
     ISMCTS_DEV bool occupied_by(uint32_t p, uint32_t cell) const
     {
@@ -57,7 +57,6 @@ struct MnkGame {
         }
         return out;
     }
-    ISMCTS_DEV Mask choices() const { return legal(); }
 
     // hasWinningSequence, mnkgame.cpp:109-130: run length through `cell` along (dr, dc)
     ISMCTS_DEV bool exact_run(uint32_t cell, int dr, int dc) const
@@ -86,7 +85,6 @@ struct MnkGame {
         for (uint32_t i = 0; i < 8; ++i) filled += popc64(stones[i * stride]);
         if (filled < m * n) player = 1u - player; else res2 = 1;
     }
-    ISMCTS_DEV void apply(uint32_t move, Philox&) { step(move); }
 
     // getResult * 2, mnkgame.cpp:56-59
     ISMCTS_DEV uint32_t result2(uint32_t who) const { return (uint32_t)(who == 0 ? res2 : 2 - res2); }

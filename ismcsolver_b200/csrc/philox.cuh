@@ -4,71 +4,84 @@
 // knockoutwhist.cpp:28-32).  Word d of an iteration is
 //   Philox4x32-10(counter = (d/4, iteration, global tree id, position id),
 //                 key = seed)[d % 4],
-// so any random choice can be recomputed from its coordinates alone and the
-// result of a search does not depend on how trees map to threads or GPUs.
+// (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11), so any
+// random choice can be recomputed from its coordinates alone and the result of a
+// search does not depend on how trees map to threads, warps or GPUs.  Every
+// random choice of the engine is "uniform integer below n" = high word of
+// word * n, and consumes exactly one word.
 #pragma once
 
 #include "devdefs.cuh"
 
 namespace ismcts {
 
-struct Philox {
-    uint32_t k0, k1;         // key = seed
-    uint32_t c1, c2, c3;     // iteration, tree, position
-    uint32_t d;              // next word index
-    uint32_t r0, r1, r2, r3; // words of the current block not yet handed out (r0 first)
+ISMCTS_DEV void philox4x32_10(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t a, uint32_t b,
+                              uint32_t out[4])
+{
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+        x0 = hi1 ^ x1 ^ a;
+        x1 = lo1;
+        x2 = hi0 ^ x3 ^ b;
+        x3 = lo0;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+}
 
-    ISMCTS_DEV void init(uint64_t seed, uint32_t pos, uint32_t tree)
+// The stream of one lane.  Generated words wait in a small ring in shared memory
+// (one 4-byte column per thread, 8 rows): the search loop refills all lanes of a
+// warp at the same passes (every fourth), so the ten Philox rounds are executed
+// with all lanes active although the lanes consume their words at different
+// rates and start their iterations at different times.
+struct LaneRng {
+    static constexpr uint32_t kRingWords = 8;
+    uint32_t k0, k1;      // key = seed
+    uint32_t c1, c2, c3;  // iteration, tree, position
+    uint32_t next_block;  // next block (d / 4) to generate
+    uint32_t head, count; // ring read position, words waiting
+    uint32_t* ring;       // ring[(i % 8) * stride]
+    uint32_t stride;
+
+    ISMCTS_DEV void init(uint64_t seed, uint32_t pos, uint32_t tree, uint32_t* ring_base, uint32_t ring_stride)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        c1 = 0; c2 = tree; c3 = pos; d = 0;
-        r0 = r1 = r2 = r3 = 0;
+        c1 = 0; c2 = tree; c3 = pos; next_block = 0; head = 0; count = 0;
+        ring = ring_base; stride = ring_stride;
     }
 
-    ISMCTS_DEV void begin_iteration(uint32_t iteration) { c1 = iteration; d = 0; }
-
-    // Positions the stream at word `nd` of the current iteration (host helpers resume
-    // a stream in the middle of a block; the search only starts at boundaries).
-    ISMCTS_DEV void seek(uint32_t nd)
-    {
-        d = nd & ~3u;
-        if (nd & 3u) {
-            refill();
-            for (uint32_t i = 0; i < (nd & 3u); ++i) { r0 = r1; r1 = r2; r2 = r3; }
-        }
-        d = nd;
-    }
-
-    // Skips to the next block boundary (rollouts start on one so that all lanes
-    // of a warp refill on the same step).
-    ISMCTS_DEV void align() { d = (d + 3u) & ~3u; }
-
+    // Generates the next block of four words into the ring.
     ISMCTS_DEV void refill()
     {
-        uint32_t x0 = d >> 2, x1 = c1, x2 = c2, x3 = c3;
-        uint32_t a = k0, b = k1;
+        uint32_t w[4];
+        philox4x32_10(next_block, c1, c2, c3, k0, k1, w);
+        ++next_block;
+        const uint32_t at = head + count;
 #pragma unroll
-        for (int round = 0; round < 10; ++round) {
-            const uint32_t hi0 = mulhi32(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-            const uint32_t hi1 = mulhi32(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-            x0 = hi1 ^ x1 ^ a;
-            x1 = lo1;
-            x2 = hi0 ^ x3 ^ b;
-            x3 = lo0;
-            a += 0x9E3779B9u;
-            b += 0xBB67AE85u;
-        }
-        r0 = x0; r1 = x1; r2 = x2; r3 = x3;
+        for (uint32_t i = 0; i < 4; ++i) ring[((at + i) & (kRingWords - 1)) * stride] = w[i];
+        count += 4;
     }
 
-    // Next 32-bit word of the stream.  Words are always consumed in order from a
-    // block boundary (d starts at 0 and align() only moves to boundaries).
+    // Starts the stream of `iteration` at word 0 (or at word `d` for the host helpers).
+    ISMCTS_DEV void begin_iteration(uint32_t iteration, uint32_t d = 0)
+    {
+        c1 = iteration; next_block = d >> 2; head = 0; count = 0;
+        refill();
+        head = d & 3u; count -= d & 3u;
+    }
+
+    ISMCTS_DEV bool low() const { return count < 4; }   // room for one more block
+    ISMCTS_DEV uint32_t consumed() const { return next_block * 4 - count; } // = d, words handed out
+
+    // Next 32-bit word of the stream; there is always one waiting (the caller
+    // refills whenever low() at least once per four words).
     ISMCTS_DEV uint32_t word()
     {
-        if ((d & 3u) == 0u) refill();
-        const uint32_t w = r0;
-        r0 = r1; r1 = r2; r2 = r3;
-        ++d;
+        const uint32_t w = ring[(head & (kRingWords - 1)) * stride];
+        ++head; --count;
         return w;
     }
 

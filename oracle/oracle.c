@@ -484,7 +484,6 @@ uint32_t orc_playout(uint32_t game, const void* root, uint64_t seed, uint32_t po
     if (og_load(&g, game, root)) return 0xFFFFFFFFu;
     rng r = { seed, pos, tree, iteration, 0, NULL };
     og_determinise(&g, og_player(&g), &r);
-    r.d = (r.d + 3u) & ~3u;
     const uint32_t plies = og_rollout(&g, &r);
     uint32_t winner;
     if (game == ISMCTS_GAME_KW) {
@@ -677,7 +676,6 @@ static void so_iteration(otree* t, const ogame* root, uint32_t policy, double ex
         node = otree_select(t, node, legal, n, policy, exploration, r); /* select, sosolver.h:53-61 */
         og_apply(&g, (int)t->n[node].move, r);
     }
-    r->d = (r->d + 3u) & ~3u;
     og_rollout(&g, r);
     otree_backprop(t, node, &g, policy, r->cnt);
     if (r->cnt) r->cnt->iterations++;
@@ -750,7 +748,6 @@ static void mo_iteration(motrees* m, const ogame* root, uint32_t policy, double 
         og_apply(&g, (int)mv, r);
         if (u > 0) break;
     }
-    r->d = (r->d + 3u) & ~3u;
     og_rollout(&g, r);
     for (int i = 0; i < m->np; ++i) otree_backprop(&m->t[i], cur[i], &g, policy, r->cnt); /* :97-101 */
     if (r->cnt) r->cnt->iterations++;

@@ -7,7 +7,7 @@
 // has no CPU path: the real kernels are in ismcsolver_b200/csrc/engine.cu.
 //
 // Build: g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC
-#include "../../ismcsolver_b200/csrc/so_search.cuh"
+#include "../../ismcsolver_b200/csrc/lane_search.cuh"
 #include "../../ismcsolver_b200/csrc/kw_game.cuh"
 #include "../../ismcsolver_b200/csrc/mnk_game.cuh"
 
@@ -17,6 +17,24 @@
 #include <vector>
 
 using namespace ismcts;
+
+static uint32_t g_thresh = 8, g_period = 8;
+
+template <class Game>
+static uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_t iteration)
+{
+    SearchParams P;
+    std::memset(&P, 0, sizeof P);
+    uint32_t out = 0;
+    // position `pos` of the caller is record 0 here: shift pos_base instead of the pointer
+    P.roots = root; P.n_positions = 1; P.pos_base = pos; P.seed = seed; P.playout_out = &out - iteration;
+    P.tree_thresh = g_thresh; P.tree_period = g_period;
+    uint64_t scratch[Game::kHandWords];
+    uint32_t ring[LaneRng::kRingWords];
+    // thread `iteration` of a launch with per_position > iteration plays playout `iteration` of record 0
+    lane_playout<Game>(P, iteration, true, 0x7FFFFFFFu, scratch, 1, ring, 1);
+    return out;
+}
 
 template <class Game>
 static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos, uint32_t tree_id,
@@ -42,8 +60,11 @@ static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uin
     P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
     P.visits = v.data(); P.score2 = s.data(); P.avail = a.data(); P.iters_done = it.data();
 
+    P.tree_thresh = g_thresh; P.tree_period = g_period;
     uint64_t scratch[Game::kHandWords];
-    so_tree_search<Game>(P, 0, scratch, 1);
+    uint32_t ring[LaneRng::kRingWords];
+    std::vector<uint32_t> path(Game::kMaxDepth);
+    lane_tree_search<Game>(P, 0, true, scratch, 1, ring, 1, path.data());
 
     uint32_t n = 0;
     for (const Slot& sl : table) if (sl.key != 0) ++n;
@@ -62,12 +83,13 @@ static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uin
 
 extern "C" {
 
+// Schedule of the search loop (when pending tree operations run); results must not depend on it.
+void emu_set_schedule(uint32_t thresh, uint32_t period) { g_thresh = thresh; g_period = period; }
+
 uint32_t emu_playout(uint32_t game, const void* root, uint64_t seed, uint32_t pos, uint32_t iteration)
 {
-    uint64_t scratch[8];
-    if (game == ISMCTS_GAME_KW)
-        return playout_only<KwGame>((const ismcts_kw_state*)root, seed, pos, iteration, scratch, 1);
-    return playout_only<MnkGame>((const ismcts_mnk_state*)root, seed, pos, iteration, scratch, 1);
+    if (game == ISMCTS_GAME_KW) return playout_t<KwGame>(root, seed, pos, iteration);
+    return playout_t<MnkGame>(root, seed, pos, iteration);
 }
 
 int emu_so_search(uint32_t game, const void* root, uint64_t iterations, uint64_t seed, uint32_t pos, uint32_t tree,

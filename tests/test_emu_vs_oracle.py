@@ -23,6 +23,7 @@ def emu():
     E.emu_playout.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
     E.emu_so_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double,
                                 C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    E.emu_set_schedule.argtypes = [C.c_uint32, C.c_uint32]
     return E
 
 
@@ -93,3 +94,19 @@ def test_exploration_constant_is_used(emu):
         got = emu_search(emu, O.GAME_KW, s, 1500, 2, 0, 0, exploration=c)
         for f in FIELDS:
             assert (got[f] == want[f]).all(), (c, f)
+
+
+@pytest.mark.parametrize("thresh,period", [(1, 1), (1, 7), (8, 3), (40, 16), (40, 64)])
+def test_result_does_not_depend_on_the_schedule(emu, thresh, period):
+    """lane_search.cuh defers tree operations and batches them; when they run must not matter."""
+    try:
+        emu.emu_set_schedule(thresh, period)
+        s = O.kw_deal(3, 3, 4)
+        want = O.so_search(O.GAME_KW, s, 1200, seed=8)
+        got = emu_search(emu, O.GAME_KW, s, 1200, 8, 0, 0)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), f
+        for it in range(60):
+            assert O.playout(O.GAME_KW, s, 5, 2, 0, it) == emu.emu_playout(O.GAME_KW, C.byref(s), 5, 2, it)
+    finally:
+        emu.emu_set_schedule(8, 8)
