@@ -76,9 +76,11 @@ ISMCTS_DEV uint32_t kth_bit32(uint32_t w, uint32_t k)
 
 ISMCTS_DEV uint32_t kth_bit64(uint64_t m, uint32_t k)
 {
+    // choose the half first so that the 32-bit search exists once in the code
     const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
     const uint32_t c = popc32(lo);
-    return (k >= c) ? 32u + kth_bit32(hi, k - c) : kth_bit32(lo, k);
+    const bool upper = k >= c;
+    return (upper ? 32u : 0u) + kth_bit32(upper ? hi : lo, upper ? k - c : k);
 }
 
 } // namespace ismcts

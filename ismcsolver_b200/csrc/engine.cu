@@ -33,8 +33,10 @@ constexpr size_t block_smem()
     return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + LaneRng::kRingWords * sizeof(uint32_t));
 }
 
-template <class Game>
-__global__ void __launch_bounds__(kBlock) so_root_parallel_kernel(SearchParams P)
+// kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
+// for warps per scheduler; the variants are instantiated below and chosen per game at launch.
+template <class Game, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) so_root_parallel_kernel(SearchParams P)
 {
     extern __shared__ uint64_t smem[];
     uint64_t* scratch = smem + threadIdx.x;
@@ -42,6 +44,16 @@ __global__ void __launch_bounds__(kBlock) so_root_parallel_kernel(SearchParams P
     uint32_t path[Game::kMaxDepth];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     lane_tree_search<Game>(P, gtid, gtid < P.n_positions * P.trees, scratch, kBlock, ring, kBlock, path);
+}
+
+// Root records -> the register image every iteration starts from (one thread per position).
+template <class Game>
+__global__ void prepare_kernel(const typename Game::Root* roots, typename Game::Prepared* prepared, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t scratch[Game::kHandWords];
+    Game::prepare(roots + i, prepared + i, scratch);
 }
 
 template <class Game>
@@ -73,11 +85,13 @@ struct ismcts_ctx {
     void* pool = nullptr;        size_t pool_bytes = 0;
     double* ln_table = nullptr;  uint32_t ln_count = 0;
     void* roots = nullptr;       size_t roots_bytes = 0;
+    void* prepared = nullptr;    size_t prepared_bytes = 0;
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD override
-    uint32_t tree_thresh = 8, tree_period = 8;
+    uint32_t tree_thresh = 12, tree_period = 32;
+    int min_blocks = 5;          // resident CTAs per SM the search kernel is compiled for; ISMCTS_MIN_BLOCKS
 
     // geometry of the last search (for ismcts_dump_tree)
     uint32_t last_log2cap = 0;
@@ -147,6 +161,8 @@ int ismcts_create(int device, ismcts_ctx** out)
     ctx->stream = ctx->own_stream;
     if (const char* e = std::getenv("ISMCTS_TREE_THRESH")) ctx->tree_thresh = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("ISMCTS_TREE_PERIOD")) ctx->tree_period = std::max(1, std::atoi(e));
+    while (ctx->tree_period & (ctx->tree_period - 1)) ++ctx->tree_period; // a power of two
+    if (const char* e = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(e);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -156,7 +172,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->out); cudaFree(ctx->play_out);
+    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared); cudaFree(ctx->out); cudaFree(ctx->play_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -227,11 +243,32 @@ static int ensure_ln_table(ismcts_ctx* ctx, uint32_t count)
     return ISMCTS_OK;
 }
 
+// Runs prepare_kernel over `n` root records at d_roots into ctx->prepared.
 template <class Game>
-static int launch_so(ismcts_ctx* ctx, const SearchParams& P, uint32_t n_threads)
+static int launch_prepare(ismcts_ctx* ctx, const void* d_roots, uint32_t n)
 {
+    int rc = ensure(ctx, ctx->prepared, ctx->prepared_bytes, (size_t)n * sizeof(typename Game::Prepared));
+    if (rc) return rc;
+    prepare_kernel<Game><<<(n + 127) / 128, 128, 0, ctx->stream>>>((const typename Game::Root*)d_roots,
+                                                                  (typename Game::Prepared*)ctx->prepared, n);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return ISMCTS_OK;
+}
+
+template <class Game>
+static int launch_so(ismcts_ctx* ctx, SearchParams& P, const void* d_roots, uint32_t n_threads)
+{
+    int rc = launch_prepare<Game>(ctx, d_roots, P.n_positions);
+    if (rc) return rc;
+    P.prepared = ctx->prepared;
     const uint32_t grid = (n_threads + kBlock - 1) / kBlock;
-    so_root_parallel_kernel<Game><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
+    switch (ctx->min_blocks) {
+    case 8: so_root_parallel_kernel<Game, 8><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
+    case 6: so_root_parallel_kernel<Game, 6><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
+    case 5: so_root_parallel_kernel<Game, 5><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
+    default: so_root_parallel_kernel<Game, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
+    }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return ISMCTS_OK;
@@ -282,7 +319,6 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
 
     SearchParams P;
-    P.roots = d_roots;
     P.n_positions = d->n_positions; P.trees = d->trees; P.trees_total = d->trees_total;
     P.tree_base = d->tree_base; P.pos_base = d->pos_base;
     P.iterations = d->iterations; P.time_ns = d->time_ns; P.seed = d->seed;
@@ -295,8 +331,8 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
 
     ctx->last_log2cap = log2cap; ctx->last_trees_launched = n_threads; ctx->last_game = d->game;
 
-    if (d->game == ISMCTS_GAME_KW) return launch_so<KwGame>(ctx, P, n_threads);
-    return launch_so<MnkGame>(ctx, P, n_threads);
+    if (d->game == ISMCTS_GAME_KW) return launch_so<KwGame>(ctx, P, d_roots, n_threads);
+    return launch_so<MnkGame>(ctx, P, d_roots, n_threads);
 }
 
 template <class Mask>
@@ -390,8 +426,12 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
     const uint32_t grid = (uint32_t)((n + kBlock - 1) / kBlock);
     SearchParams P;
     std::memset(&P, 0, sizeof P);
-    P.roots = ctx->roots; P.n_positions = n_positions; P.seed = seed; P.playout_out = ctx->play_out;
+    P.n_positions = n_positions; P.seed = seed; P.playout_out = ctx->play_out;
     P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
+    rc = game == ISMCTS_GAME_KW ? launch_prepare<KwGame>(ctx, ctx->roots, n_positions)
+                                : launch_prepare<MnkGame>(ctx, ctx->roots, n_positions);
+    if (rc) return rc;
+    P.prepared = ctx->prepared;
     if (game == ISMCTS_GAME_KW) playout_kernel<KwGame><<<grid, kBlock, block_smem<KwGame>(), ctx->stream>>>(P, per_position);
     else playout_kernel<MnkGame><<<grid, kBlock, block_smem<MnkGame>(), ctx->stream>>>(P, per_position);
     ctx->launches++;

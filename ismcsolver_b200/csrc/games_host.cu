@@ -26,7 +26,9 @@ void kw_store(const KwGame& g, const uint64_t* hands, uint64_t unknown, ismcts_k
     s->unknown = unknown;
     s->player = (uint8_t)g.player; s->dealer = (uint8_t)g.dealer; s->trump = (uint8_t)g.trump;
     s->tricks_left = (uint8_t)g.tricks_left; s->request_trump = (uint8_t)g.request_trump;
-    s->alive_mask = (uint8_t)g.alive;
+    uint32_t alive = 0;
+    for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) alive |= ((g.alive4 >> (4 * p)) & 1u) << p;
+    s->alive_mask = (uint8_t)alive;
     s->trick_len = (uint8_t)g.trick_len;
     for (uint32_t p = 0; p < 8; ++p) s->tricks_taken[p] = p < 7 ? (uint8_t)((g.tricks >> (4 * p)) & 15u) : 0;
 }

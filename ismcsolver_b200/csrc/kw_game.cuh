@@ -4,7 +4,10 @@
 // (test/common/knockoutwhist.{h,cpp}; rules restated in SURVEY.md appendix B).
 // One GPU thread owns one game.  Card sets are 64-bit masks (bit id =
 // rank + 13*suit, card.h:38-41); the seven hands live in shared memory, one
-// 8-byte column per thread, everything else in registers.
+// 8-byte column per thread, everything else in registers.  Sets of players and
+// the trick counts are kept as one 4-bit field per player, so that the
+// round-end bookkeeping (knock-outs, most tricks, ties, deal sizes) is a
+// handful of word-parallel operations instead of loops over the players.
 //
 // Every random event of the reference — the determinisation shuffle
 // (cloneAndRandomise, knockoutwhist.cpp:56-76), the re-deal shuffle (deal,
@@ -24,6 +27,21 @@
 
 namespace ismcts {
 
+// What every iteration of a search starts from: the root position as the lane's
+// registers want it, with the determinisation (cloneAndRandomise for the root's
+// player to move) already set up as a pending deal.  Built once per position.
+struct alignas(16) KwPrepared {
+    uint64_t hand_obs;   // the observer's own hand (the only one it can see)
+    uint64_t unseen;     // unknown cards + the other players' hands: the pool to deal back
+    uint32_t sizes;      // 4 bits per player: cards to deal back (0 for the observer)
+    uint32_t observer;
+    uint32_t player, dealer, trump, tricks_left, request_trump;
+    uint32_t alive4, tricks, best;
+    uint32_t trick_len, lead_suit, win_key, win_player;
+    uint32_t pad[2];
+};
+static_assert(sizeof(KwPrepared) == 80, "five 16-byte loads");
+
 struct KwGame {
     static constexpr uint32_t kGameId = ISMCTS_GAME_KW;
     static constexpr uint32_t kMoveStride = 64;
@@ -31,33 +49,61 @@ struct KwGame {
     static constexpr uint32_t kMaxDepth = 208;  // plies are bounded by 6 + players * 28 (gametest.cpp:166-178)
     using Mask = Mask64;
     using Root = ismcts_kw_state;
+    using Prepared = KwPrepared;
 
     enum Mode : uint32_t { kPlay = 0, kDeal = 1, kTie = 2 };
 
     static constexpr uint64_t kFullDeck = (uint64_t(1) << 52) - 1;
     static constexpr uint64_t kTrumpChoices = uint64_t(1) | (uint64_t(1) << 13) | (uint64_t(1) << 26) | (uint64_t(1) << 39);
     static constexpr uint64_t kSuit = 0x1FFF;
+    static constexpr uint32_t kOnes = 0x1111111u; // bit 4p for each of the 7 players
 
     // per-thread hands: hand of player p is hands[p * stride]
     uint64_t* hands;
     uint32_t stride;
 
     uint32_t player, dealer, trump, tricks_left, request_trump;
-    uint32_t alive;      // bit p: player p is still in (m_players)
+    uint32_t alive4;     // bit 4p: player p is still in (m_players)
     uint32_t tricks;     // 4 bits per player (m_tricksTaken)
+    uint32_t best;       // most tricks taken by one player in this round
     uint32_t trick_len;  // cards in the current trick
     uint32_t lead_suit;  // suit of its first card
-    uint32_t win_card;   // card currently winning it
+    uint32_t win_key;    // strength of the card currently winning it (card_key)
     uint32_t win_player; // who played that card
     uint32_t mode;       // pending chance event, if any
-    uint64_t pool;       // kDeal: cards not dealt yet; kTie: tied players
+    uint64_t pool;       // kDeal: cards not dealt yet; kTie: tied players (bit 4p)
     uint32_t deal_player, deal_left; // kDeal: who is being dealt to and how many more cards
     uint32_t need;       // kDeal: 4 bits per player, cards the players after deal_player still get
 
     ISMCTS_DEV uint64_t hand(uint32_t p) const { return hands[p * stride]; }
     ISMCTS_DEV void set_hand(uint32_t p, uint64_t v) { hands[p * stride] = v; }
 
-    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; }
+    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; mode = kPlay; }
+
+    // bit p -> bit 4p
+    ISMCTS_DEV static uint32_t spread4(uint32_t bits)
+    {
+        uint32_t out = 0;
+        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) out |= ((bits >> p) & 1u) << (4 * p);
+        return out;
+    }
+    // bit 4p set for every non-zero 4-bit field of x
+    ISMCTS_DEV static uint32_t nonzero4(uint32_t x)
+    {
+        x |= x >> 1;
+        x |= x >> 2;
+        return x & kOnes;
+    }
+
+    // trickWinner, knockoutwhist.cpp:182-196, as a key: a later card beats the
+    // winning one if it has the same suit and a higher rank, or another suit that
+    // is trumps.  With (trumps 2, suit led 1, other 0) * 16 + rank that is
+    // "strictly larger key" (the first card of a trick is of the suit led).
+    ISMCTS_DEV uint32_t card_key(uint32_t card, uint32_t lead) const
+    {
+        const uint32_t suit = card / 13u, rank = card - 13u * suit;
+        return rank + (suit == trump ? 32u : suit == lead ? 16u : 0u);
+    }
 
     // Loads a root position (knockoutwhist.h:36-48 as POD).
     ISMCTS_DEV void load(const Root* r)
@@ -65,23 +111,62 @@ struct KwGame {
         for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) set_hand(p, r->hands[p]);
         player = r->player; dealer = r->dealer; trump = r->trump;
         tricks_left = r->tricks_left; request_trump = r->request_trump;
-        alive = r->alive_mask;
-        tricks = 0;
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) tricks |= (uint32_t)(r->tricks_taken[p] & 15u) << (4 * p);
+        alive4 = spread4(r->alive_mask);
+        tricks = 0; best = 0;
+        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) {
+            const uint32_t t = r->tricks_taken[p] & 15u;
+            tricks |= t << (4 * p);
+            if (((r->alive_mask >> p) & 1u) && t > best) best = t;
+        }
         trick_len = r->trick_len;
-        lead_suit = 0; win_card = 0; win_player = 0;
-        // fold the trick so far into its running winner (trickWinner, knockoutwhist.cpp:182-196)
+        lead_suit = 0; win_key = 0; win_player = 0;
         for (uint32_t i = 0; i < trick_len; ++i) fold_trick(i, r->trick_player[i], r->trick_card[i]);
         mode = kPlay; pool = 0; deal_player = 0; deal_left = 0; need = 0;
     }
 
     ISMCTS_DEV void fold_trick(uint32_t index, uint32_t who, uint32_t card)
     {
-        const uint32_t suit = card / 13u;
-        if (index == 0) { lead_suit = suit; win_card = card; win_player = who; return; }
-        const uint32_t win_suit = win_card / 13u;
-        const bool beats = (suit == win_suit) ? (card > win_card) : (suit == trump);
-        if (beats) { win_card = card; win_player = who; }
+        if (index == 0) lead_suit = card / 13u;
+        const uint32_t key = card_key(card, lead_suit);
+        if (index == 0 || key > win_key) { win_key = key; win_player = who; }
+    }
+
+    // The start of an iteration for `observer` = the root's player to move.
+    ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t* scratch)
+    {
+        KwGame g;
+        g.bind(scratch, 1);
+        g.load(r);
+        Prepared p;
+        p.observer = g.player;
+        p.hand_obs = g.hand(g.player);
+        // cloneAndRandomise, knockoutwhist.cpp:56-76: what the observer cannot see (the unknown
+        // cards and the other players' hands) is pooled and dealt back to the other players,
+        // ascending id, keeping their hand sizes
+        p.unseen = r->unknown; p.sizes = 0;
+        for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q) {
+            if (!((g.alive4 >> (4 * q)) & 1u) || q == g.player) continue;
+            p.unseen |= g.hand(q);
+            p.sizes |= popc64(g.hand(q)) << (4 * q);
+        }
+        p.player = g.player; p.dealer = g.dealer; p.trump = g.trump; p.tricks_left = g.tricks_left;
+        p.request_trump = g.request_trump; p.alive4 = g.alive4; p.tricks = g.tricks; p.best = g.best;
+        p.trick_len = g.trick_len; p.lead_suit = g.lead_suit; p.win_key = g.win_key; p.win_player = g.win_player;
+        p.pad[0] = p.pad[1] = 0;
+        *out = p;
+    }
+
+    // Clone of the root with the determinisation pending (sosolver.h:46).
+    ISMCTS_DEV void start(const Prepared* q)
+    {
+        const Prepared p = *q;
+        for (uint32_t i = 0; i < ISMCTS_KW_MAX_PLAYERS; ++i) set_hand(i, 0);
+        set_hand(p.observer, p.hand_obs);
+        player = p.player; dealer = p.dealer; trump = p.trump; tricks_left = p.tricks_left;
+        request_trump = p.request_trump; alive4 = p.alive4; tricks = p.tricks; best = p.best;
+        trick_len = p.trick_len; lead_suit = p.lead_suit; win_key = p.win_key; win_player = p.win_player;
+        mode = kPlay;
+        begin_deal(p.unseen, p.sizes);
     }
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
@@ -90,8 +175,8 @@ struct KwGame {
     // nextPlayer, knockoutwhist.cpp:83-88: next id, cyclically, that is still in.
     ISMCTS_DEV uint32_t next_alive(uint32_t p) const
     {
-        const uint32_t above = alive & ~((2u << p) - 1u);
-        return ctz32(above ? above : alive);
+        const uint32_t above = alive4 & ~((2u << (4 * p)) - 1u);
+        return ctz32(above ? above : alive4) >> 2;
     }
 
     // validMoves, knockoutwhist.cpp:122-136 (empty <=> the game is over).  Only
@@ -109,64 +194,34 @@ struct KwGame {
     ISMCTS_DEV Mask chance_set() const { return Mask{pool}; }
 
     // getResult * 2, knockoutwhist.cpp:117-120: the first remaining player has won.
-    ISMCTS_DEV uint32_t result2(uint32_t who) const { return who == ctz32(alive) ? 2u : 0u; }
-    ISMCTS_DEV uint32_t outcome() const { return ctz32(alive); }
+    ISMCTS_DEV uint32_t result2(uint32_t who) const { return 4u * who == ctz32(alive4) ? 2u : 0u; }
+    ISMCTS_DEV uint32_t outcome() const { return ctz32(alive4) >> 2; }
 
-    // Starts dealing from `pool`: `sizes` holds 4 bits per player, the number of
+    // Starts dealing from `from`: `sizes` holds 4 bits per player, the number of
     // cards each gets, ascending id.
     ISMCTS_DEV void begin_deal(uint64_t from, uint32_t sizes)
     {
         if (sizes == 0) { mode = kPlay; return; }
         pool = from;
-        const uint32_t first = ctz32(sizes) >> 2;
-        deal_player = first;
-        deal_left = (sizes >> (4 * first)) & 15u;
-        need = sizes & ~(15u << (4 * first));
+        const uint32_t shift = ctz32(sizes) & ~3u;
+        deal_player = shift >> 2;
+        deal_left = (sizes >> shift) & 15u;
+        need = sizes & ~(15u << shift);
         mode = kDeal;
     }
 
     // deal, knockoutwhist.cpp:138-152: a fresh deck, tricks_left cards to each remaining player.
-    ISMCTS_DEV void start_deal()
-    {
-        uint32_t sizes = 0;
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p)
-            if ((alive >> p) & 1u) sizes |= tricks_left << (4 * p);
-        begin_deal(kFullDeck, sizes);
-    }
-
-    // cloneAndRandomise, knockoutwhist.cpp:56-76: what the observer cannot see (the
-    // unknown cards and the other players' hands) is pooled and dealt back to the
-    // other players, ascending id, keeping their hand sizes.
-    ISMCTS_DEV void begin_determinise(uint32_t observer, const Root* r)
-    {
-        uint64_t unseen = r->unknown;
-        uint32_t sizes = 0;
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) {
-            if (!((alive >> p) & 1u) || p == observer) continue;
-            const uint64_t h = hand(p);
-            unseen |= h;
-            sizes |= popc64(h) << (4 * p);
-            set_hand(p, 0);
-        }
-        begin_deal(unseen, sizes);
-    }
+    ISMCTS_DEV void start_deal() { begin_deal(kFullDeck, alive4 * tricks_left); }
 
     // finishRound, knockoutwhist.cpp:163-180
     ISMCTS_DEV void finish_round()
     {
-        uint32_t still = 0, best = 0;
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) {
-            const uint32_t t = (tricks >> (4 * p)) & 15u;
-            if (((alive >> p) & 1u) && t > 0) { still |= 1u << p; best = t > best ? t : best; }
-        }
-        alive = still;
-        if (popc32(alive) > 1) {
+        alive4 &= nonzero4(tricks);                       // players without a trick are knocked out
+        if (alive4 & (alive4 - 1u)) {                     // more than one player left
             --tricks_left;
             request_trump = 1;
-            uint32_t tied = 0; // roundWinner, :198-210: uniform among the players with most tricks
-            for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p)
-                if (((alive >> p) & 1u) && ((tricks >> (4 * p)) & 15u) == best) tied |= 1u << p;
-            pool = tied;
+            // roundWinner, :198-210: uniform among the players with most tricks
+            pool = alive4 & ~nonzero4(tricks ^ (best * kOnes));
             mode = kTie;
         } else {
             tricks_left = 0; // over: nobody holds cards, validMoves() is empty
@@ -182,10 +237,10 @@ struct KwGame {
             set_hand(deal_player, hand(deal_player) | bit);
             if (--deal_left == 0) {
                 if (need) {
-                    const uint32_t next = ctz32(need) >> 2;
-                    deal_player = next;
-                    deal_left = (need >> (4 * next)) & 15u;
-                    need &= ~(15u << (4 * next));
+                    const uint32_t shift = ctz32(need) & ~3u;
+                    deal_player = shift >> 2;
+                    deal_left = (need >> shift) & 15u;
+                    need &= ~(15u << shift);
                 } else {
                     mode = kPlay;
                 }
@@ -193,9 +248,9 @@ struct KwGame {
             return;
         }
         if (mode == kTie) {
-            player = b;                    // the round winner calls trumps
+            player = b >> 2;               // the round winner calls trumps
             dealer = next_alive(dealer);
-            tricks = 0;
+            tricks = 0; best = 0;
             start_deal();
             return;
         }
@@ -210,8 +265,10 @@ struct KwGame {
         fold_trick(trick_len, player, b);
         ++trick_len;
         player = next_alive(player);
-        if (trick_len == popc32(alive)) { // finishTrick, :155-161
+        if (trick_len == popc32(alive4)) { // finishTrick, :155-161
             tricks += 1u << (4 * win_player);
+            const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
+            best = taken > best ? taken : best;
             trick_len = 0;
             player = win_player;
         }

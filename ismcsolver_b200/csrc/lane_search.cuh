@@ -32,7 +32,7 @@
 namespace ismcts {
 
 struct SearchParams {
-    const void* roots;       // n_positions packed Game::Root records
+    const void* prepared;    // n_positions Game::Prepared records (prepare_kernel)
     uint32_t n_positions;
     uint32_t trees;          // trees per position in this launch
     uint32_t trees_total;    // trees per position over all devices
@@ -53,7 +53,7 @@ struct SearchParams {
     uint64_t* iters_done;    // [n_positions * trees]
     uint32_t* playout_out;   // playout-only launches: one packed result per thread
     uint32_t tree_thresh;    // run the pending tree operations when this many lanes of the warp wait ...
-    uint32_t tree_period;    // ... or at the latest every tree_period passes
+    uint32_t tree_period;    // ... or at the latest every tree_period passes (a power of two)
 };
 
 // Iterations of one tree in count mode: the reference drains one shared counter
@@ -70,14 +70,14 @@ enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
 template <class Game, bool kTree>
 struct Lane {
     using Mask = typename Game::Mask;
-    using Root = typename Game::Root;
+    using Prepared = typename Game::Prepared;
     using Slot = SlotT<Mask>;
 
     const SearchParams& P;
     Game g;
     LaneRng rng;
     TreePool<Mask> tree;
-    const Root* root;
+    const Prepared* prep;    // this lane's position, ready to start an iteration from
     uint32_t* path;          // slot | player << 24 of the nodes on the current descent
     uint32_t phase, node, depth, plies;
     Mask node_children, root_children;
@@ -89,8 +89,7 @@ struct Lane {
     ISMCTS_DEV void start_iteration()
     {
         rng.begin_iteration(first_iteration + (uint32_t)done);
-        g.load(root);
-        g.begin_determinise(g.current_player(), root);        // sosolver.h:46
+        g.start(prep);                                        // cloneAndRandomise, sosolver.h:46
         node = 0; depth = 0; plies = 0;
         node_children = root_children;
         phase = kTree ? kSelect : kRollout;
@@ -185,7 +184,7 @@ struct Lane {
                 g.step(set.kth(rng.below(set.count())));
             }
             const uint32_t pending = warp_ballot(tree_op);
-            if (pending != 0 && (popc32(pending) >= P.tree_thresh || pass % P.tree_period == P.tree_period - 1u)) {
+            if (pending != 0 && (popc32(pending) >= P.tree_thresh || (pass & (P.tree_period - 1u)) == P.tree_period - 1u)) {
                 if (tree_op) {
                     if (over) finish_iteration(gtid);
                     else descend();
@@ -213,7 +212,7 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
     if (valid) {
         pos = gtid / P.trees;
         const uint32_t tree_global = P.tree_base + gtid % P.trees;
-        L.root = reinterpret_cast<const typename Game::Root*>(P.roots) + pos;
+        L.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
         L.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)gtid << P.log2cap), P.log2cap);
         L.tree.init_root();
         L.rng.init(P.seed, P.pos_base + pos, tree_global, ring, ring_stride);
@@ -253,7 +252,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
     if (valid) {
         const uint32_t pos = gtid / per_position;
         L.first_iteration = gtid % per_position;
-        L.root = reinterpret_cast<const typename Game::Root*>(P.roots) + pos;
+        L.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
         L.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
         L.start_iteration();
     }

@@ -20,6 +20,7 @@ struct MnkGame {
     static constexpr uint32_t kMaxDepth = 256;
     using Mask = Mask256;
     using Root = ismcts_mnk_state;
+    using Prepared = ismcts_mnk_state;   // perfect information: an iteration starts from the root itself
 
     uint64_t* stones; // stones[(p * 4 + word) * stride]
     uint32_t stride;
@@ -36,7 +37,9 @@ struct MnkGame {
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
     ISMCTS_DEV bool chance_pending() const { return false; }    // perfect information, no chance events
-    ISMCTS_DEV void begin_determinise(uint32_t, const Root*) {} // cloneAndRandomise is a plain copy, mnkgame.cpp:34-37
+    // cloneAndRandomise is a plain copy, mnkgame.cpp:34-37
+    ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t*) { *out = *r; }
+    ISMCTS_DEV void start(const Prepared* p) { load(p); }
     ISMCTS_DEV Mask chance_set() const { return Mask::none(); }
 
     ISMCTS_DEV bool occupied_by(uint32_t p, uint32_t cell) const

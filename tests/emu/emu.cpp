@@ -27,7 +27,10 @@ static uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_
     std::memset(&P, 0, sizeof P);
     uint32_t out = 0;
     // position `pos` of the caller is record 0 here: shift pos_base instead of the pointer
-    P.roots = root; P.n_positions = 1; P.pos_base = pos; P.seed = seed; P.playout_out = &out - iteration;
+    typename Game::Prepared prepared;
+    uint64_t prep_scratch[Game::kHandWords];
+    Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
+    P.prepared = &prepared; P.n_positions = 1; P.pos_base = pos; P.seed = seed; P.playout_out = &out - iteration;
     P.tree_thresh = g_thresh; P.tree_period = g_period;
     uint64_t scratch[Game::kHandWords];
     uint32_t ring[LaneRng::kRingWords];
@@ -54,7 +57,10 @@ static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uin
 
     SearchParams P;
     std::memset(&P, 0, sizeof P);
-    P.roots = root; P.n_positions = 1; P.trees = 1; P.trees_total = tree_id + 1; P.tree_base = tree_id;
+    typename Game::Prepared prepared;
+    uint64_t prep_scratch[Game::kHandWords];
+    Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
+    P.prepared = &prepared; P.n_positions = 1; P.trees = 1; P.trees_total = tree_id + 1; P.tree_base = tree_id;
     P.pos_base = pos; P.iterations = iterations * (tree_id + 1); P.seed = seed; P.exploration = exploration;
     P.pool = table.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
     P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
