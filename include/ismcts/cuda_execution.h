@@ -1,0 +1,333 @@
+/*
+ * cuda_execution.h — CUDA execution policies: ISMCTS::CudaRootParallel and
+ * ISMCTS::CudaTreeParallel.
+ *
+ * Drop-in counterparts of the reference's std::async execution policies
+ * (include/ismcts/execution.h:26-232).  They keep the policy interface the solvers
+ * and their callers rely on —
+ *   explicit Policy(std::size_t iterationCount = 1000, unsigned n = default)
+ *   explicit Policy(Duration iterationTime, unsigned n = default)
+ *   iterationCount() / setIterationCount() / iterationTime() / setIterationTime()
+ *   (setting one budget zeroes the other, execution.h:42-63), numThreads(),
+ *   non-copyable (execution.h:34-35)
+ * — and run the search iterations in the engine's sm_100a kernels through the C ABI
+ * of include/ismcts_b200.h instead of on host threads.  `n` is the number of
+ * independent trees (root parallel; the reference: one tree per thread) or the
+ * number of iterations in flight on the one shared tree (tree parallel; the
+ * reference: threads sharing tree 0).
+ *
+ * There is no CPU path: without a usable CUDA device every search throws.
+ */
+#ifndef ISMCTS_CUDA_EXECUTION_H
+#define ISMCTS_CUDA_EXECUTION_H
+
+#include "../ismcts_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstddef>
+#include <cstdint>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ISMCTS
+{
+
+/// Thrown for engine failures (no device, CUDA errors, capacity); illegal moves keep std::out_of_range.
+struct CudaError : std::runtime_error
+{
+    CudaError(int code, std::string const &what) : std::runtime_error{what}, code{code} {}
+    int code;
+};
+
+namespace detail
+{
+
+/// What one search call produced for the root position (summed over trees and devices).
+struct RootStatistics
+{
+    std::vector<std::uint64_t> visits, score2, available; // per move id
+    std::vector<std::uint64_t> iterationsPerTree;
+    std::uint32_t bestMove {0xFFFFFFFFu};                 // first maximum of visits, ascending move id
+    std::uint64_t iterations() const
+    {
+        std::uint64_t n = 0;
+        for (auto i : iterationsPerTree)
+            n += i;
+        return n;
+    }
+};
+
+/// RAII owner of one engine context (one CUDA device).
+class Context
+{
+public:
+    explicit Context(int device) : m_device{device}
+    {
+        int const rc = ismcts_create(device, &m_ctx);
+        if (rc != ISMCTS_OK)
+            throw CudaError{rc, std::string{"ISMCTS CUDA engine: "} + ismcts_last_error(nullptr)};
+    }
+    ~Context() { ismcts_destroy(m_ctx); }
+    Context(Context const &) = delete;
+    Context &operator=(Context const &) = delete;
+
+    ismcts_ctx *get() const { return m_ctx; }
+    int device() const { return m_device; }
+
+    void check(int rc) const
+    {
+        if (rc != ISMCTS_OK)
+            throw CudaError{rc, std::string{"ISMCTS CUDA engine: "} + ismcts_last_error(m_ctx)};
+    }
+
+private:
+    ismcts_ctx *m_ctx {nullptr};
+    int m_device;
+};
+
+} // detail
+
+class CudaExecutionPolicy
+{
+public:
+    using Duration = std::chrono::duration<double>;
+
+    CudaExecutionPolicy(CudaExecutionPolicy const &) = delete;
+    CudaExecutionPolicy &operator=(CudaExecutionPolicy const &) = delete;
+    virtual ~CudaExecutionPolicy() = default;
+
+    std::size_t iterationCount() const { return m_iterCount; }
+    void setIterationCount(std::size_t count)
+    {
+        m_iterCount = count;
+        m_iterTime = Duration::zero();
+    }
+
+    Duration iterationTime() const { return m_iterTime; }
+    void setIterationTime(Duration time)
+    {
+        m_iterTime = time;
+        m_iterCount = 0;
+    }
+
+    /// Trees (root parallel) or iterations in flight on the shared tree (tree parallel).
+    /// 0 was given to the constructor: chosen per search from the budget (see treesFor()).
+    unsigned int numThreads() const { return m_parallelism ? m_parallelism : treesFor(m_iterCount); }
+
+    // ---- CUDA-specific knobs (defaulted so that reference call sites compile unchanged)
+
+    /// Fixes the Philox seed: searches become reproducible (the reference is unseeded, utility.h:62-67).
+    void setSeed(std::uint64_t seed) { m_seed = seed; m_seedFixed = true; }
+    std::uint64_t seed() const { return m_seed; }
+
+    /// CUDA devices to search on; root-parallel trees are sharded over them.
+    void setDevices(std::vector<int> devices)
+    {
+        if (devices.empty())
+            throw std::invalid_argument("setDevices: at least one device");
+        m_devices = std::move(devices);
+        m_contexts.clear();
+    }
+    std::vector<int> const &devices() const { return m_devices; }
+
+    /// How many of the searched trees currentTrees() materialises on the host (default 8).
+    void setMaterialisedTrees(unsigned int count) { m_materialised = count; }
+
+    /// Statistics of the last search (root visit / reward / availability sums, iterations run).
+    detail::RootStatistics const &lastStatistics() const { return m_last; }
+
+protected:
+    /// Fewest iterations a tree gets when the number of trees is chosen automatically.  Spreading a
+    /// small budget over many trees leaves every root child with one visit (solvertest.cpp:131-138
+    /// expects a decision from 16 iterations), so small budgets use one tree.
+    static constexpr std::size_t minIterationsPerTree = 256;
+    /// One resident wave of the search kernel on a B200: 148 SMs x 8 CTAs x 128 lanes.
+    static constexpr unsigned int fullWave = 148 * 8 * 128;
+
+    CudaExecutionPolicy(std::size_t iterationCount, unsigned int parallelism, bool sharedTree)
+        : m_parallelism{parallelism}, m_sharedTree{sharedTree}
+    {
+        setIterationCount(iterationCount);
+        m_seed = std::random_device{}();
+        m_seed = (m_seed << 32) ^ std::random_device{}();
+    }
+
+    CudaExecutionPolicy(Duration iterationTime, unsigned int parallelism, bool sharedTree)
+        : CudaExecutionPolicy{std::size_t{0}, parallelism, sharedTree}
+    {
+        setIterationTime(iterationTime);
+    }
+
+    unsigned int treesFor(std::size_t iterations) const
+    {
+        if (m_sharedTree)
+            return 1;
+        if (iterations == 0)
+            return fullWave / 4;  // time mode: every tree iterates until the deadline
+        std::size_t const trees = iterations / minIterationsPerTree;
+        return static_cast<unsigned int>(std::min<std::size_t>(std::max<std::size_t>(trees, 1), fullWave));
+    }
+
+    bool sharedTree() const { return m_sharedTree; }
+
+    /// Runs one search of `podState` (a position record of include/ismcts_b200.h) on the configured
+    /// devices and merges the per-device root arrays (RootParallel::compileVisitCounts,
+    /// execution.h:219-231, across devices).
+    detail::RootStatistics const &search(std::uint32_t game, void const *podState, std::uint32_t solver,
+                                         std::uint32_t policy, double exploration)
+    {
+        if (m_contexts.empty())
+            for (int device : m_devices)
+                m_contexts.push_back(std::make_unique<detail::Context>(device));
+        if (!m_seedFixed)
+            ++m_seed;
+
+        std::uint32_t const stride = ismcts_move_stride(game);
+        unsigned int treesTotal = m_parallelism && !m_sharedTree ? m_parallelism : treesFor(m_iterCount);
+        if (m_iterCount > 0)
+            treesTotal = static_cast<unsigned int>(std::min<std::size_t>(treesTotal, m_iterCount));
+        std::size_t const nDev = std::min<std::size_t>(m_contexts.size(), treesTotal);
+
+        struct Shard
+        {
+            ismcts_search_desc desc;
+            std::vector<std::uint64_t> visits, score2, avail, iters;
+            std::uint32_t best {0};
+            int rc {ISMCTS_OK};
+        };
+        std::vector<Shard> shards(nDev);
+        unsigned int base = 0;
+        for (std::size_t d = 0; d < nDev; ++d) {
+            unsigned int const trees = treesTotal / nDev + (d < treesTotal % nDev ? 1 : 0);
+            Shard &s = shards[d];
+            s.desc = ismcts_search_desc{};
+            s.desc.game = game;
+            s.desc.solver = solver;
+            s.desc.policy = policy;
+            s.desc.n_positions = 1;
+            s.desc.trees = trees;
+            s.desc.trees_total = treesTotal;
+            s.desc.tree_base = base;
+            s.desc.pos_base = 0;
+            s.desc.iterations = m_iterCount;
+            s.desc.time_ns = static_cast<std::uint64_t>(m_iterTime.count() * 1e9);
+            s.desc.seed = m_seed;
+            s.desc.exploration = exploration;
+            s.desc.dump_tree = 0xFFFFFFFFu;
+            s.desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (m_parallelism << ISMCTS_FLAG_LANES_SHIFT)) : 0;
+            s.visits.assign(stride, 0);
+            s.score2.assign(stride, 0);
+            s.avail.assign(stride, 0);
+            s.iters.assign(trees, 0);
+            base += trees;
+        }
+        auto runShard = [&](std::size_t d) {
+            Shard &s = shards[d];
+            ismcts_search_out out {};
+            out.visits = s.visits.data();
+            out.score2 = s.score2.data();
+            out.avail = s.avail.data();
+            out.iterations_done = s.iters.data();
+            out.best_move = &s.best;
+            s.rc = ismcts_search(m_contexts[d]->get(), &s.desc, podState, &out);
+        };
+        if (nDev == 1) {
+            runShard(0);
+        } else {
+            std::vector<std::thread> workers;
+            for (std::size_t d = 0; d < nDev; ++d)
+                workers.emplace_back(runShard, d);
+            for (auto &w : workers)
+                w.join();
+        }
+        m_last = detail::RootStatistics{};
+        m_last.visits.assign(stride, 0);
+        m_last.score2.assign(stride, 0);
+        m_last.available.assign(stride, 0);
+        for (std::size_t d = 0; d < nDev; ++d) {
+            m_contexts[d]->check(shards[d].rc);
+            for (std::uint32_t m = 0; m < stride; ++m) {
+                m_last.visits[m] += shards[d].visits[m];
+                m_last.score2[m] += shards[d].score2[m];
+                m_last.available[m] += shards[d].avail[m];
+            }
+            m_last.iterationsPerTree.insert(m_last.iterationsPerTree.end(), shards[d].iters.begin(), shards[d].iters.end());
+        }
+        // bestMove: most visits, the first maximum in ascending move order (execution.h:126-135,209-216)
+        std::uint64_t bestVisits = 0;
+        for (std::uint32_t m = 0; m < stride; ++m)
+            if (m_last.visits[m] > bestVisits) {
+                bestVisits = m_last.visits[m];
+                m_last.bestMove = m;
+            }
+        m_lastTreesOnFirstDevice = shards[0].desc.trees;
+        return m_last;
+    }
+
+    /// Reads tree `index` of the last search back from the first device (creation order).
+    std::vector<ismcts_node_rec> dumpTree(std::uint32_t index) const
+    {
+        if (m_contexts.empty())
+            return {};
+        std::uint32_t count = 0;
+        std::vector<ismcts_node_rec> nodes(1024);
+        int rc = ismcts_dump_tree(m_contexts[0]->get(), index, nodes.data(), static_cast<std::uint32_t>(nodes.size()), &count);
+        if (rc == ISMCTS_ERR_CAPACITY) {
+            nodes.resize(count);
+            rc = ismcts_dump_tree(m_contexts[0]->get(), index, nodes.data(), count, &count);
+        }
+        m_contexts[0]->check(rc);
+        nodes.resize(count);
+        return nodes;
+    }
+
+    unsigned int materialisedTrees() const { return std::min(m_materialised, m_lastTreesOnFirstDevice); }
+
+private:
+    std::size_t m_iterCount {0};
+    Duration m_iterTime {Duration::zero()};
+    unsigned int const m_parallelism;
+    bool const m_sharedTree;
+    std::uint64_t m_seed {0};
+    bool m_seedFixed {false};
+    std::vector<int> m_devices {0};
+    std::vector<std::unique_ptr<detail::Context>> m_contexts;
+    unsigned int m_materialised {8};
+    unsigned int m_lastTreesOnFirstDevice {0};
+    detail::RootStatistics m_last;
+};
+
+/// Root parallelisation on the GPU: `numTrees` independent trees (0 = chosen from the budget),
+/// one per lane; the decision sums the root visits per move over all trees
+/// (RootParallel, execution.h:181-232).
+class CudaRootParallel : public CudaExecutionPolicy
+{
+public:
+    explicit CudaRootParallel(std::size_t iterationCount = 1000, unsigned int numTrees = 0)
+        : CudaExecutionPolicy{iterationCount, numTrees, false}
+    {}
+    explicit CudaRootParallel(Duration iterationTime, unsigned int numTrees = 0)
+        : CudaExecutionPolicy{iterationTime, numTrees, false}
+    {}
+};
+
+/// Tree parallelisation on the GPU: one shared tree, `numThreads` iterations in flight with
+/// virtual loss (TreeParallel, execution.h:169-179; the reference has no virtual loss).
+class CudaTreeParallel : public CudaExecutionPolicy
+{
+public:
+    explicit CudaTreeParallel(std::size_t iterationCount = 1000, unsigned int numThreads = 32)
+        : CudaExecutionPolicy{iterationCount, std::max(numThreads, 1u), true}
+    {}
+    explicit CudaTreeParallel(Duration iterationTime, unsigned int numThreads = 32)
+        : CudaExecutionPolicy{iterationTime, std::max(numThreads, 1u), true}
+    {}
+};
+
+} // ISMCTS
+
+#endif // ISMCTS_CUDA_EXECUTION_H

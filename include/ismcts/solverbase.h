@@ -1,0 +1,106 @@
+/*
+ * solverbase.h — what SOSolver and MOSolver share on the host side.
+ *
+ * Counterpart of the reference's SolverBase (include/ismcts/solverbase.h:18-88).  There
+ * the base class holds the per-iteration steps (simulate, backPropagate, selectNode,
+ * selectChild, newRoot, newChild) that run on host threads; here those steps are the
+ * kernels' (ismcsolver_b200/csrc/lane_search.cuh) and the base class keeps the policy
+ * configuration (setConfig, solverbase.h:23-26), marshals the root position and turns the
+ * device node pool into host Node objects.
+ */
+#ifndef ISMCTS_SOLVERBASE_H
+#define ISMCTS_SOLVERBASE_H
+
+#include "game.h"
+#include "tree/policies.h"
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+namespace ISMCTS
+{
+
+/// Tree policy for sequential moves (default UCB1) and for simultaneous moves (default EXP3),
+/// as in the reference's Config (include/ismcts/config.h:20-48).
+template<class Move, template<class> class SeqTree = UCB1, template<class> class SimTree = EXP3>
+struct Config
+{
+    using SeqTreePolicy = SeqTree<Move>;
+    using SimTreePolicy = SimTree<Move>;
+    using RootNode = std::shared_ptr<Node<Move>>;
+    using ChildNode = typename Node<Move>::ChildPtr;
+    using TreeList = std::vector<RootNode>;
+
+    SeqTreePolicy seqTreePolicy;
+    SimTreePolicy simTreePolicy;
+
+    Config(SeqTreePolicy seq = SeqTreePolicy{}, SimTreePolicy sim = SimTreePolicy{})
+        : seqTreePolicy{seq}, simTreePolicy{sim}
+    {}
+};
+
+template<class Move, template<class> class... Ps>
+class SolverBase
+{
+public:
+    /// Replaces the tree policies, e.g. setConfig(UCB1<Card>{1.2}) (solverbase.h:23-26).
+    void setConfig(Ps<Move>... policies) { m_config = Config(policies...); }
+
+protected:
+    using Config = ISMCTS::Config<Move, Ps...>;
+    using RootNode = typename Config::RootNode;
+    using SeqPolicy = typename Config::SeqTreePolicy;
+
+    Config const &config() const { return m_config; }
+
+    /// The device form of a game, or a clear error: opaque host games cannot run in a kernel.
+    static PodGame const &podOf(Game<Move> const &game)
+    {
+        auto const *pod = dynamic_cast<PodGame const *>(&game);
+        if (!pod)
+            throw std::invalid_argument("ISMCTS CUDA policies need a game with a device form (ISMCTS::PodGame); "
+                                        "there is no CPU fallback");
+        if (game.currentMoveSimultaneous())
+            throw std::invalid_argument("ISMCTS CUDA policies: simultaneous-move games are not supported yet");
+        return *pod;
+    }
+
+    /// Builds host nodes from one tree of the device pool (records in creation order, root first).
+    static RootNode materialise(std::vector<ismcts_node_rec> const &records)
+    {
+        using SeqNode = typename SeqPolicy::Node;
+        if (records.empty())
+            return std::make_shared<SeqNode>();
+        std::vector<Node<Move> *> byIndex(records.size(), nullptr);
+        auto root = std::make_shared<SeqNode>();
+        byIndex[0] = root.get();
+        fill(root.get(), records[0]);
+        for (std::size_t i = 1; i < records.size(); ++i) {
+            ismcts_node_rec const &r = records[i];
+            auto node = std::make_unique<SeqNode>(MoveCodec<Move>::fromId(r.move), r.player);
+            fill(node.get(), r);
+            byIndex[i] = byIndex[r.parent]->addChild(std::move(node)); // parents are created before children
+        }
+        return root;
+    }
+
+private:
+    static void fill(UCBNode<Move> *node, ismcts_node_rec const &r)
+    {
+        node->setVisits(r.visits);
+        node->setStatistics(r.score, r.avail);
+    }
+    static void fill(EXPNode<Move> *node, ismcts_node_rec const &r)
+    {
+        node->setVisits(r.visits);
+        node->setStatistics(r.score, r.prob);
+    }
+
+    Config m_config;
+};
+
+} // ISMCTS
+
+#endif // ISMCTS_SOLVERBASE_H

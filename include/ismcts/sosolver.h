@@ -1,0 +1,63 @@
+/*
+ * sosolver.h — single-observer ISMCTS solver.
+ *
+ * Same public interface as the reference's SOSolver (include/ismcts/sosolver.h:21-76):
+ * SOSolver<Move, ExecutionPolicy, TreePolicies...>, constructors inherited from the
+ * policy, Move operator()(Game<Move> const&), currentTrees().  One tree for the player to
+ * move at the root; every iteration determinises the root for that player, descends with
+ * the sequential tree policy, expands one node, plays out uniformly at random and
+ * backpropagates (sosolver.h:44-71) — in the engine's kernels.
+ */
+#ifndef ISMCTS_SOSOLVER_H
+#define ISMCTS_SOSOLVER_H
+
+#include "cuda_execution.h"
+#include "solverbase.h"
+
+namespace ISMCTS
+{
+
+template<class Move, class _ExecutionPolicy = CudaRootParallel, template<class> class... Ps>
+class SOSolver : public _ExecutionPolicy, public SolverBase<Move, Ps...>
+{
+public:
+    using _ExecutionPolicy::_ExecutionPolicy;
+    using Config = ISMCTS::Config<Move, Ps...>;
+    using RootNode = typename Config::RootNode;
+    using TreeList = typename Config::TreeList;
+
+    /// Searches from `rootState` and returns the most visited root move (ties: the first in
+    /// ascending move order).  The game is not modified.  Returns Move{} when it is over.
+    Move operator()(Game<Move> const &rootState)
+    {
+        PodGame const &pod = SOSolver::podOf(rootState);
+        std::vector<unsigned char> state(pod.podSize());
+        pod.exportPod(state.data());
+        auto const &policy = this->config().seqTreePolicy;
+        auto const &result = this->search(pod.podKind(), state.data(), ISMCTS_SOLVER_SO,
+                                          std::remove_reference_t<decltype(policy)>::kernelPolicy, policy.exploration());
+        m_treesValid = true;
+        if (result.bestMove == 0xFFFFFFFFu)
+            return Move{};
+        return MoveCodec<Move>::fromId(result.bestMove);
+    }
+
+    /// The trees of the last search, one root per tree (a copy; the first
+    /// setMaterialisedTrees() trees are read back from the device).
+    TreeList currentTrees() const
+    {
+        TreeList trees;
+        if (!m_treesValid)
+            return trees;
+        for (unsigned int t = 0; t < this->materialisedTrees(); ++t)
+            trees.push_back(SOSolver::materialise(this->dumpTree(t)));
+        return trees;
+    }
+
+private:
+    bool m_treesValid {false};
+};
+
+} // ISMCTS
+
+#endif // ISMCTS_SOSOLVER_H

@@ -91,7 +91,7 @@ struct ismcts_ctx {
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD override
     uint32_t tree_thresh = 12, tree_period = 32;
-    int min_blocks = 5;          // resident CTAs per SM the search kernel is compiled for; ISMCTS_MIN_BLOCKS
+    int min_blocks = 8;          // resident CTAs per SM the search kernel is compiled for; ISMCTS_MIN_BLOCKS
 
     // geometry of the last search (for ismcts_dump_tree)
     uint32_t last_log2cap = 0;

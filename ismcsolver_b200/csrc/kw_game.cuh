@@ -149,6 +149,7 @@ struct KwGame {
             p.unseen |= g.hand(q);
             p.sizes |= popc64(g.hand(q)) << (4 * q);
         }
+        if (!g.legal().any()) g.tricks_left = 0;      // a finished game, however it is recorded
         p.player = g.player; p.dealer = g.dealer; p.trump = g.trump; p.tricks_left = g.tricks_left;
         p.request_trump = g.request_trump; p.alive4 = g.alive4; p.tricks = g.tricks; p.best = g.best;
         p.trick_len = g.trick_len; p.lead_suit = g.lead_suit; p.win_key = g.win_key; p.win_player = g.win_player;
@@ -228,8 +229,13 @@ struct KwGame {
         }
     }
 
-    // One micro-step: `b` is the drawn member of chance_set() (chance pending) or the move played.
-    ISMCTS_DEV void step(uint32_t b)
+    // validMoves() is empty: the game is over.  Every transition leaves either a
+    // player with cards to move, a pending chance event, or tricks_left == 0
+    // (prepare() normalises root records that are finished in some other way).
+    ISMCTS_DEV bool terminal() const { return tricks_left == 0; }
+
+    // A pending chance event: `b` is the drawn member of chance_set().
+    ISMCTS_DEV void chance_step(uint32_t b)
     {
         if (mode == kDeal) {
             const uint64_t bit = (uint64_t)1 << b;
@@ -247,14 +253,16 @@ struct KwGame {
             }
             return;
         }
-        if (mode == kTie) {
-            player = b >> 2;               // the round winner calls trumps
-            dealer = next_alive(dealer);
-            tricks = 0; best = 0;
-            start_deal();
-            return;
-        }
-        // doMove, knockoutwhist.cpp:95-115
+        // kTie: the round winner calls trumps (roundWinner, knockoutwhist.cpp:198-210)
+        player = b >> 2;
+        dealer = next_alive(dealer);
+        tricks = 0; best = 0;
+        start_deal();
+    }
+
+    // doMove, knockoutwhist.cpp:95-115 (no chance event pending).
+    ISMCTS_DEV void play(uint32_t b)
+    {
         if (request_trump) {
             trump = b / 13u;
             request_trump = 0;
@@ -273,6 +281,12 @@ struct KwGame {
             player = win_player;
         }
         if (hand(player) == 0) finish_round();
+    }
+
+    // One micro-step of either kind.
+    ISMCTS_DEV void step(uint32_t b)
+    {
+        if (mode != kPlay) chance_step(b); else play(b);
     }
 };
 

@@ -166,25 +166,38 @@ struct Lane {
         }
     }
 
+    // The loop.  Every pass is ONE kind of micro-step for the whole warp — a chance
+    // event (determinisation or re-deal card, tie-break) or a rollout move,
+    // whichever more lanes are waiting for — so that a pass executes one short
+    // code path with most lanes active instead of the union of all paths.  Lanes
+    // waiting for the other kind sit the pass out; deals and rounds are runs of
+    // 20-30 steps of one kind, so the lanes of a warp fall into step with each
+    // other.  Tree operations are deferred and batched in the same way.
     ISMCTS_DEV void run(uint32_t gtid)
     {
         for (uint32_t pass = 0;; ++pass) {
             const bool playing = phase != kDone;
             if (!warp_any(playing)) break;
             const bool chance = playing && g.chance_pending();
-            Mask legal = Mask::none();
-            if (playing && !chance) legal = g.legal();
-            const bool over = playing && !chance && !legal.any();
+            const bool over = playing && !chance && g.terminal();
             const bool tree_op = over || (playing && !chance && phase == kSelect);
-            if (playing && !tree_op) {
-                // one random micro-step: a chance event (determinisation, re-deal, tie-break)
-                // or a rollout move — simulate, solverbase.h:36-43 with RandomElement, utility.h:69-83
-                const Mask set = chance ? g.chance_set() : legal;
-                plies += chance ? 0u : 1u;
-                g.step(set.kth(rng.below(set.count())));
+            const bool move = playing && !chance && !tree_op;
+            const uint32_t n_chance = popc32(warp_ballot(chance)), n_move = popc32(warp_ballot(move));
+            if (n_chance >= n_move) {
+                if (chance) {
+                    // determinisation (cloneAndRandomise), re-deal or tie-break: one card / one player
+                    const Mask set = g.chance_set();
+                    g.chance_step(set.kth(rng.below(set.count())));
+                }
+            } else if (move) {
+                // simulate, solverbase.h:36-43 with RandomElement, utility.h:69-83
+                const Mask legal = g.legal();
+                ++plies;
+                g.play(legal.kth(rng.below(legal.count())));
             }
             const uint32_t pending = warp_ballot(tree_op);
-            if (pending != 0 && (popc32(pending) >= P.tree_thresh || (pass & (P.tree_period - 1u)) == P.tree_period - 1u)) {
+            if (pending != 0 && (popc32(pending) >= P.tree_thresh || (pass & (P.tree_period - 1u)) == P.tree_period - 1u ||
+                                 n_chance + n_move == 0)) {
                 if (tree_op) {
                     if (over) finish_iteration(gtid);
                     else descend();

@@ -41,6 +41,9 @@ struct MnkGame {
     ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t*) { *out = *r; }
     ISMCTS_DEV void start(const Prepared* p) { load(p); }
     ISMCTS_DEV Mask chance_set() const { return Mask::none(); }
+    ISMCTS_DEV void chance_step(uint32_t) {}
+    ISMCTS_DEV bool terminal() const { return res2 != -1; }     // validMoves() is empty, mnkgame.cpp:61-64
+    ISMCTS_DEV void play(uint32_t cell) { step(cell); }
 
     ISMCTS_DEV bool occupied_by(uint32_t p, uint32_t cell) const
     {
