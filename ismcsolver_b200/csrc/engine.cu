@@ -91,6 +91,7 @@ struct ismcts_ctx {
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD override
     uint32_t tree_thresh = 12, tree_period = 32;
+    uint32_t sched_mode = 0, sched_split_min = 8; // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT
     int min_blocks = 8;          // resident CTAs per SM the search kernel is compiled for; ISMCTS_MIN_BLOCKS
 
     // geometry of the last search (for ismcts_dump_tree)
@@ -163,6 +164,8 @@ int ismcts_create(int device, ismcts_ctx** out)
     if (const char* e = std::getenv("ISMCTS_TREE_PERIOD")) ctx->tree_period = std::max(1, std::atoi(e));
     while (ctx->tree_period & (ctx->tree_period - 1)) ++ctx->tree_period; // a power of two
     if (const char* e = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(e);
+    if (const char* e = std::getenv("ISMCTS_SCHED_MODE")) ctx->sched_mode = (uint32_t)std::atoi(e);
+    if (const char* e = std::getenv("ISMCTS_SCHED_SPLIT")) ctx->sched_split_min = (uint32_t)std::atoi(e);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -328,6 +331,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
     P.playout_out = nullptr; P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
+    P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
 
     ctx->last_log2cap = log2cap; ctx->last_trees_launched = n_threads; ctx->last_game = d->game;
 
@@ -428,6 +432,7 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
     std::memset(&P, 0, sizeof P);
     P.n_positions = n_positions; P.seed = seed; P.playout_out = ctx->play_out;
     P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
+    P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
     rc = game == ISMCTS_GAME_KW ? launch_prepare<KwGame>(ctx, ctx->roots, n_positions)
                                 : launch_prepare<MnkGame>(ctx, ctx->roots, n_positions);
     if (rc) return rc;

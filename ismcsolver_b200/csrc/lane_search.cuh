@@ -54,6 +54,8 @@ struct SearchParams {
     uint32_t* playout_out;   // playout-only launches: one packed result per thread
     uint32_t tree_thresh;    // run the pending tree operations when this many lanes of the warp wait ...
     uint32_t tree_period;    // ... or at the latest every tree_period passes (a power of two)
+    uint32_t sched_mode;     // Schedule::mode
+    uint32_t sched_split_min;
 };
 
 // Iterations of one tree in count mode: the reference drains one shared counter
@@ -64,6 +66,50 @@ ISMCTS_DEV uint64_t tree_iterations(uint64_t total, uint32_t trees_total, uint32
 }
 
 enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
+
+// Which kinds of micro-step a pass performs (the same for all lanes of the warp).
+struct PassPlan { bool chance, move, tree; };
+
+// The schedule of a warp: decides from the numbers of lanes waiting for a chance
+// event, a rollout move and a tree operation what the next pass does.  A pass
+// that does one kind only runs one short code path with the waiting lanes
+// active; a pass that does several kinds runs the paths one after the other.
+// The result of a search does not depend on the schedule (tests/emu checks that).
+struct Schedule {
+    uint32_t tree_thresh, tree_period, mode, split_min;
+    uint32_t current; // kind the warp is running (hysteresis modes)
+
+    ISMCTS_DEV void init(const SearchParams& P)
+    {
+        tree_thresh = P.tree_thresh; tree_period = P.tree_period; mode = P.sched_mode; split_min = P.sched_split_min;
+        current = 0;
+    }
+
+    ISMCTS_DEV PassPlan plan_pass(uint32_t n_chance, uint32_t n_move, uint32_t n_tree, uint32_t pass)
+    {
+        PassPlan plan;
+        plan.tree = n_tree != 0 && (n_tree >= tree_thresh || (pass & (tree_period - 1u)) == tree_period - 1u ||
+                                    n_chance + n_move == 0);
+        if (mode == 0) {                       // every kind every pass
+            plan.chance = n_chance != 0; plan.move = n_move != 0;
+        } else if (mode == 1) {                // the kind more lanes wait for
+            plan.chance = n_chance >= n_move && n_chance != 0;
+            plan.move = !plan.chance && n_move != 0;
+        } else if (mode == 2) {                // majority, but both when the minority is large enough
+            const uint32_t lo = n_chance < n_move ? n_chance : n_move;
+            const bool both = lo >= split_min;
+            plan.chance = (both || n_chance >= n_move) && n_chance != 0;
+            plan.move = (both || n_move > n_chance) && n_move != 0;
+        } else {                               // stay with a kind until few lanes want it
+            const uint32_t n_cur = current == 0 ? n_chance : n_move, n_other = current == 0 ? n_move : n_chance;
+            if (n_cur < split_min && n_other > n_cur) current ^= 1u;
+            plan.chance = current == 0 && n_chance != 0;
+            plan.move = current == 1 && n_move != 0;
+            if (!plan.chance && !plan.move) { plan.chance = n_chance != 0; plan.move = n_move != 0 && !plan.chance; }
+        }
+        return plan;
+    }
+};
 
 // kTree = false: determinise + rollout only (SolverBase::simulate after
 // cloneAndRandomise), one iteration per lane, no tree — the playout kernel.
@@ -166,44 +212,53 @@ struct Lane {
         }
     }
 
-    // The loop.  Every pass is ONE kind of micro-step for the whole warp — a chance
-    // event (determinisation or re-deal card, tie-break) or a rollout move,
-    // whichever more lanes are waiting for — so that a pass executes one short
-    // code path with most lanes active instead of the union of all paths.  Lanes
-    // waiting for the other kind sit the pass out; deals and rounds are runs of
-    // 20-30 steps of one kind, so the lanes of a warp fall into step with each
-    // other.  Tree operations are deferred and batched in the same way.
+    // ---- one pass of the loop, in two halves so that the warp votes sit between them
+
+    struct Wants { bool chance, move, tree, over; };
+
+    ISMCTS_DEV Wants classify() const
+    {
+        Wants w;
+        const bool playing = phase != kDone;
+        w.chance = playing && g.chance_pending();
+        w.over = playing && !w.chance && g.terminal();
+        w.tree = w.over || (playing && !w.chance && phase == kSelect);
+        w.move = playing && !w.chance && !w.tree;
+        return w;
+    }
+
+    ISMCTS_DEV void act(const Wants& w, const PassPlan& plan, uint32_t pass, uint32_t gtid)
+    {
+        const bool do_chance = plan.chance && w.chance, do_move = plan.move && w.move;
+        if (do_chance || do_move) {
+            // One random micro-step.  Chance: a determinisation (cloneAndRandomise) or re-deal card or
+            // a tie-break.  Move: simulate, solverbase.h:36-43 with RandomElement, utility.h:69-83.
+            // Both are "the k-th member of a set", drawn by code the two kinds share.
+            const Mask set = do_chance ? g.chance_set() : g.legal();
+            const uint32_t b = set.kth(rng.below(set.count()));
+            if (do_chance) g.chance_step(b);
+            else { ++plies; g.play(b); }
+        }
+        if (plan.tree && w.tree) {
+            if (w.over) finish_iteration(gtid);
+            else descend();
+        }
+        if ((pass & 3u) == 3u && phase != kDone && rng.low()) rng.refill();
+    }
+
+    // The loop.  Every pass performs, for the whole warp, the kinds of micro-step the
+    // schedule (plan_pass) picks from the numbers of lanes waiting for each kind.
     ISMCTS_DEV void run(uint32_t gtid)
     {
+        Schedule sched;
+        sched.init(P);
         for (uint32_t pass = 0;; ++pass) {
-            const bool playing = phase != kDone;
-            if (!warp_any(playing)) break;
-            const bool chance = playing && g.chance_pending();
-            const bool over = playing && !chance && g.terminal();
-            const bool tree_op = over || (playing && !chance && phase == kSelect);
-            const bool move = playing && !chance && !tree_op;
-            const uint32_t n_chance = popc32(warp_ballot(chance)), n_move = popc32(warp_ballot(move));
-            if (n_chance >= n_move) {
-                if (chance) {
-                    // determinisation (cloneAndRandomise), re-deal or tie-break: one card / one player
-                    const Mask set = g.chance_set();
-                    g.chance_step(set.kth(rng.below(set.count())));
-                }
-            } else if (move) {
-                // simulate, solverbase.h:36-43 with RandomElement, utility.h:69-83
-                const Mask legal = g.legal();
-                ++plies;
-                g.play(legal.kth(rng.below(legal.count())));
-            }
-            const uint32_t pending = warp_ballot(tree_op);
-            if (pending != 0 && (popc32(pending) >= P.tree_thresh || (pass & (P.tree_period - 1u)) == P.tree_period - 1u ||
-                                 n_chance + n_move == 0)) {
-                if (tree_op) {
-                    if (over) finish_iteration(gtid);
-                    else descend();
-                }
-            }
-            if ((pass & 3u) == 3u && phase != kDone && rng.low()) rng.refill();
+            if (!warp_any(phase != kDone)) break;
+            const Wants w = classify();
+            const uint32_t n_chance = popc32(warp_ballot(w.chance)), n_move = popc32(warp_ballot(w.move)),
+                           n_tree = popc32(warp_ballot(w.tree));
+            const PassPlan plan = sched.plan_pass(n_chance, n_move, n_tree, pass);
+            act(w, plan, pass, gtid);
         }
     }
 };

@@ -14,11 +14,12 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 using namespace ismcts;
 
-static uint32_t g_thresh = 8, g_period = 8;
+static uint32_t g_thresh = 8, g_period = 8, g_mode = 0, g_split = 8;
 
 template <class Game>
 static uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_t iteration)
@@ -31,7 +32,7 @@ static uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_
     uint64_t prep_scratch[Game::kHandWords];
     Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
     P.prepared = &prepared; P.n_positions = 1; P.pos_base = pos; P.seed = seed; P.playout_out = &out - iteration;
-    P.tree_thresh = g_thresh; P.tree_period = g_period;
+    P.tree_thresh = g_thresh; P.tree_period = g_period; P.sched_mode = g_mode; P.sched_split_min = g_split;
     uint64_t scratch[Game::kHandWords];
     uint32_t ring[LaneRng::kRingWords];
     // thread `iteration` of a launch with per_position > iteration plays playout `iteration` of record 0
@@ -66,7 +67,7 @@ static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uin
     P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
     P.visits = v.data(); P.score2 = s.data(); P.avail = a.data(); P.iters_done = it.data();
 
-    P.tree_thresh = g_thresh; P.tree_period = g_period;
+    P.tree_thresh = g_thresh; P.tree_period = g_period; P.sched_mode = g_mode; P.sched_split_min = g_split;
     uint64_t scratch[Game::kHandWords];
     uint32_t ring[LaneRng::kRingWords];
     std::vector<uint32_t> path(Game::kMaxDepth);
@@ -91,6 +92,74 @@ extern "C" {
 
 // Schedule of the search loop (when pending tree operations run); results must not depend on it.
 void emu_set_schedule(uint32_t thresh, uint32_t period) { g_thresh = thresh; g_period = period; }
+void emu_set_schedule_mode(uint32_t mode, uint32_t split_min) { g_mode = mode; g_split = split_min; }
+
+// A warp of 32 lanes (32 trees of one Knockout Whist position) run pass by pass with real warp votes:
+// measures how busy the lanes are under a schedule.  stats: [0] passes, [1] passes doing chance only,
+// [2] move only, [3] both, [4] passes with tree operations, [5] chance lane-steps, [6] move lane-steps,
+// [7] tree operations, [8] iterations.
+void emu_warp_sim(const void* root, uint32_t iters_per_tree, uint64_t seed, uint64_t* stats)
+{
+    using Game = KwGame;
+    using L = Lane<Game, true>;
+    using Slot = SlotT<Game::Mask>;
+    constexpr int W = 32;
+    uint32_t log2cap = 4;
+    while (((uint64_t)1 << log2cap) < 2 * ((uint64_t)iters_per_tree + 2)) ++log2cap;
+    std::vector<Slot> pool((size_t)W << log2cap);
+    std::memset(pool.data(), 0, pool.size() * sizeof(Slot));
+    std::vector<double> ln(iters_per_tree + 4);
+    ln[0] = 0.0;
+    for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
+    std::vector<uint64_t> v(64), s2(64), a(64), it(W);
+    Game::Prepared prepared;
+    uint64_t prep_scratch[Game::kHandWords];
+    Game::prepare((const Game::Root*)root, &prepared, prep_scratch);
+    SearchParams P;
+    std::memset(&P, 0, sizeof P);
+    P.prepared = &prepared; P.n_positions = 1; P.trees = W; P.trees_total = W; P.iterations = (uint64_t)iters_per_tree * W;
+    P.seed = seed; P.exploration = 0.7; P.pool = pool.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
+    P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
+    P.visits = v.data(); P.score2 = s2.data(); P.avail = a.data(); P.iters_done = it.data();
+    P.tree_thresh = g_thresh; P.tree_period = g_period; P.sched_mode = g_mode; P.sched_split_min = g_split;
+    std::vector<std::unique_ptr<L>> lanes;
+    std::vector<std::vector<uint64_t>> scratch(W, std::vector<uint64_t>(Game::kHandWords));
+    std::vector<std::vector<uint32_t>> ring(W, std::vector<uint32_t>(LaneRng::kRingWords)), path(W, std::vector<uint32_t>(Game::kMaxDepth));
+    for (int i = 0; i < W; ++i) {
+        lanes.emplace_back(new L(P));
+        L& l = *lanes.back();
+        l.path = path[i].data();
+        l.g.bind(scratch[i].data(), 1);
+        l.done = 0; l.deadline = 0; l.first_iteration = 0; l.root_children = Game::Mask::none();
+        l.prep = &prepared;
+        l.tree.bind(pool.data() + ((size_t)i << log2cap), log2cap);
+        l.tree.init_root();
+        l.rng.init(seed, 0, i, ring[i].data(), 1);
+        l.quota = iters_per_tree;
+        l.start_iteration();
+    }
+    for (int i = 0; i < 9; ++i) stats[i] = 0;
+    Schedule sched;
+    sched.init(P);
+    for (uint32_t pass = 0;; ++pass) {
+        L::Wants w[W];
+        uint32_t nc = 0, nm = 0, nt = 0, alive = 0;
+        for (int i = 0; i < W; ++i) {
+            alive += lanes[i]->phase != kDone;
+            w[i] = lanes[i]->classify();
+            nc += w[i].chance; nm += w[i].move; nt += w[i].tree;
+        }
+        if (!alive) break;
+        const PassPlan plan = sched.plan_pass(nc, nm, nt, pass);
+        stats[0]++;
+        if (plan.chance && plan.move) stats[3]++; else if (plan.chance) stats[1]++; else if (plan.move) stats[2]++;
+        if (plan.tree) { stats[4]++; stats[7] += nt; }
+        if (plan.chance) stats[5] += nc;
+        if (plan.move) stats[6] += nm;
+        for (int i = 0; i < W; ++i) lanes[i]->act(w[i], plan, pass, i);
+    }
+    for (int i = 0; i < W; ++i) stats[8] += lanes[i]->done;
+}
 
 uint32_t emu_playout(uint32_t game, const void* root, uint64_t seed, uint32_t pos, uint32_t iteration)
 {
