@@ -146,6 +146,11 @@ int ismcts_set_stream(ismcts_ctx* ctx, void* cuda_stream);
  * all devices.  Time mode (iterations == 0): every tree iterates until
  * `time_ns` nanoseconds have passed on the device clock (utility.h:51-60).
  */
+/* Tree parallelisation (TreeParallel, execution.h:169-179): the `trees` trees of a position are ONE
+ * shared tree searched by `lanes` iterations in flight with virtual loss; lanes in bits 8..23. */
+#define ISMCTS_FLAG_SHARED_TREE 1u
+#define ISMCTS_FLAG_LANES_SHIFT 8
+
 typedef struct ismcts_search_desc {
     uint32_t game;          /* ISMCTS_GAME_* */
     uint32_t solver;        /* ISMCTS_SOLVER_* (sosolver.h / mosolver.h) */
@@ -161,7 +166,7 @@ typedef struct ismcts_search_desc {
     double exploration;     /* UCB1 exploration constant (ucb1.h:65-67), default 0.7 */
     uint32_t dump_tree;     /* 0xffffffff = none; else local tree index (of position 0..) to dump:
                                dump index = position * trees + tree */
-    uint32_t flags;         /* reserved, 0 */
+    uint32_t flags;         /* 0 (ISMCTS_FLAG_*) */
 } ismcts_search_desc;
 
 /* One tree node as the reference keeps it (tree/node.h:113-118, ucb1.h:50-51),
@@ -182,8 +187,8 @@ typedef struct ismcts_search_out {
      * summed over this call's trees — RootParallel::compileVisitCounts
      * (execution.h:219-231) plus the reward and availability sums. */
     uint64_t* visits;       /* [n_positions * stride] */
-    uint64_t* score2;       /* [n_positions * stride], 2*score */
-    uint64_t* avail;        /* [n_positions * stride] */
+    uint64_t* score2;       /* [n_positions * stride], UCB1: 2*score; EXP3: score (exp3.h:45-48) in 48.16 fixed point */
+    uint64_t* avail;        /* [n_positions * stride], UCB1: availability; EXP3: probability in 32.32 fixed point */
     uint64_t* iterations_done; /* [n_positions * trees]: iterations each tree ran */
     uint32_t* best_move;    /* [n_positions]: first maximum of visits in ascending move order
                                (execution.h:209-216); 0xffffffff when the root is terminal */
@@ -211,6 +216,11 @@ int ismcts_synchronize(ismcts_ctx* ctx);
  * as node records in creation order. */
 int ismcts_dump_tree(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes,
                      uint32_t capacity, uint32_t* count);
+
+/* Same for MO-ISMCTS searches: the tree of `player` (mosolver.h:31-34 keeps one tree per player;
+ * ismcts_dump_tree reads the one that decides, the tree of the root's player to move). */
+int ismcts_dump_tree_of(ismcts_ctx* ctx, uint32_t dump_index, uint32_t player, ismcts_node_rec* nodes,
+                        uint32_t capacity, uint32_t* count);
 
 /* ------------------------------------------------------------------ playouts
  * Determinise + uniform random rollout only (SolverBase::simulate,

@@ -24,7 +24,7 @@ EXPORTS = [
     "ismcts_kw_deal", "ismcts_kw_legal", "ismcts_kw_apply", "ismcts_kw_result2",
     "ismcts_mnk_init", "ismcts_mnk_legal", "ismcts_mnk_apply", "ismcts_mnk_result2",
     "ismcts_create", "ismcts_destroy", "ismcts_last_error", "ismcts_set_stream",
-    "ismcts_search", "ismcts_search_device", "ismcts_synchronize", "ismcts_dump_tree",
+    "ismcts_search", "ismcts_search_device", "ismcts_synchronize", "ismcts_dump_tree", "ismcts_dump_tree_of",
     "ismcts_playouts", "ismcts_launch_count", "ismcts_version",
 ]
 
@@ -111,6 +111,7 @@ def load_library() -> C.CDLL:
     L.ismcts_search_device.argtypes = [vp, C.POINTER(SearchDesc), vp, vp, vp, vp, vp]
     L.ismcts_synchronize.argtypes = [vp]
     L.ismcts_dump_tree.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
+    L.ismcts_dump_tree_of.argtypes = [vp, u32, u32, vp, u32, C.POINTER(u32)]
     L.ismcts_playouts.argtypes = [vp, u32, vp, u32, u32, u64, vp]
     L.ismcts_launch_count.restype = u64
     L.ismcts_launch_count.argtypes = [vp]
@@ -204,10 +205,15 @@ class Engine:
                                                   C.c_void_p(d_visits), C.c_void_p(d_score2),
                                                   C.c_void_p(d_avail), C.c_void_p(d_iters)))
 
-    def dump_tree(self, index: int, capacity: int) -> np.ndarray:
+    def dump_tree(self, index: int, capacity: int, player: int | None = None) -> np.ndarray:
+        """Node records of tree `index` of the last search (MO: the tree of `player`, default the
+        root's player to move), in creation order."""
         nodes = np.zeros(capacity, dtype=NODE_DTYPE)
         n = C.c_uint32(0)
-        self._check(self.lib.ismcts_dump_tree(self.ctx, index, nodes.ctypes.data, capacity, C.byref(n)))
+        if player is None:
+            self._check(self.lib.ismcts_dump_tree(self.ctx, index, nodes.ctypes.data, capacity, C.byref(n)))
+        else:
+            self._check(self.lib.ismcts_dump_tree_of(self.ctx, index, player, nodes.ctypes.data, capacity, C.byref(n)))
         return nodes[:n.value].copy()
 
     def playouts(self, game: int, roots: np.ndarray, n_positions: int, per_position: int, seed: int) -> np.ndarray:

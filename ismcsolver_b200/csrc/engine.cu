@@ -1,8 +1,9 @@
 // engine.cu — CUDA kernels (sm_100a) and the C ABI of include/ismcts_b200.h.
 //
 // Kernel map (reference symbols in SURVEY.md section 8a):
-//   so_root_parallel_kernel<Game>  a1,a3-a10,a12-a15  one thread = one SO-ISMCTS tree
-//   playout_kernel<Game>           a3-a6,a8           determinise + rollout only
+//   prepare_kernel<Game>                       a3 (set-up)   root record -> the register image iterations start from
+//   search_kernel<Game, Slot, kind, occupancy> a1-a15        one lane = one SO tree / one set of MO trees
+//   playout_kernel<Game>                       a3-a6,a8      determinise + rollout only
 // No tensor cores are involved: the path has no dense contraction; it is
 // bound by SM instruction issue.
 #include "lane_search.cuh"
@@ -33,19 +34,6 @@ constexpr size_t block_smem()
     return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + LaneRng::kRingWords * sizeof(uint32_t));
 }
 
-// kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
-// for warps per scheduler; the variants are instantiated below and chosen per game at launch.
-template <class Game, int kMinBlocks>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) so_root_parallel_kernel(SearchParams P)
-{
-    extern __shared__ uint64_t smem[];
-    uint64_t* scratch = smem + threadIdx.x;
-    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
-    uint32_t path[Game::kMaxDepth];
-    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    lane_tree_search<Game>(P, gtid, gtid < P.n_positions * P.trees, scratch, kBlock, ring, kBlock, path);
-}
-
 // Root records -> the register image every iteration starts from (one thread per position).
 template <class Game>
 __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::Prepared* prepared, uint32_t n)
@@ -54,6 +42,19 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
     if (i >= n) return;
     uint64_t scratch[Game::kHandWords];
     Game::prepare(roots + i, prepared + i, scratch);
+}
+
+// kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
+// for warps per scheduler.
+template <class Game, class Slot, uint32_t kKind, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams P)
+{
+    extern __shared__ uint64_t smem[];
+    uint64_t* scratch = smem + threadIdx.x;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
+    uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    lane_tree_search<Game, Slot, kKind>(P, gtid, gtid < P.n_positions * P.trees, scratch, kBlock, ring, kBlock, path);
 }
 
 template <class Game>
@@ -89,15 +90,15 @@ struct ismcts_ctx {
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
 
-    // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD override
+    // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD /
+    // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT override
     uint32_t tree_thresh = 12, tree_period = 32;
-    uint32_t sched_mode = 0, sched_split_min = 8; // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT
-    int min_blocks = 8;          // resident CTAs per SM the search kernel is compiled for; ISMCTS_MIN_BLOCKS
+    uint32_t sched_mode = 0, sched_split_min = 8;
+    int min_blocks = 8;          // resident CTAs per SM the SO/UCB1 Knockout Whist kernel is compiled for; ISMCTS_MIN_BLOCKS
 
     // geometry of the last search (for ismcts_dump_tree)
-    uint32_t last_log2cap = 0;
-    uint32_t last_trees_launched = 0;
-    uint32_t last_game = 0;
+    uint32_t last_log2cap = 0, last_lanes = 0, last_game = 0, last_solver = 0, last_policy = 0;
+    std::vector<uint8_t> last_root_player; // per position
 };
 
 static thread_local std::string g_create_error;
@@ -127,7 +128,7 @@ static int ensure(ismcts_ctx* ctx, T*& ptr, size_t& have, size_t need)
 
 extern "C" {
 
-const char* ismcts_version(void) { return "ismcsolver_b200 0.1 (sm_100a)"; }
+const char* ismcts_version(void) { return "ismcsolver_b200 0.2 (sm_100a)"; }
 
 size_t ismcts_state_size(uint32_t game)
 {
@@ -160,12 +161,12 @@ int ismcts_create(int device, ismcts_ctx** out)
                                                       cudaGetErrorString(cudaGetLastError()));
     }
     ctx->stream = ctx->own_stream;
-    if (const char* e = std::getenv("ISMCTS_TREE_THRESH")) ctx->tree_thresh = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("ISMCTS_TREE_PERIOD")) ctx->tree_period = std::max(1, std::atoi(e));
+    if (const char* v = std::getenv("ISMCTS_TREE_THRESH")) ctx->tree_thresh = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("ISMCTS_TREE_PERIOD")) ctx->tree_period = std::max(1, std::atoi(v));
     while (ctx->tree_period & (ctx->tree_period - 1)) ++ctx->tree_period; // a power of two
-    if (const char* e = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(e);
-    if (const char* e = std::getenv("ISMCTS_SCHED_MODE")) ctx->sched_mode = (uint32_t)std::atoi(e);
-    if (const char* e = std::getenv("ISMCTS_SCHED_SPLIT")) ctx->sched_split_min = (uint32_t)std::atoi(e);
+    if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(v);
+    if (const char* v = std::getenv("ISMCTS_SCHED_MODE")) ctx->sched_mode = (uint32_t)std::atoi(v);
+    if (const char* v = std::getenv("ISMCTS_SCHED_SPLIT")) ctx->sched_split_min = (uint32_t)std::atoi(v);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -175,7 +176,8 @@ void ismcts_destroy(ismcts_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared); cudaFree(ctx->out); cudaFree(ctx->play_out);
+    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
+    cudaFree(ctx->out); cudaFree(ctx->play_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -205,11 +207,6 @@ int ismcts_synchronize(ismcts_ctx* ctx)
 // search
 // ---------------------------------------------------------------------------
 
-static size_t slot_bytes(uint32_t game)
-{
-    return game == ISMCTS_GAME_KW ? sizeof(SlotT<KwGame::Mask>) : sizeof(SlotT<MnkGame::Mask>);
-}
-
 static uint32_t ceil_log2(uint64_t x)
 {
     uint32_t l = 0;
@@ -217,12 +214,26 @@ static uint32_t ceil_log2(uint64_t x)
     return l;
 }
 
+static size_t slot_bytes(uint32_t game, uint32_t policy)
+{
+    if (game == ISMCTS_GAME_KW)
+        return policy == ISMCTS_POLICY_UCB1 ? sizeof(SlotUcb<KwGame::Mask>) : sizeof(SlotExp<KwGame::Mask>);
+    return policy == ISMCTS_POLICY_UCB1 ? sizeof(SlotUcb<MnkGame::Mask>) : sizeof(SlotExp<MnkGame::Mask>);
+}
+
+static uint32_t trees_per_lane(uint32_t game, uint32_t solver)
+{
+    if (solver == ISMCTS_SOLVER_SO) return 1;
+    return game == ISMCTS_GAME_KW ? KwGame::kMaxPlayers : MnkGame::kMaxPlayers;
+}
+
 static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
 {
     if (!ctx || !d) return ISMCTS_ERR_INVALID;
     if (d->game != ISMCTS_GAME_KW && d->game != ISMCTS_GAME_MNK) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
-    if (d->solver != ISMCTS_SOLVER_SO) return fail(ctx, ISMCTS_ERR_INVALID, "solver kind not available in this build");
-    if (d->policy != ISMCTS_POLICY_UCB1) return fail(ctx, ISMCTS_ERR_INVALID, "policy not available in this build");
+    if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
+    if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
+    if (d->flags != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
     if (d->n_positions == 0 || d->trees == 0) return fail(ctx, ISMCTS_ERR_INVALID, "n_positions and trees must be > 0");
     if ((uint64_t)d->n_positions * d->trees > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many trees");
     if (d->trees_total < d->tree_base + d->trees) return fail(ctx, ISMCTS_ERR_INVALID, "trees_total < tree_base + trees");
@@ -259,19 +270,36 @@ static int launch_prepare(ismcts_ctx* ctx, const void* d_roots, uint32_t n)
     return ISMCTS_OK;
 }
 
-template <class Game>
-static int launch_so(ismcts_ctx* ctx, SearchParams& P, const void* d_roots, uint32_t n_threads)
+template <class Game, class Slot, uint32_t kKind, bool kTuned>
+static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32_t grid)
 {
+    const size_t smem = block_smem<Game>();
+    if constexpr (kTuned) {
+        // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
+        switch (ctx->min_blocks) {
+        case 4: search_kernel<Game, Slot, kKind, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        case 5: search_kernel<Game, Slot, kKind, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        case 6: search_kernel<Game, Slot, kKind, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        default: search_kernel<Game, Slot, kKind, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        }
+    } else {
+        search_kernel<Game, Slot, kKind, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
+    }
+}
+
+template <class Game>
+static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_desc* d, const void* d_roots, uint32_t lanes)
+{
+    using Mask = typename Game::Mask;
     int rc = launch_prepare<Game>(ctx, d_roots, P.n_positions);
     if (rc) return rc;
     P.prepared = ctx->prepared;
-    const uint32_t grid = (n_threads + kBlock - 1) / kBlock;
-    switch (ctx->min_blocks) {
-    case 8: so_root_parallel_kernel<Game, 8><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
-    case 6: so_root_parallel_kernel<Game, 6><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
-    case 5: so_root_parallel_kernel<Game, 5><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
-    default: so_root_parallel_kernel<Game, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P); break;
-    }
+    const uint32_t grid = (lanes + kBlock - 1) / kBlock;
+    const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
+    if (so && ucb) launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+    else if (so) launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
+    else if (ucb) launch_search_variant<Game, SlotUcb<Mask>, kMO, false>(ctx, P, grid);
+    else launch_search_variant<Game, SlotExp<Mask>, kMO, false>(ctx, P, grid);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return ISMCTS_OK;
@@ -285,26 +313,28 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     if (!d_roots || !d_visits || !d_score2 || !d_avail || !d_iters) return fail(ctx, ISMCTS_ERR_INVALID, "null device pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 
-    const uint32_t n_threads = d->n_positions * d->trees;
+    const uint32_t lanes = d->n_positions * d->trees;
     const uint32_t stride = ismcts_move_stride(d->game);
+    const uint32_t per_lane = trees_per_lane(d->game, d->solver);
+    const size_t slot = slot_bytes(d->game, d->policy);
 
-    // nodes per tree: one per iteration plus the root
+    // nodes per lane: every iteration adds at most one node to each of its trees
     uint64_t max_it;
     uint32_t log2cap;
     if (d->iterations > 0) {
         max_it = d->iterations / d->trees_total + 1;
-        log2cap = std::max<uint32_t>(4, ceil_log2(2 * (max_it + 1)));
+        log2cap = std::max<uint32_t>(4, ceil_log2(2 * per_lane * (max_it + 1)));
         if (log2cap > kMaxSlotsLog2) return fail(ctx, ISMCTS_ERR_CAPACITY, "too many iterations per tree for the node pool");
     } else {
-        // time mode: the iteration count is unknown; give every tree an equal share of the free memory
+        // time mode: the iteration count is unknown; give every lane an equal share of the free memory
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
         const size_t budget = (free_b + ctx->pool_bytes) / 2;
         log2cap = 4;
-        while (log2cap < 21 && ((size_t)n_threads << (log2cap + 1)) * slot_bytes(d->game) <= budget) ++log2cap;
-        max_it = ((uint64_t)1 << (log2cap - 1)) - 1;
+        while (log2cap < 21 && ((size_t)lanes << (log2cap + 1)) * slot <= budget) ++log2cap;
+        max_it = (((uint64_t)1 << (log2cap - 1)) - 1) / per_lane;
     }
-    const size_t pool_need = ((size_t)n_threads << log2cap) * slot_bytes(d->game);
+    const size_t pool_need = ((size_t)lanes << log2cap) * slot;
     {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -322,58 +352,91 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
 
     SearchParams P;
+    std::memset(&P, 0, sizeof P);
     P.n_positions = d->n_positions; P.trees = d->trees; P.trees_total = d->trees_total;
     P.tree_base = d->tree_base; P.pos_base = d->pos_base;
     P.iterations = d->iterations; P.time_ns = d->time_ns; P.seed = d->seed;
     P.exploration = d->exploration < 0.0 ? 0.0 : d->exploration; // UCB1 ctor clamps, ucb1.h:65-67
     P.pool = ctx->pool; P.log2cap = log2cap;
-    P.max_nodes = (uint32_t)std::min<uint64_t>(((uint64_t)1 << (log2cap - 1)), ctx->ln_count - 2);
+    P.max_nodes = (uint32_t)std::min<uint64_t>(((uint64_t)1 << (log2cap - 1)), (uint64_t)per_lane * (ctx->ln_count - 2));
     P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
     P.playout_out = nullptr; P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
     P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
 
-    ctx->last_log2cap = log2cap; ctx->last_trees_launched = n_threads; ctx->last_game = d->game;
+    ctx->last_log2cap = log2cap; ctx->last_lanes = lanes; ctx->last_game = d->game;
+    ctx->last_solver = d->solver; ctx->last_policy = d->policy;
 
-    if (d->game == ISMCTS_GAME_KW) return launch_so<KwGame>(ctx, P, d_roots, n_threads);
-    return launch_so<MnkGame>(ctx, P, d_roots, n_threads);
+    if (d->game == ISMCTS_GAME_KW) return launch_search<KwGame>(ctx, P, d, d_roots, lanes);
+    return launch_search<MnkGame>(ctx, P, d, d_roots, lanes);
 }
 
-template <class Mask>
-static int dump_tree_t(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count)
+// One lane's table -> node records of the tree rooted at slot `root`, in creation order.
+template <class Slot>
+static int dump_tree_t(ismcts_ctx* ctx, uint32_t lane, uint32_t root, ismcts_node_rec* nodes, uint32_t capacity,
+                       uint32_t* count)
 {
-    using Slot = SlotT<Mask>;
     const size_t cap = (size_t)1 << ctx->last_log2cap;
     std::vector<Slot> table(cap);
-    CUDA_TRY(ctx, cudaMemcpy(table.data(), (const Slot*)ctx->pool + (size_t)dump_index * cap, cap * sizeof(Slot),
+    CUDA_TRY(ctx, cudaMemcpy(table.data(), (const Slot*)ctx->pool + (size_t)lane * cap, cap * sizeof(Slot),
                              cudaMemcpyDeviceToHost));
-    // slots -> creation order
-    uint32_t n = 0;
-    for (const Slot& s : table) if (s.key != 0) ++n;
-    *count = n;
-    if (n > capacity) return fail(ctx, ISMCTS_ERR_CAPACITY, "dump buffer too small");
+    const uint32_t n_roots = trees_per_lane(ctx->last_game, ctx->last_solver);
+    // the root slot of every node (follow the parent links), then the members of the wanted tree by creation index
+    auto root_of = [&](size_t i) {
+        while (i >= n_roots) i = slot_parent_of(table[i].key);
+        return (uint32_t)i;
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> members; // (created, slot)
     for (size_t i = 0; i < cap; ++i) {
-        const Slot& s = table[i];
-        if (s.key == 0) continue;
-        if (s.created >= n) return fail(ctx, ISMCTS_ERR_CUDA, "corrupt node pool");
-        ismcts_node_rec& r = nodes[s.created];
+        if (table[i].key == 0) continue;
+        if (i < n_roots ? i == root : root_of(i) == root) members.emplace_back(i < n_roots ? 0u : table[i].created, (uint32_t)i);
+    }
+    std::sort(members.begin(), members.end());
+    *count = (uint32_t)members.size();
+    if (members.size() > capacity) return fail(ctx, ISMCTS_ERR_CAPACITY, "dump buffer too small");
+    std::vector<uint32_t> index_of_slot(cap, 0);
+    for (size_t k = 0; k < members.size(); ++k) index_of_slot[members[k].second] = (uint32_t)k;
+    for (size_t k = 0; k < members.size(); ++k) {
+        const Slot& s = table[members[k].second];
+        ismcts_node_rec& r = nodes[k];
         if (s.key == kRootKey) { r.parent = 0; r.move = 0; }
-        else { r.parent = table[slot_parent_of(s.key)].created; r.move = slot_move_of(s.key); }
-        r.player = s.player; r.visits = s.visits; r.score2 = s.score2; r.avail = s.avail;
-        r.score = 0.5 * (double)s.score2; r.prob = 1.0;
+        else { r.parent = index_of_slot[slot_parent_of(s.key)]; r.move = slot_move_of(s.key); }
+        r.player = s.player; r.visits = s.visits;
+        if constexpr (Slot::kExp3) { r.score2 = 0; r.avail = 1; r.score = s.score; r.prob = s.prob; }
+        else { r.score2 = s.score2; r.avail = s.avail; r.score = 0.5 * (double)s.score2; r.prob = 1.0; }
     }
     return ISMCTS_OK;
+}
+
+extern "C" int ismcts_dump_tree_of(ismcts_ctx* ctx, uint32_t dump_index, uint32_t player, ismcts_node_rec* nodes,
+                                   uint32_t capacity, uint32_t* count)
+{
+    if (!ctx || !nodes || !count) return ISMCTS_ERR_INVALID;
+    if (dump_index >= ctx->last_lanes) return fail(ctx, ISMCTS_ERR_INVALID, "dump index out of range");
+    const uint32_t n_roots = trees_per_lane(ctx->last_game, ctx->last_solver);
+    if (ctx->last_solver == ISMCTS_SOLVER_SO) player = 0;
+    if (player >= n_roots) return fail(ctx, ISMCTS_ERR_INVALID, "player out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const bool ucb = ctx->last_policy == ISMCTS_POLICY_UCB1;
+    if (ctx->last_game == ISMCTS_GAME_KW)
+        return ucb ? dump_tree_t<SlotUcb<KwGame::Mask>>(ctx, dump_index, player, nodes, capacity, count)
+                   : dump_tree_t<SlotExp<KwGame::Mask>>(ctx, dump_index, player, nodes, capacity, count);
+    return ucb ? dump_tree_t<SlotUcb<MnkGame::Mask>>(ctx, dump_index, player, nodes, capacity, count)
+               : dump_tree_t<SlotExp<MnkGame::Mask>>(ctx, dump_index, player, nodes, capacity, count);
 }
 
 extern "C" int ismcts_dump_tree(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes, uint32_t capacity,
                                 uint32_t* count)
 {
-    if (!ctx || !nodes || !count) return ISMCTS_ERR_INVALID;
-    if (dump_index >= ctx->last_trees_launched) return fail(ctx, ISMCTS_ERR_INVALID, "dump index out of range");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->last_game == ISMCTS_GAME_KW) return dump_tree_t<KwGame::Mask>(ctx, dump_index, nodes, capacity, count);
-    return dump_tree_t<MnkGame::Mask>(ctx, dump_index, nodes, capacity, count);
+    if (!ctx) return ISMCTS_ERR_INVALID;
+    uint32_t player = 0;
+    if (ctx->last_solver == ISMCTS_SOLVER_MO && ctx->last_lanes) {
+        // the tree that decides: the one of the root's player to move (mosolver.h:42-46)
+        const size_t pos = dump_index / (ctx->last_lanes / std::max<size_t>(1, ctx->last_root_player.size()));
+        if (pos < ctx->last_root_player.size()) player = ctx->last_root_player[pos];
+    }
+    return ismcts_dump_tree_of(ctx, dump_index, player, nodes, capacity, count);
 }
 
 extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const void* roots, ismcts_search_out* out)
@@ -383,21 +446,29 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     if (!roots || !out || !out->visits) return fail(ctx, ISMCTS_ERR_INVALID, "null host pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const uint32_t stride = ismcts_move_stride(d->game);
-    const size_t root_bytes = (size_t)d->n_positions * ismcts_state_size(d->game);
+    const size_t state = ismcts_state_size(d->game);
+    const size_t root_bytes = (size_t)d->n_positions * state;
     const size_t per_arr = (size_t)d->n_positions * stride;
-    const size_t n_trees = (size_t)d->n_positions * d->trees;
+    const size_t n_lanes = (size_t)d->n_positions * d->trees;
     rc = ensure(ctx, ctx->roots, ctx->roots_bytes, root_bytes);
     if (rc) return rc;
-    rc = ensure(ctx, ctx->out, ctx->out_bytes, (3 * per_arr + n_trees) * sizeof(uint64_t));
+    rc = ensure(ctx, ctx->out, ctx->out_bytes, (3 * per_arr + n_lanes) * sizeof(uint64_t));
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->roots, roots, root_bytes, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t* dv = ctx->out; uint64_t* ds = dv + per_arr; uint64_t* da = ds + per_arr; uint64_t* di = da + per_arr;
     rc = ismcts_search_device(ctx, d, ctx->roots, dv, ds, da, di);
     if (rc) return rc;
+    // who moves at each root (for dumps of MO searches)
+    ctx->last_root_player.resize(d->n_positions);
+    for (uint32_t p = 0; p < d->n_positions; ++p) {
+        const uint8_t* rec = (const uint8_t*)roots + p * state;
+        ctx->last_root_player[p] = d->game == ISMCTS_GAME_KW ? ((const ismcts_kw_state*)rec)->player
+                                                            : ((const ismcts_mnk_state*)rec)->player;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(out->visits, dv, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (out->score2) CUDA_TRY(ctx, cudaMemcpyAsync(out->score2, ds, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (out->avail) CUDA_TRY(ctx, cudaMemcpyAsync(out->avail, da, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out->iterations_done) CUDA_TRY(ctx, cudaMemcpyAsync(out->iterations_done, di, n_trees * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out->iterations_done) CUDA_TRY(ctx, cudaMemcpyAsync(out->iterations_done, di, n_lanes * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (out->best_move) {
         // RootParallel::bestMove, execution.h:209-216: first maximum in ascending move order

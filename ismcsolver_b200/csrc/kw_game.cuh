@@ -46,6 +46,8 @@ struct KwGame {
     static constexpr uint32_t kGameId = ISMCTS_GAME_KW;
     static constexpr uint32_t kMoveStride = 64;
     static constexpr uint32_t kHandWords = ISMCTS_KW_MAX_PLAYERS; // 8-byte words of per-thread scratch
+    static constexpr uint32_t kMaxPlayers = ISMCTS_KW_MAX_PLAYERS;
+    static constexpr uint32_t kMaxLegal = ISMCTS_KW_CARDS;
     static constexpr uint32_t kMaxDepth = 208;  // plies are bounded by 6 + players * 28 (gametest.cpp:166-178)
     using Mask = Mask64;
     using Root = ismcts_kw_state;
@@ -171,6 +173,14 @@ struct KwGame {
     }
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
+    ISMCTS_DEV static uint32_t root_player(const Prepared* p) { return p->player; }
+    // players(), knockoutwhist.cpp:90-93, of the root position as a bit set
+    ISMCTS_DEV static uint32_t root_players(const Prepared* p)
+    {
+        uint32_t out = 0;
+        for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q) out |= ((p->alive4 >> (4 * q)) & 1u) << q;
+        return out;
+    }
     ISMCTS_DEV bool chance_pending() const { return mode != kPlay; }
 
     // nextPlayer, knockoutwhist.cpp:83-88: next id, cyclically, that is still in.

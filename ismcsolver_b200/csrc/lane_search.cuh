@@ -111,53 +111,95 @@ struct Schedule {
     }
 };
 
-// kTree = false: determinise + rollout only (SolverBase::simulate after
-// cloneAndRandomise), one iteration per lane, no tree — the playout kernel.
-template <class Game, bool kTree>
+// Solver kinds of a lane.  kPlayout: determinise + rollout only
+// (SolverBase::simulate after cloneAndRandomise), one iteration per lane, no tree.
+enum LaneKind : uint32_t { kPlayout = 0, kSO = 1, kMO = 2 };
+
+template <class Game, class SlotType, uint32_t kKind>
 struct Lane {
     using Mask = typename Game::Mask;
     using Prepared = typename Game::Prepared;
-    using Slot = SlotT<Mask>;
+    using Slot = SlotType;
+    static constexpr bool kTree = kKind != kPlayout;
+    static constexpr bool kMulti = kKind == kMO;
+    static constexpr bool kExp3 = Slot::kExp3;
+    // MO-ISMCTS: one tree per player (mosolver.h:31-34); the root of player p's tree is slot p
+    static constexpr uint32_t kTrees = kMulti ? Game::kMaxPlayers : 1;
 
     const SearchParams& P;
     Game g;
     LaneRng rng;
-    TreePool<Mask> tree;
+    TreePool<Slot> tree;
     const Prepared* prep;    // this lane's position, ready to start an iteration from
-    uint32_t* path;          // slot | player << 24 of the nodes on the current descent
-    uint32_t phase, node, depth, plies;
-    Mask node_children, root_children;
-    uint64_t done, quota, deadline;
+    uint32_t* path;          // SO + UCB1: slot | player << 24 of the nodes on the current descent
+    uint32_t phase, depth, plies;
+    uint32_t node[kTrees];   // the cursor of every tree
+    Mask node_children[kTrees];
+    Mask root_children;      // SO: children of the root (saves its reload every iteration)
+    uint32_t done, quota;
+    uint64_t deadline;
     uint32_t first_iteration; // index of this lane's first iteration (playout kernel: the playout id)
+    uint32_t tree_players;    // MO: bit p = player p has a tree (the players of the root position)
 
     ISMCTS_DEV explicit Lane(const SearchParams& p) : P(p) {}
 
     ISMCTS_DEV void start_iteration()
     {
-        rng.begin_iteration(first_iteration + (uint32_t)done);
-        g.start(prep);                                        // cloneAndRandomise, sosolver.h:46
-        node = 0; depth = 0; plies = 0;
-        node_children = root_children;
+        rng.begin_iteration(first_iteration + done);
+        g.start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
+        depth = 0; plies = 0;
+        if (kMulti) {
+            for (uint32_t t = 0; t < kTrees; ++t) { node[t] = t; node_children[t] = load_slot(&tree.slots[t]).child_mask; }
+        } else {
+            node[0] = 0; node_children[0] = root_children;
+        }
         phase = kTree ? kSelect : kRollout;
     }
 
     ISMCTS_DEV bool budget_left() const
     {
-        if (kTree && tree.count >= P.max_nodes) return false;
+        if (kTree && tree.count + kTrees > P.max_nodes) return false;
         return P.iterations > 0 || !kTree ? done < quota : global_timer_ns() < deadline;
     }
 
-    // The game is over (validMoves() empty): backPropagate, solverbase.h:45-51;
-    // Node::update, node.h:74-80 (the root is never updated); UCBNode::updateData,
-    // ucb1.h:53-56.  One 64-bit reduction per node on the path: visits += 1 in
-    // the low word, score2 += 2 * reward in the high word.  Then the next iteration.
+    // Node::update + updateData of one node (node.h:74-80; ucb1.h:53-56; exp3.h:45-48).
+    ISMCTS_DEV void update_node(uint32_t slot, uint32_t who, double prob)
+    {
+        const uint32_t r2 = g.result2(who);
+        if (!kExp3) {
+            // one 64-bit reduction: visits += 1 in the low word, score2 += 2 * reward in the high word
+            red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[slot]), 1u | ((uint64_t)r2 << 32));
+        } else {
+            update_exp(&tree.slots[slot], r2, prob);
+        }
+    }
+    template <class S>
+    ISMCTS_DEV static void update_exp(S* s, uint32_t r2, double prob)
+    {
+        if constexpr (S::kExp3) {
+            s->visits += 1;
+            s->score = ISMCTS_DADD(s->score, ISMCTS_DDIV(ISMCTS_DMUL((double)r2, 0.5), prob));
+        }
+    }
+
+    // The game is over (validMoves() empty): backPropagate, solverbase.h:45-51 /
+    // mosolver.h:97-101 — every node from the cursor up to but excluding the root.
+    // Then the next iteration.
     ISMCTS_DEV void finish_iteration(uint32_t gtid)
     {
         if (kTree) {
-            for (uint32_t i = 0; i < depth; ++i) {
-                const uint32_t e = path[i];
-                const uint64_t delta = 1u | ((uint64_t)g.result2(e >> 24) << 32);
-                red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[e & 0xFFFFFFu]), delta);
+            if (!kMulti && !kExp3) {
+                for (uint32_t i = 0; i < depth; ++i) update_node(path[i] & 0xFFFFFFu, path[i] >> 24, 1.0);
+            } else {
+                // walk the parent links (the key of a node holds its parent's slot)
+                for (uint32_t t = 0; t < kTrees; ++t) {
+                    uint32_t n = node[t];
+                    while (n >= tree.roots) {
+                        const Slot s = load_slot(&tree.slots[n]);
+                        update_node(n, s.player, slot_prob(s));
+                        n = slot_parent_of(s.key);
+                    }
+                }
             }
         } else {
             P.playout_out[gtid] = (g.outcome() & 0xFFu) | ((plies & 0xFFFu) << 8) | ((rng.consumed() & 0xFFFu) << 20);
@@ -166,48 +208,107 @@ struct Lane {
         if (budget_left()) start_iteration(); else phase = kDone;
     }
 
-    // select + expand, sosolver.h:53-71, from the current node until a node is
-    // added, the game ends or a move triggers chance events (they are drained by
-    // the random micro-steps of the following passes, then the descent resumes).
+    template <class S> ISMCTS_DEV static double slot_prob(const S& s) { if constexpr (S::kExp3) return s.prob; else return 1.0; }
+
+    // Node::selectChild + UCB1::operator(), node.h:58-72, ucb1.h:69-76: every legal
+    // child becomes available, then the first maximum in creation order.
+    template <class S>
+    ISMCTS_DEV uint32_t select_child(uint32_t parent, const Mask& legal, S& chosen, uint32_t& chosen_move)
+    {
+        if constexpr (!S::kExp3) {
+            uint32_t best = 0;
+            double best_u = -1.0;
+            chosen.created = 0xFFFFFFFFu;
+            for (Mask rest = legal; rest.any();) {
+                const uint32_t move = rest.pop_lowest();
+                S c;
+                const uint32_t ci = tree.find(parent, move, c);
+                c.avail += 1;
+                tree.slots[ci].avail = c.avail;
+                const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[c.avail], P.exploration);
+                if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
+            }
+            return best;
+        } else {
+            // EXP3::operator(), exp3.h:57-95: p_i = eps_t + (1 - K eps_t) exp(eps_{t-1} s_i) / sum_j exp(eps_{t-1} s_j),
+            // stored in the nodes, then one sample.  Children are taken in ascending move order.
+            uint32_t idx[Game::kMaxLegal];
+            double val[Game::kMaxLegal];
+            uint32_t K = 0;
+            uint64_t t = 0;
+            double smax = 0.0;
+            for (Mask rest = legal; rest.any(); ++K) {
+                const uint32_t move = rest.pop_lowest();
+                S c;
+                idx[K] = tree.find(parent, move, c);
+                val[K] = c.score;
+                t += c.visits;
+                smax = (K == 0 || c.score > smax) ? c.score : smax;
+            }
+            const double lnK = P.ln_table[K];
+            const double e_t = ismcts_exp3_epsilon(K, lnK, (double)t);
+            const double e_tm1 = ismcts_exp3_epsilon(K, lnK, (double)(uint64_t)(t - 1));
+            double sum = 0.0;
+            for (uint32_t i = 0; i < K; ++i) {
+                val[i] = ismcts_det_exp(ISMCTS_DMUL(e_tm1, ISMCTS_DSUB(val[i], smax)));
+                sum = ISMCTS_DADD(sum, val[i]);
+            }
+            const double rest_mass = ISMCTS_DSUB(1.0, ISMCTS_DMUL((double)K, e_t));
+            const double x = ISMCTS_DMUL((double)rng.word(), 1.0 / 4294967296.0);
+            double cum = 0.0;
+            uint32_t pick = K - 1;
+            bool picked = false;
+            for (uint32_t i = 0; i < K; ++i) {
+                const double p = ISMCTS_DADD(e_t, ISMCTS_DDIV(ISMCTS_DMUL(rest_mass, val[i]), sum));
+                tree.slots[idx[i]].prob = p;                  // setProbability, exp3.h:84
+                cum = ISMCTS_DADD(cum, p);
+                if (!picked && x < cum) { pick = i; picked = true; }
+            }
+            chosen = load_slot(&tree.slots[idx[pick]]);
+            chosen_move = slot_move_of(chosen.key);
+            return idx[pick];
+        }
+    }
+
+    // select + expand (sosolver.h:53-71; mosolver.h:69-95) from the current cursor(s)
+    // until a node is added, the game ends or a move triggers chance events (they
+    // are drained by the random micro-steps of the following passes, then the
+    // descent resumes).  MO: the tree of the player to move decides, then the
+    // cursor of EVERY tree moves to the child for that move, which is created where
+    // it does not exist yet (findOrAddChild, node.h:50-56).
     ISMCTS_DEV void descend()
     {
         for (;;) {
             const Mask legal = g.legal();
             if (!legal.any()) return;                             // terminal: selectNode, solverbase.h:53-56
-            const Mask untried = legal.minus(node_children);      // untriedMoves, node.h:82-91
-            if (untried.any()) {                                  // expand, sosolver.h:63-71
-                const uint32_t move = untried.kth(rng.below(untried.count()));
-                const uint32_t who = g.current_player();          // newChild, solverbase.h:74-80: before the move
-                const Mask grown = node_children.with(move);
-                tree.slots[node].child_mask = grown;
-                if (node == 0) root_children = grown;
-                node = tree.insert(node, move, who);
-                path[depth++] = node | (who << 24);
-                g.step(move);
-                phase = kRollout;
-                return;
-            }
-            // Node::selectChild + UCB1::operator(), node.h:58-72, ucb1.h:69-76: every
-            // legal child becomes available, then the first maximum in creation order.
-            uint32_t best = 0, best_created = 0xFFFFFFFFu, best_move = 0, best_player = 0;
-            double best_u = -1.0;
-            Mask best_children = Mask::none();
-            for (Mask rest = legal; rest.any();) {
-                const uint32_t move = rest.pop_lowest();
-                Slot c;
-                const uint32_t ci = tree.find(node, move, c);
-                c.avail += 1;
-                tree.slots[ci].avail = c.avail;
-                const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[c.avail], P.exploration);
-                if (u > best_u || (u == best_u && c.created < best_created)) {
-                    best_u = u; best = ci; best_created = c.created; best_move = move; best_player = c.player;
-                    best_children = c.child_mask;
+            const uint32_t who = g.current_player();              // newChild, solverbase.h:74-80: before the move
+            const uint32_t a = kMulti ? who : 0;                  // the deciding tree
+            const Mask untried = legal.minus(node_children[a]);   // untriedMoves, node.h:82-91
+            const bool expand = untried.any();
+            uint32_t move = 0, chosen_slot = 0;
+            Slot chosen;
+            chosen.child_mask = Mask::none();
+            if (expand) move = untried.kth(rng.below(untried.count()));   // expand, sosolver.h:63-71
+            else chosen_slot = select_child(node[a], legal, chosen, move);
+            for (uint32_t t = 0; t < kTrees; ++t) {
+                if (kMulti && !((tree_players >> t) & 1u)) continue;
+                if (t == a && !expand) {
+                    node[t] = chosen_slot; node_children[t] = chosen.child_mask;
+                } else if (node_children[t].test(move)) {         // MO: the child exists in this tree
+                    Slot c;
+                    node[t] = tree.find(node[t], move, c);
+                    node_children[t] = c.child_mask;
+                } else {
+                    const Mask grown = node_children[t].with(move);
+                    tree.slots[node[t]].child_mask = grown;
+                    if (!kMulti && node[t] == 0) root_children = grown;
+                    node[t] = tree.insert(node[t], move, who, tree.count);
+                    node_children[t] = Mask::none();
                 }
             }
-            node = best;
-            node_children = best_children;
-            path[depth++] = node | (best_player << 24);
-            g.step(best_move);
+            if (!kMulti && !kExp3) path[depth++] = node[0] | (who << 24);
+            g.step(move);
+            if (expand) { phase = kRollout; return; }
             if (g.chance_pending()) return;
         }
     }
@@ -263,46 +364,56 @@ struct Lane {
     }
 };
 
-// The whole search of tree `gtid` of this launch (`valid` = false for the lanes
-// that only pad the last warp: they take part in the warp votes and do nothing).
-template <class Game>
+// The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees
+// (`valid` = false for the lanes that only pad the last warp: they take part in
+// the warp votes and do nothing).
+template <class Game, class Slot, uint32_t kKind>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
                                  uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
     using Mask = typename Game::Mask;
-    using Slot = SlotT<Mask>;
-    Lane<Game, true> L(P);
-    L.path = path;
-    L.g.bind(scratch, scratch_stride);
-    L.phase = kDone; L.done = 0; L.quota = 0; L.deadline = 0; L.first_iteration = 0;
-    L.root_children = Mask::none();
+    using L = Lane<Game, Slot, kKind>;
+    L lane(P);
+    lane.path = path;
+    lane.g.bind(scratch, scratch_stride);
+    lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
+    lane.root_children = Mask::none();
     uint32_t pos = 0;
     if (valid) {
         pos = gtid / P.trees;
         const uint32_t tree_global = P.tree_base + gtid % P.trees;
-        L.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
-        L.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)gtid << P.log2cap), P.log2cap);
-        L.tree.init_root();
-        L.rng.init(P.seed, P.pos_base + pos, tree_global, ring, ring_stride);
-        if (P.iterations > 0) L.quota = tree_iterations(P.iterations, P.trees_total, tree_global);
-        else L.deadline = global_timer_ns() + P.time_ns;   // time mode, utility.h:51-60
-        if (L.budget_left()) L.start_iteration();
+        lane.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
+        lane.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)gtid << P.log2cap), P.log2cap, L::kTrees);
+        lane.tree.init_roots();
+        lane.tree_players = Game::root_players(lane.prep);
+        lane.rng.init(P.seed, P.pos_base + pos, tree_global, ring, ring_stride);
+        if (P.iterations > 0) lane.quota = (uint32_t)tree_iterations(P.iterations, P.trees_total, tree_global);
+        else lane.deadline = global_timer_ns() + P.time_ns;   // time mode, utility.h:51-60
+        if (lane.budget_left()) lane.start_iteration();
     }
-    L.run(gtid);
+    lane.run(gtid);
     if (!valid) return;
-    P.iters_done[gtid] = L.done;
+    P.iters_done[gtid] = lane.done;
 
     // Root children -> per-position sums (RootParallel::compileVisitCounts, execution.h:219-231).
+    // MO: the tree of the root's player to move decides (mosolver.h:42-46).
+    const uint32_t root = kKind == kMO ? Game::root_player(lane.prep) : 0;
     uint64_t* v = P.visits + (size_t)pos * Game::kMoveStride;
     uint64_t* s = P.score2 + (size_t)pos * Game::kMoveStride;
     uint64_t* a = P.avail + (size_t)pos * Game::kMoveStride;
-    for (Mask rest = L.root_children; rest.any();) {
+    for (Mask rest = load_slot(&lane.tree.slots[root]).child_mask; rest.any();) {
         const uint32_t move = rest.pop_lowest();
         Slot c;
-        L.tree.find(0, move, c);
+        lane.tree.find(root, move, c);
         atomic_add_u64(v + move, c.visits);
-        atomic_add_u64(s + move, c.score2);
-        atomic_add_u64(a + move, c.avail);
+        if constexpr (!Slot::kExp3) {
+            atomic_add_u64(s + move, c.score2);
+            atomic_add_u64(a + move, c.avail);
+        } else {
+            // EXP3: fixed point, so that the sums do not depend on the order of the additions
+            atomic_add_u64(s + move, (uint64_t)(long long)llrint(c.score * 65536.0));
+            atomic_add_u64(a + move, (uint64_t)(long long)llrint(c.prob * 4294967296.0));
+        }
     }
 }
 
@@ -312,19 +423,19 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
                              uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride)
 {
     using Mask = typename Game::Mask;
-    Lane<Game, false> L(P);
-    L.path = nullptr;
-    L.g.bind(scratch, scratch_stride);
-    L.phase = kDone; L.done = 0; L.quota = 1; L.deadline = 0; L.first_iteration = 0;
-    L.root_children = Mask::none();
+    Lane<Game, SlotUcb<Mask>, kPlayout> lane(P);
+    lane.path = nullptr;
+    lane.g.bind(scratch, scratch_stride);
+    lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
+    lane.root_children = Mask::none();
     if (valid) {
         const uint32_t pos = gtid / per_position;
-        L.first_iteration = gtid % per_position;
-        L.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
-        L.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
-        L.start_iteration();
+        lane.first_iteration = gtid % per_position;
+        lane.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
+        lane.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
+        lane.start_iteration();
     }
-    L.run(gtid);
+    lane.run(gtid);
 }
 
 } // namespace ismcts

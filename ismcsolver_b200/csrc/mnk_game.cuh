@@ -17,6 +17,8 @@ struct MnkGame {
     static constexpr uint32_t kGameId = ISMCTS_GAME_MNK;
     static constexpr uint32_t kMoveStride = 256;
     static constexpr uint32_t kHandWords = 8; // stones[2][4]
+    static constexpr uint32_t kMaxPlayers = 2;
+    static constexpr uint32_t kMaxLegal = ISMCTS_MNK_MAX_CELLS;
     static constexpr uint32_t kMaxDepth = 256;
     using Mask = Mask256;
     using Root = ismcts_mnk_state;
@@ -36,6 +38,8 @@ struct MnkGame {
     }
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
+    ISMCTS_DEV static uint32_t root_player(const Prepared* p) { return p->player; }
+    ISMCTS_DEV static uint32_t root_players(const Prepared*) { return 3u; } // players(), mnkgame.cpp:76-79
     ISMCTS_DEV bool chance_pending() const { return false; }    // perfect information, no chance events
     // cloneAndRandomise is a plain copy, mnkgame.cpp:34-37
     ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t*) { *out = *r; }

@@ -76,10 +76,13 @@ struct LaneRng {
     ISMCTS_DEV bool low() const { return count < 4; }   // room for one more block
     ISMCTS_DEV uint32_t consumed() const { return next_block * 4 - count; } // = d, words handed out
 
-    // Next 32-bit word of the stream; there is always one waiting (the caller
-    // refills whenever low() at least once per four words).
+    // Next 32-bit word of the stream.  The search loop refills all lanes together
+    // whenever low(), at least once per four passes, so a word is normally waiting;
+    // a lane that draws several words in one pass (an EXP3 descent draws one per
+    // level) generates the block it needs here.
     ISMCTS_DEV uint32_t word()
     {
+        if (count == 0) refill();
         const uint32_t w = ring[(head & (kRingWords - 1)) * stride];
         ++head; --count;
         return w;

@@ -1,18 +1,21 @@
-// pool.cuh — flat node pool of one search tree in HBM.
+// pool.cuh — flat node pool of the search tree(s) of one lane, in HBM.
 //
 // Replaces the reference's pointer tree (tree/node.h:113-118: parent pointer,
 // vector<unique_ptr<Node>> children, one std::mutex per node; UCBNode adds
-// atomic<double> score and atomic_uint available, ucb1.h:50-51).  A tree is an
+// atomic<double> score and atomic_uint available, ucb1.h:50-51; EXPNode adds
+// atomic<double> probability and score, exp3.h:42-43).  A pool is an
 // open-addressing hash table of fixed-size slots keyed by (parent slot, move):
 // finding the child for a move is one slot load (one or two 32-byte DRAM
 // sectors) instead of a walk over the child vector (node.h:58-72,
 // O(children x legal)), and the per-node `child_mask` answers untriedMoves
-// (node.h:82-91) with one AND.
+// (node.h:82-91) with one AND.  The first `roots` slots are the root nodes: one
+// for SO-ISMCTS, one per player for MO-ISMCTS (mosolver.h:31-34,106-112) — the
+// trees of all players share one table, their keys cannot collide because their
+// parent slots differ.
 //
-// Slot layout: (visits, score2) share one aligned 64-bit word so that
+// UCB1 slot: (visits, score2) share one aligned 64-bit word so that
 // backpropagation is ONE fire-and-forget 64-bit reduction per node
-// (visits += 1, score2 += reward*2 — vectorised backpropagation), which is also
-// what makes a tree shareable between the lanes of a wave.
+// (visits += 1, score2 += reward*2 — vectorised backpropagation).
 #pragma once
 
 #include "devdefs.cuh"
@@ -20,15 +23,36 @@
 
 namespace ismcts {
 
-template <class Mask>
-struct alignas(32) SlotT {
+template <class MaskType>
+struct alignas(32) SlotUcb {
+    using Mask = MaskType;
+    static constexpr bool kExp3 = false;
     uint32_t visits;     // m_visits                      } one 64-bit word:
     uint32_t score2;     // 2 * m_score (rewards 0,1/2,1) } low = visits, high = score2
-    uint32_t key;        // ((parent slot << 8) | move) + 1; 0 = empty; root = kRootKey
+    uint32_t key;        // ((parent slot << 8) | move) + 1; 0 = empty; roots = kRootKey
     uint32_t avail;      // m_available (ucb1.h:51)
-    uint32_t created;    // creation index (root 0): the order of the reference's child vector
+    uint32_t created;    // creation index within its tree (root 0): order of the reference's child vector
     uint32_t player;     // m_playerJustMoved
     Mask child_mask;     // moves that have a child
+
+    ISMCTS_DEV void set_fresh() { visits = 0; score2 = 0; avail = 1; }
+};
+
+template <class MaskType>
+struct alignas(32) SlotExp {
+    using Mask = MaskType;
+    static constexpr bool kExp3 = true;
+    uint32_t visits;     // m_visits
+    uint32_t pad0;
+    uint32_t key;
+    uint32_t pad1;
+    uint32_t created;
+    uint32_t player;
+    Mask child_mask;
+    double score;        // m_score: sum of reward / probability (exp3.h:45-48)
+    double prob;         // m_probability, 1 until the node is first offered (exp3.h:42)
+
+    ISMCTS_DEV void set_fresh() { visits = 0; pad0 = 0; pad1 = 0; score = 0.0; prob = 1.0; }
 };
 
 constexpr uint32_t kRootKey = 0xFFFFFFFFu;
@@ -56,30 +80,32 @@ ISMCTS_DEV Slot load_slot(const Slot* p)
 #endif
 }
 
-template <class Mask>
+template <class SlotType>
 struct TreePool {
-    using Slot = SlotT<Mask>;
-    Slot* slots;     // this tree's table
+    using Slot = SlotType;
+    using Mask = typename Slot::Mask;
+    Slot* slots;     // this lane's table
     uint32_t mask;   // capacity - 1 (capacity is a power of two)
     uint32_t shift;  // 32 - log2(capacity)
-    uint32_t count;  // nodes created so far, root included
+    uint32_t count;  // nodes created so far in all trees of the table, roots included
+    uint32_t roots;  // slots [0, roots) are root nodes
 
-    ISMCTS_DEV void bind(Slot* base, uint32_t log2cap)
+    ISMCTS_DEV void bind(Slot* base, uint32_t log2cap, uint32_t n_roots)
     {
-        slots = base; mask = (1u << log2cap) - 1u; shift = 32u - log2cap; count = 1;
+        slots = base; mask = (1u << log2cap) - 1u; shift = 32u - log2cap; count = n_roots; roots = n_roots;
     }
 
     ISMCTS_DEV uint32_t home(uint32_t key) const { return (key * 2654435769u) >> shift; }
 
-    // Writes the root (a default-constructed node, node.h:30-33) into slot 0.
-    // The caller guarantees the table memory is zero.
-    ISMCTS_DEV void init_root()
+    // Writes the roots (default-constructed nodes, node.h:30-33).  The caller
+    // guarantees the table memory is zero.
+    ISMCTS_DEV void init_roots()
     {
         Slot r;
-        r.visits = 0; r.score2 = 0; r.key = kRootKey; r.avail = 1; r.created = 0; r.player = 0;
-        r.child_mask = Mask::none();
-        slots[0] = r;
-        count = 1;
+        r.set_fresh();
+        r.key = kRootKey; r.created = 0; r.player = 0; r.child_mask = Mask::none();
+        for (uint32_t i = 0; i < roots; ++i) slots[i] = r;
+        count = roots;
     }
 
     // Slot index (and contents) of the child of `parent` reached by `move`; the child must exist.
@@ -88,7 +114,7 @@ struct TreePool {
         const uint32_t key = slot_make_key(parent, move);
         uint32_t i = home(key);
         for (;;) {
-            if (i != 0) { // slot 0 is the root
+            if (i >= roots) {
                 out = load_slot(&slots[i]);
                 if (out.key == key) return i;
             }
@@ -96,17 +122,19 @@ struct TreePool {
         }
     }
 
-    // addChild + newChild, node.h:44-48 / solverbase.h:74-80: a fresh node with
-    // available = 1 (ucb1.h:51).  Returns its slot index.
-    ISMCTS_DEV uint32_t insert(uint32_t parent, uint32_t move, uint32_t player)
+    // addChild + newChild, node.h:44-48 / solverbase.h:74-80: a fresh node
+    // (available = 1, ucb1.h:51; probability = 1, exp3.h:42).  `created` is its
+    // creation index within its own tree.  Returns its slot index.
+    ISMCTS_DEV uint32_t insert(uint32_t parent, uint32_t move, uint32_t player, uint32_t created)
     {
         const uint32_t key = slot_make_key(parent, move);
         uint32_t i = home(key);
-        while (i == 0 || load_slot(&slots[i]).key != 0) i = (i + 1u) & mask;
+        while (i < roots || load_slot(&slots[i]).key != 0) i = (i + 1u) & mask;
         Slot s;
-        s.visits = 0; s.score2 = 0; s.key = key; s.avail = 1; s.created = count++; s.player = player;
-        s.child_mask = Mask::none();
+        s.set_fresh();
+        s.key = key; s.created = created; s.player = player; s.child_mask = Mask::none();
         slots[i] = s;
+        ++count;
         return i;
     }
 };

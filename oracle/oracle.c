@@ -606,6 +606,14 @@ static uint32_t otree_select(otree* t, uint32_t node, const uint16_t* legal, int
         }
         return best;
     }
+    /* EXP3: the reference samples a std::discrete_distribution over the legal children in
+     * child-vector order (exp3.h:57-62); any fixed order gives the same distribution.  The oracle
+     * and the kernels take them in ascending move order (legal[] is ascending). */
+    K = 0;
+    for (int j = 0; j < n; ++j) {
+        const int c = otree_find(t, node, legal[j]);
+        if (c >= 0) cand[K++] = (uint32_t)c;
+    }
     double scores[256], probs[256];
     uint32_t visits[256];
     for (uint32_t i = 0; i < K; ++i) { scores[i] = t->n[cand[i]].fscore; visits[i] = t->n[cand[i]].visits; }

@@ -13,6 +13,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -40,17 +41,17 @@ static uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_
     return out;
 }
 
-template <class Game>
-static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos, uint32_t tree_id,
-                       double exploration, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count)
+// One lane (one SO tree or one set of MO trees); writes the tree of `player` in creation order.
+template <class Game, class Slot, uint32_t kKind>
+static int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos, uint32_t tree_id,
+                    double exploration, uint32_t player, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count)
 {
-    using Mask = typename Game::Mask;
-    using Slot = SlotT<Mask>;
+    using L = Lane<Game, Slot, kKind>;
     uint32_t log2cap = 4;
-    while (((uint64_t)1 << log2cap) < 2 * (iterations + 2)) ++log2cap;
+    while (((uint64_t)1 << log2cap) < 2 * L::kTrees * (iterations + 2)) ++log2cap;
     std::vector<Slot> table((size_t)1 << log2cap);
-    std::memset(table.data(), 0, table.size() * sizeof(Slot));
-    std::vector<double> ln(iterations + 4);
+    std::memset((void*)table.data(), 0, table.size() * sizeof(Slot));
+    std::vector<double> ln(iterations + 300);
     ln[0] = 0.0;
     for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
     const uint32_t stride = Game::kMoveStride;
@@ -66,26 +67,50 @@ static int so_search_t(const void* root, uint64_t iterations, uint64_t seed, uin
     P.pool = table.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
     P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
     P.visits = v.data(); P.score2 = s.data(); P.avail = a.data(); P.iters_done = it.data();
-
     P.tree_thresh = g_thresh; P.tree_period = g_period; P.sched_mode = g_mode; P.sched_split_min = g_split;
     uint64_t scratch[Game::kHandWords];
     uint32_t ring[LaneRng::kRingWords];
     std::vector<uint32_t> path(Game::kMaxDepth);
-    lane_tree_search<Game>(P, 0, true, scratch, 1, ring, 1, path.data());
+    lane_tree_search<Game, Slot, kKind>(P, 0, true, scratch, 1, ring, 1, path.data());
 
-    uint32_t n = 0;
-    for (const Slot& sl : table) if (sl.key != 0) ++n;
-    *count = n;
-    if (n > capacity) return 5;
-    for (const Slot& sl : table) {
-        if (sl.key == 0) continue;
-        ismcts_node_rec& r = nodes[sl.created];
+    const uint32_t n_roots = L::kTrees;
+    const uint32_t root_slot = kKind == kMO ? player : 0;
+    auto root_of = [&](size_t i) { while (i >= n_roots) i = slot_parent_of(table[i].key); return (uint32_t)i; };
+    std::vector<std::pair<uint32_t, uint32_t>> members;
+    for (size_t i = 0; i < table.size(); ++i) {
+        if (table[i].key == 0) continue;
+        if (i < n_roots ? i == root_slot : root_of(i) == root_slot) members.emplace_back(i < n_roots ? 0u : table[i].created, (uint32_t)i);
+    }
+    std::sort(members.begin(), members.end());
+    *count = (uint32_t)members.size();
+    if (members.size() > capacity) return 5;
+    std::vector<uint32_t> index_of_slot(table.size(), 0);
+    for (size_t k = 0; k < members.size(); ++k) index_of_slot[members[k].second] = (uint32_t)k;
+    for (size_t k = 0; k < members.size(); ++k) {
+        const Slot& sl = table[members[k].second];
+        ismcts_node_rec& r = nodes[k];
         if (sl.key == kRootKey) { r.parent = 0; r.move = 0; }
-        else { r.parent = table[slot_parent_of(sl.key)].created; r.move = slot_move_of(sl.key); }
-        r.player = sl.player; r.visits = sl.visits; r.score2 = sl.score2; r.avail = sl.avail;
-        r.score = 0.5 * (double)sl.score2; r.prob = 1.0;
+        else { r.parent = index_of_slot[slot_parent_of(sl.key)]; r.move = slot_move_of(sl.key); }
+        r.player = sl.player; r.visits = sl.visits;
+        if constexpr (Slot::kExp3) { r.score2 = 0; r.avail = 1; r.score = sl.score; r.prob = sl.prob; }
+        else { r.score2 = sl.score2; r.avail = sl.avail; r.score = 0.5 * (double)sl.score2; r.prob = 1.0; }
     }
     return 0;
+}
+
+template <class Game>
+static int search_game(const void* root, uint32_t solver, uint32_t policy, uint64_t iterations, uint64_t seed, uint32_t pos,
+                       uint32_t tree, double exploration, uint32_t player, ismcts_node_rec* nodes, uint32_t capacity,
+                       uint32_t* count)
+{
+    using Mask = typename Game::Mask;
+    if (solver == ISMCTS_SOLVER_SO && policy == ISMCTS_POLICY_UCB1)
+        return search_t<Game, SlotUcb<Mask>, kSO>(root, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
+    if (solver == ISMCTS_SOLVER_SO)
+        return search_t<Game, SlotExp<Mask>, kSO>(root, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
+    if (policy == ISMCTS_POLICY_UCB1)
+        return search_t<Game, SlotUcb<Mask>, kMO>(root, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
+    return search_t<Game, SlotExp<Mask>, kMO>(root, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
 }
 
 extern "C" {
@@ -101,13 +126,13 @@ void emu_set_schedule_mode(uint32_t mode, uint32_t split_min) { g_mode = mode; g
 void emu_warp_sim(const void* root, uint32_t iters_per_tree, uint64_t seed, uint64_t* stats)
 {
     using Game = KwGame;
-    using L = Lane<Game, true>;
-    using Slot = SlotT<Game::Mask>;
+    using Slot = SlotUcb<Game::Mask>;
+    using L = Lane<Game, Slot, kSO>;
     constexpr int W = 32;
     uint32_t log2cap = 4;
     while (((uint64_t)1 << log2cap) < 2 * ((uint64_t)iters_per_tree + 2)) ++log2cap;
     std::vector<Slot> pool((size_t)W << log2cap);
-    std::memset(pool.data(), 0, pool.size() * sizeof(Slot));
+    std::memset((void*)pool.data(), 0, pool.size() * sizeof(Slot));
     std::vector<double> ln(iters_per_tree + 4);
     ln[0] = 0.0;
     for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
@@ -132,8 +157,9 @@ void emu_warp_sim(const void* root, uint32_t iters_per_tree, uint64_t seed, uint
         l.g.bind(scratch[i].data(), 1);
         l.done = 0; l.deadline = 0; l.first_iteration = 0; l.root_children = Game::Mask::none();
         l.prep = &prepared;
-        l.tree.bind(pool.data() + ((size_t)i << log2cap), log2cap);
-        l.tree.init_root();
+        l.tree.bind(pool.data() + ((size_t)i << log2cap), log2cap, 1);
+        l.tree.init_roots();
+        l.tree_players = 1;
         l.rng.init(seed, 0, i, ring[i].data(), 1);
         l.quota = iters_per_tree;
         l.start_iteration();
@@ -171,8 +197,18 @@ int emu_so_search(uint32_t game, const void* root, uint64_t iterations, uint64_t
                   double exploration, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count)
 {
     if (game == ISMCTS_GAME_KW)
-        return so_search_t<KwGame>(root, iterations, seed, pos, tree, exploration, nodes, capacity, count);
-    return so_search_t<MnkGame>(root, iterations, seed, pos, tree, exploration, nodes, capacity, count);
+        return search_game<KwGame>(root, ISMCTS_SOLVER_SO, ISMCTS_POLICY_UCB1, iterations, seed, pos, tree, exploration, 0, nodes, capacity, count);
+    return search_game<MnkGame>(root, ISMCTS_SOLVER_SO, ISMCTS_POLICY_UCB1, iterations, seed, pos, tree, exploration, 0, nodes, capacity, count);
+}
+
+// Any solver / tree policy; MO: the tree of `player`.
+int emu_search(uint32_t game, const void* root, uint32_t solver, uint32_t policy, uint64_t iterations, uint64_t seed,
+               uint32_t pos, uint32_t tree, double exploration, uint32_t player, ismcts_node_rec* nodes, uint32_t capacity,
+               uint32_t* count)
+{
+    if (game == ISMCTS_GAME_KW)
+        return search_game<KwGame>(root, solver, policy, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
+    return search_game<MnkGame>(root, solver, policy, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
 }
 
 } // extern "C"

@@ -24,6 +24,9 @@ def emu():
     E.emu_so_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double,
                                 C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     E.emu_set_schedule.argtypes = [C.c_uint32, C.c_uint32]
+    E.emu_set_schedule_mode.argtypes = [C.c_uint32, C.c_uint32]
+    E.emu_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
+                             C.c_uint32, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     return E
 
 
@@ -110,3 +113,60 @@ def test_result_does_not_depend_on_the_schedule(emu, thresh, period):
             assert O.playout(O.GAME_KW, s, 5, 2, 0, it) == emu.emu_playout(O.GAME_KW, C.byref(s), 5, 2, it)
     finally:
         emu.emu_set_schedule(8, 8)
+
+
+def emu_any(E, game, root, solver, policy, iters, seed, player):
+    cap = 8 * (iters + 2)
+    nodes = np.zeros(cap, dtype=O.NODE_DTYPE)
+    n = C.c_uint32()
+    assert E.emu_search(game, C.byref(root), solver, policy, iters, seed, 0, 0, 0.7, player, nodes.ctypes.data, cap,
+                        C.byref(n)) == 0
+    return nodes[:n.value]
+
+
+EXP_FIELDS = ("parent", "move", "player", "visits", "score", "prob")
+
+
+@pytest.mark.parametrize("players", [2, 4, 6])
+@pytest.mark.parametrize("policy", [O.POLICY_UCB1, O.POLICY_EXP3])
+def test_kw_mo_and_exp3_every_node(emu, players, policy):
+    """MO-ISMCTS (one tree per player) and EXP3 (as the sequential policy, BASELINE config 4)."""
+    s = O.kw_deal(1234, players, players)
+    fields = EXP_FIELDS if policy == O.POLICY_EXP3 else FIELDS
+    want = O.so_search(O.GAME_KW, s, 1200, seed=5, policy=policy)
+    got = emu_any(emu, O.GAME_KW, s, O.SOLVER_SO, policy, 1200, 5, 0)
+    assert len(got) == len(want)
+    for f in fields:
+        assert (got[f] == want[f]).all(), ("so", f)
+    trees = O.mo_search(O.GAME_KW, s, 700, seed=6, policy=policy)
+    assert sorted(trees) == list(range(players))
+    for p, want in trees.items():
+        got = emu_any(emu, O.GAME_KW, s, O.SOLVER_MO, policy, 700, 6, p)
+        assert len(got) == len(want)
+        for f in fields:
+            assert (got[f] == want[f]).all(), ("mo", p, f)
+
+
+@pytest.mark.parametrize("policy", [O.POLICY_UCB1, O.POLICY_EXP3])
+def test_mnk_mo_every_node(emu, policy):
+    s = O.mnk_init(4, 4, 3)
+    fields = EXP_FIELDS if policy == O.POLICY_EXP3 else FIELDS
+    trees = O.mo_search(O.GAME_MNK, s, 1500, seed=3, policy=policy)
+    for p, want in trees.items():
+        got = emu_any(emu, O.GAME_MNK, s, O.SOLVER_MO, policy, 1500, 3, p)
+        assert len(got) == len(want)
+        for f in fields:
+            assert (got[f] == want[f]).all(), (p, f)
+
+
+@pytest.mark.parametrize("mode,split", [(1, 0), (2, 6), (3, 10)])
+def test_result_does_not_depend_on_the_pass_plan(emu, mode, split):
+    try:
+        emu.emu_set_schedule_mode(mode, split)
+        s = O.kw_deal(3, 5, 4)
+        want = O.so_search(O.GAME_KW, s, 800, seed=8)
+        got = emu_search(emu, O.GAME_KW, s, 800, 8, 0, 0)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), f
+    finally:
+        emu.emu_set_schedule_mode(0, 8)

@@ -163,3 +163,58 @@ def test_time_mode_runs_and_replays(engine):
             if nrec["parent"] == 0:
                 v[nrec["move"]] += nrec["visits"]
     assert (v == res["visits"][0]).all()
+
+
+EXP_FIELDS = ("parent", "move", "player", "visits", "score", "prob")
+
+
+@pytest.mark.parametrize("policy", [capi.POLICY_UCB1, capi.POLICY_EXP3])
+def test_mo_trees_kw_every_node_bit_exact(engine, policy):
+    """MO-ISMCTS (mosolver.h:57-101): every player's tree of several lanes; EXP3 as the sequential
+    policy is BASELINE config 4 (MOSolver<Card, Policy, EXP3>)."""
+    n_pos, lanes, per_lane = 2, 3, 600
+    states = [_midgame(9, i, i * 11) for i in range(n_pos)]
+    desc = engine.make_desc(capi.GAME_KW, n_pos, lanes, iterations=lanes * per_lane, seed=31, solver=capi.SOLVER_MO,
+                            policy=policy)
+    res = engine.search(desc, capi.pack_states(states))
+    assert (res["iterations_done"] == per_lane).all()
+    fields = EXP_FIELDS if policy == capi.POLICY_EXP3 else FIELDS
+    for i, s in enumerate(states):
+        for t in range(lanes):
+            want = O.mo_search(O.GAME_KW, _okw(s), per_lane, seed=31, pos=i, tree=t, policy=policy)
+            for player, w in want.items():
+                got = engine.dump_tree(i * lanes + t, 4 * per_lane, player=player)
+                assert len(got) == len(w)
+                for f in fields:
+                    assert (got[f] == w[f]).all(), (i, t, player, f)
+        # the decision comes from the tree of the root's player to move (mosolver.h:42-46)
+        v = np.zeros(64, dtype=np.uint64)
+        for t in range(lanes):
+            w = O.mo_search(O.GAME_KW, _okw(s), per_lane, seed=31, pos=i, tree=t, policy=policy)[s.player]
+            for nrec in w[1:]:
+                if nrec["parent"] == 0:
+                    v[nrec["move"]] += nrec["visits"]
+        assert (v == res["visits"][i]).all()
+        assert int(res["best_move"][i]) == int(np.argmax(v))
+
+
+def test_so_exp3_and_mnk_mo_bit_exact(engine):
+    s = capi.kw_deal(4, 4, 4)
+    per = 900
+    engine.search(engine.make_desc(capi.GAME_KW, 1, 2, iterations=2 * per, seed=2, policy=capi.POLICY_EXP3),
+                  capi.pack_states([s]))
+    for t in range(2):
+        got = engine.dump_tree(t, per + 2)
+        want = O.so_search(O.GAME_KW, _okw(s), per, seed=2, tree=t, policy=O.POLICY_EXP3)
+        assert len(got) == len(want)
+        for f in EXP_FIELDS:
+            assert (got[f] == want[f]).all(), (t, f)
+    m = capi.mnk_init(5, 5, 4)
+    engine.search(engine.make_desc(capi.GAME_MNK, 1, 1, iterations=1200, seed=8, solver=capi.SOLVER_MO),
+                  capi.pack_states([m]))
+    want = O.mo_search(O.GAME_MNK, _omnk(m), 1200, seed=8)
+    for player, w in want.items():
+        got = engine.dump_tree(0, 3000, player=player)
+        assert len(got) == len(w)
+        for f in FIELDS:
+            assert (got[f] == w[f]).all(), (player, f)
