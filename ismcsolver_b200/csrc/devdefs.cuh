@@ -40,6 +40,13 @@ ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { atomicAdd((unsigned lo
 // Warp votes over all 32 lanes (every lane of a warp runs the search loop, see lane_search.cuh).
 ISMCTS_DEV uint32_t warp_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 ISMCTS_DEV bool warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
+// Shared-tree (tree-parallel) primitives: slot reservation, child publication, counters.
+ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value) { return atomicCAS(p, expect, value); }
+ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { atomicOr((unsigned long long*)p, (unsigned long long)v); }
+ISMCTS_DEV void fence_device() { __threadfence(); }
+ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return __ldcg(p); }
+ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
 // Fire-and-forget 64-bit reduction (SASS RED.E.ADD.64): no return value, no scoreboard wait.
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v)
 {
@@ -58,6 +65,17 @@ ISMCTS_DEV uint64_t global_timer_ns()
 }
 ISMCTS_DEV uint32_t warp_ballot(bool p) { return p ? 1u : 0u; } // host build: a "warp" of one lane
 ISMCTS_DEV bool warp_any(bool p) { return p; }
+ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value)
+{
+    const uint32_t old = *p;
+    if (old == expect) *p = value;
+    return old;
+}
+ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t old = *p; *p += v; return old; }
+ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { *p |= v; }
+ISMCTS_DEV void fence_device() {}
+ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }
+ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return *p; }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 #endif

@@ -46,7 +46,7 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
 
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
-template <class Game, class Slot, uint32_t kKind, int kMinBlocks>
+template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams P)
 {
     extern __shared__ uint64_t smem[];
@@ -54,7 +54,24 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    lane_tree_search<Game, Slot, kKind>(P, gtid, gtid < P.n_positions * P.trees, scratch, kBlock, ring, kBlock, path);
+    const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
+    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, scratch, kBlock, ring, kBlock, path);
+}
+
+// Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
+template <class Slot>
+__global__ void init_shared_roots_kernel(SearchParams P)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_positions * P.trees) init_shared_root<Slot>(P, i);
+}
+
+// Root statistics of every tree -> per-position sums (one thread per tree), after the search.
+template <class Game, class Slot, uint32_t kKind>
+__global__ void collect_roots_kernel(SearchParams P)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_positions * P.trees) collect_roots<Game, Slot, kKind>(P, i);
 }
 
 template <class Game>
@@ -89,6 +106,7 @@ struct ismcts_ctx {
     void* prepared = nullptr;    size_t prepared_bytes = 0;
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
+    uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD /
     // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT override
@@ -97,7 +115,7 @@ struct ismcts_ctx {
     int min_blocks = 8;          // resident CTAs per SM the SO/UCB1 Knockout Whist kernel is compiled for; ISMCTS_MIN_BLOCKS
 
     // geometry of the last search (for ismcts_dump_tree)
-    uint32_t last_log2cap = 0, last_lanes = 0, last_game = 0, last_solver = 0, last_policy = 0;
+    uint32_t last_log2cap = 0, last_lanes = 0 /* tables */, last_game = 0, last_solver = 0, last_policy = 0;
     std::vector<uint8_t> last_root_player; // per position
 };
 
@@ -177,7 +195,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
-    cudaFree(ctx->out); cudaFree(ctx->play_out);
+    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -233,7 +251,14 @@ static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
     if (d->game != ISMCTS_GAME_KW && d->game != ISMCTS_GAME_MNK) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
     if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
     if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
-    if (d->flags != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
+    if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
+        if ((d->flags & 0xFEu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
+        if ((d->flags >> ISMCTS_FLAG_LANES_SHIFT) == 0) return fail(ctx, ISMCTS_ERR_INVALID, "shared tree: lanes must be > 0");
+        if (d->solver != ISMCTS_SOLVER_SO || d->policy != ISMCTS_POLICY_UCB1)
+            return fail(ctx, ISMCTS_ERR_INVALID, "shared trees (tree parallelisation) are available for SO-ISMCTS with UCB1");
+    } else if (d->flags != 0) {
+        return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
+    }
     if (d->n_positions == 0 || d->trees == 0) return fail(ctx, ISMCTS_ERR_INVALID, "n_positions and trees must be > 0");
     if ((uint64_t)d->n_positions * d->trees > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many trees");
     if (d->trees_total < d->tree_base + d->trees) return fail(ctx, ISMCTS_ERR_INVALID, "trees_total < tree_base + trees");
@@ -277,13 +302,13 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
     if constexpr (kTuned) {
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
         switch (ctx->min_blocks) {
-        case 4: search_kernel<Game, Slot, kKind, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        case 5: search_kernel<Game, Slot, kKind, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        case 6: search_kernel<Game, Slot, kKind, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        default: search_kernel<Game, Slot, kKind, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         }
     } else {
-        search_kernel<Game, Slot, kKind, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
+        search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
     }
 }
 
@@ -295,12 +320,29 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
     if (rc) return rc;
     P.prepared = ctx->prepared;
     const uint32_t grid = (lanes + kBlock - 1) / kBlock;
+    const uint32_t tables = P.n_positions * P.trees, tgrid = (tables + 127) / 128;
     const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
-    if (so && ucb) launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
-    else if (so) launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
-    else if (ucb) launch_search_variant<Game, SlotUcb<Mask>, kMO, false>(ctx, P, grid);
-    else launch_search_variant<Game, SlotExp<Mask>, kMO, false>(ctx, P, grid);
-    ctx->launches++;
+    if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
+        init_shared_roots_kernel<SlotUcb<Mask>><<<tgrid, 128, 0, ctx->stream>>>(P);
+        search_kernel<Game, SlotUcb<Mask>, kSO, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
+        collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
+        ctx->launches += 3;
+    } else {
+        if (so && ucb) {
+            launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
+        } else if (so) {
+            launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
+            collect_roots_kernel<Game, SlotExp<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
+        } else if (ucb) {
+            launch_search_variant<Game, SlotUcb<Mask>, kMO, false>(ctx, P, grid);
+            collect_roots_kernel<Game, SlotUcb<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
+        } else {
+            launch_search_variant<Game, SlotExp<Mask>, kMO, false>(ctx, P, grid);
+            collect_roots_kernel<Game, SlotExp<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
+        }
+        ctx->launches += 2;
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return ISMCTS_OK;
 }
@@ -313,7 +355,11 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     if (!d_roots || !d_visits || !d_score2 || !d_avail || !d_iters) return fail(ctx, ISMCTS_ERR_INVALID, "null device pointer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 
-    const uint32_t lanes = d->n_positions * d->trees;
+    const bool shared = (d->flags & ISMCTS_FLAG_SHARED_TREE) != 0;
+    const uint32_t width = shared ? d->flags >> ISMCTS_FLAG_LANES_SHIFT : 1u;
+    const uint32_t tables = d->n_positions * d->trees;           // node pools
+    if ((uint64_t)tables * width > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many lanes");
+    const uint32_t lanes = tables * width;                       // threads
     const uint32_t stride = ismcts_move_stride(d->game);
     const uint32_t per_lane = trees_per_lane(d->game, d->solver);
     const size_t slot = slot_bytes(d->game, d->policy);
@@ -323,7 +369,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     uint32_t log2cap;
     if (d->iterations > 0) {
         max_it = d->iterations / d->trees_total + 1;
-        log2cap = std::max<uint32_t>(4, ceil_log2(2 * per_lane * (max_it + 1)));
+        log2cap = std::max<uint32_t>(4, ceil_log2(2 * (per_lane * (max_it + 1) + (shared ? width : 0))));
         if (log2cap > kMaxSlotsLog2) return fail(ctx, ISMCTS_ERR_CAPACITY, "too many iterations per tree for the node pool");
     } else {
         // time mode: the iteration count is unknown; give every lane an equal share of the free memory
@@ -331,10 +377,10 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
         CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
         const size_t budget = (free_b + ctx->pool_bytes) / 2;
         log2cap = 4;
-        while (log2cap < 21 && ((size_t)lanes << (log2cap + 1)) * slot <= budget) ++log2cap;
+        while (log2cap < 21 && ((size_t)tables << (log2cap + 1)) * slot <= budget) ++log2cap;
         max_it = (((uint64_t)1 << (log2cap - 1)) - 1) / per_lane;
     }
-    const size_t pool_need = ((size_t)lanes << log2cap) * slot;
+    const size_t pool_need = ((size_t)tables << log2cap) * slot;
     {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
@@ -350,6 +396,11 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     CUDA_TRY(ctx, cudaMemsetAsync(d_visits, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_score2, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
+    if (shared) {
+        rc = ensure(ctx, ctx->counters, ctx->counters_bytes, (size_t)tables * sizeof(uint32_t));
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemsetAsync(d_iters, 0, (size_t)tables * sizeof(uint64_t), ctx->stream));
+    }
 
     SearchParams P;
     std::memset(&P, 0, sizeof P);
@@ -363,8 +414,9 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
     P.playout_out = nullptr; P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
     P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
+    P.lanes_per_tree = width; P.node_counters = ctx->counters;
 
-    ctx->last_log2cap = log2cap; ctx->last_lanes = lanes; ctx->last_game = d->game;
+    ctx->last_log2cap = log2cap; ctx->last_lanes = tables; ctx->last_game = d->game;
     ctx->last_solver = d->solver; ctx->last_policy = d->policy;
 
     if (d->game == ISMCTS_GAME_KW) return launch_search<KwGame>(ctx, P, d, d_roots, lanes);

@@ -56,6 +56,9 @@ struct SearchParams {
     uint32_t tree_period;    // ... or at the latest every tree_period passes (a power of two)
     uint32_t sched_mode;     // Schedule::mode
     uint32_t sched_split_min;
+    // tree parallelisation: `lanes_per_tree` lanes search ONE tree together (1 = private trees)
+    uint32_t lanes_per_tree;
+    uint32_t* node_counters; // [n_positions * trees] nodes created per shared tree (root included)
 };
 
 // Iterations of one tree in count mode: the reference drains one shared counter
@@ -115,7 +118,12 @@ struct Schedule {
 // (SolverBase::simulate after cloneAndRandomise), one iteration per lane, no tree.
 enum LaneKind : uint32_t { kPlayout = 0, kSO = 1, kMO = 2 };
 
-template <class Game, class SlotType, uint32_t kKind>
+// kShared: tree parallelisation (TreeParallel, execution.h:169-179) — the lanes of a tree group
+// work on ONE tree: nodes are reserved with compare-and-swap, statistics are updated with
+// reductions, and every node a descent passes through is counted as visited at once (virtual
+// loss: the visit is in, the reward follows at backpropagation), which steers the other
+// lanes away from the path while its playout is still running.  SO + UCB1 only.
+template <class Game, class SlotType, uint32_t kKind, bool kShared = false>
 struct Lane {
     using Mask = typename Game::Mask;
     using Prepared = typename Game::Prepared;
@@ -139,26 +147,29 @@ struct Lane {
     uint32_t done, quota;
     uint64_t deadline;
     uint32_t first_iteration; // index of this lane's first iteration (playout kernel: the playout id)
+    uint32_t iteration_stride; // shared tree: the lanes of a tree interleave their iteration ids
+    uint32_t* node_counter;   // shared tree: nodes created so far (all lanes)
     uint32_t tree_players;    // MO: bit p = player p has a tree (the players of the root position)
 
     ISMCTS_DEV explicit Lane(const SearchParams& p) : P(p) {}
 
     ISMCTS_DEV void start_iteration()
     {
-        rng.begin_iteration(first_iteration + done);
+        rng.begin_iteration(first_iteration + done * iteration_stride);
         g.start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
         depth = 0; plies = 0;
         if (kMulti) {
             for (uint32_t t = 0; t < kTrees; ++t) { node[t] = t; node_children[t] = load_slot(&tree.slots[t]).child_mask; }
         } else {
-            node[0] = 0; node_children[0] = root_children;
+            node[0] = 0; node_children[0] = root_children;   // (shared tree: masks are re-read at every level)
         }
         phase = kTree ? kSelect : kRollout;
     }
 
     ISMCTS_DEV bool budget_left() const
     {
-        if (kTree && tree.count + kTrees > P.max_nodes) return false;
+        if (kTree && !kShared && tree.count + kTrees > P.max_nodes) return false;
+        if (kShared && load_u32_cg(node_counter) + P.lanes_per_tree > P.max_nodes) return false;
         return P.iterations > 0 || !kTree ? done < quota : global_timer_ns() < deadline;
     }
 
@@ -188,7 +199,12 @@ struct Lane {
     ISMCTS_DEV void finish_iteration(uint32_t gtid)
     {
         if (kTree) {
-            if (!kMulti && !kExp3) {
+            if (kShared) {
+                // the visits were counted on the way down (virtual loss); now the rewards
+                for (uint32_t i = 0; i < depth; ++i)
+                    red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[path[i] & 0xFFFFFFu]),
+                                (uint64_t)g.result2(path[i] >> 24) << 32);
+            } else if (!kMulti && !kExp3) {
                 for (uint32_t i = 0; i < depth; ++i) update_node(path[i] & 0xFFFFFFu, path[i] >> 24, 1.0);
             } else {
                 // walk the parent links (the key of a node holds its parent's slot)
@@ -313,6 +329,49 @@ struct Lane {
         }
     }
 
+    // select + expand on a tree shared with other lanes (tree parallelisation).
+    ISMCTS_DEV void descend_shared()
+    {
+        if constexpr (kShared) {
+            for (;;) {
+                const Mask legal = g.legal();
+                if (!legal.any()) return;
+                const uint32_t who = g.current_player();
+                const Mask kids = Mask::load_shared(&tree.slots[node[0]].child_mask); // other lanes add children
+                const Mask untried = legal.minus(kids);
+                uint32_t move, next;
+                const bool expand = untried.any();
+                if (expand) {
+                    move = untried.kth(rng.below(untried.count()));
+                    next = tree.find_or_insert_shared(node[0], move, who, node_counter);
+                    // count the visit before the child becomes visible: a published child has visits >= 1
+                    red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[next]), 1u);
+                    fence_device();
+                    Mask::set_shared(&tree.slots[node[0]].child_mask, move);
+                } else {
+                    double best_u = -1.0;
+                    uint32_t best_created = 0xFFFFFFFFu;
+                    move = 0; next = 0;
+                    for (Mask rest = legal; rest.any();) {
+                        const uint32_t m = rest.pop_lowest();
+                        Slot c;
+                        const uint32_t ci = tree.find(node[0], m, c);
+                        atomic_add_u32(&tree.slots[ci].avail, 1u);                 // markAvailable, ucb1.h:71-72
+                        const uint32_t avail = c.avail + 1u < P.ln_count ? c.avail + 1u : P.ln_count - 1u;
+                        const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[avail], P.exploration);
+                        if (u > best_u || (u == best_u && c.created < best_created)) { best_u = u; best_created = c.created; next = ci; move = m; }
+                    }
+                    red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[next]), 1u);  // virtual loss
+                }
+                node[0] = next;
+                path[depth++] = next | (who << 24);
+                g.step(move);
+                if (expand) { phase = kRollout; return; }
+                if (g.chance_pending()) return;
+            }
+        }
+    }
+
     // ---- one pass of the loop, in two halves so that the warp votes sit between them
 
     struct Wants { bool chance, move, tree, over; };
@@ -342,6 +401,7 @@ struct Lane {
         }
         if (plan.tree && w.tree) {
             if (w.over) finish_iteration(gtid);
+            else if (kShared) descend_shared();
             else descend();
         }
         if ((pass & 3u) == 3u && phase != kDone && rng.low()) rng.refill();
@@ -364,47 +424,81 @@ struct Lane {
     }
 };
 
-// The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees
-// (`valid` = false for the lanes that only pad the last warp: they take part in
-// the warp votes and do nothing).
-template <class Game, class Slot, uint32_t kKind>
+// The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees, or — tree
+// parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
+// lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
+// statistics of the root children are collected afterwards by collect_roots.
+template <class Game, class Slot, uint32_t kKind, bool kShared>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
                                  uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
     using Mask = typename Game::Mask;
-    using L = Lane<Game, Slot, kKind>;
+    using L = Lane<Game, Slot, kKind, kShared>;
     L lane(P);
     lane.path = path;
     lane.g.bind(scratch, scratch_stride);
     lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
+    lane.iteration_stride = 1; lane.node_counter = nullptr;
     lane.root_children = Mask::none();
-    uint32_t pos = 0;
+    uint32_t tree_index = 0;
     if (valid) {
-        pos = gtid / P.trees;
-        const uint32_t tree_global = P.tree_base + gtid % P.trees;
+        const uint32_t width = kShared ? P.lanes_per_tree : 1u;
+        tree_index = gtid / width;                            // position * trees + tree
+        const uint32_t lane_in_tree = gtid % width;
+        const uint32_t pos = tree_index / P.trees;
+        const uint32_t tree_global = P.tree_base + tree_index % P.trees;
         lane.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
-        lane.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)gtid << P.log2cap), P.log2cap, L::kTrees);
-        lane.tree.init_roots();
+        lane.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)tree_index << P.log2cap), P.log2cap, L::kTrees);
+        if (!kShared) lane.tree.init_roots();                 // shared trees: init_shared_roots
         lane.tree_players = Game::root_players(lane.prep);
         lane.rng.init(P.seed, P.pos_base + pos, tree_global, ring, ring_stride);
-        if (P.iterations > 0) lane.quota = (uint32_t)tree_iterations(P.iterations, P.trees_total, tree_global);
-        else lane.deadline = global_timer_ns() + P.time_ns;   // time mode, utility.h:51-60
+        if (P.iterations > 0) {
+            // the iterations of a tree, dealt round-robin to its lanes
+            const uint64_t of_tree = tree_iterations(P.iterations, P.trees_total, tree_global);
+            lane.quota = (uint32_t)(of_tree / width + (lane_in_tree < of_tree % width ? 1u : 0u));
+        } else {
+            lane.deadline = global_timer_ns() + P.time_ns;    // time mode, utility.h:51-60
+        }
+        if (kShared) {
+            lane.first_iteration = lane_in_tree; lane.iteration_stride = width;
+            lane.node_counter = P.node_counters + tree_index;
+        }
         if (lane.budget_left()) lane.start_iteration();
     }
     lane.run(gtid);
     if (!valid) return;
-    P.iters_done[gtid] = lane.done;
+    if (kShared) atomic_add_u64(P.iters_done + tree_index, lane.done);
+    else P.iters_done[tree_index] = lane.done;
+}
 
-    // Root children -> per-position sums (RootParallel::compileVisitCounts, execution.h:219-231).
-    // MO: the tree of the root's player to move decides (mosolver.h:42-46).
-    const uint32_t root = kKind == kMO ? Game::root_player(lane.prep) : 0;
+// Shared trees: the root node and the node counter of tree `index`, before the search starts.
+template <class Slot>
+ISMCTS_DEV void init_shared_root(const SearchParams& P, uint32_t index)
+{
+    TreePool<Slot> tree;
+    tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)index << P.log2cap), P.log2cap, 1);
+    tree.init_roots();
+    P.node_counters[index] = 1;
+}
+
+// Root children of tree `index` -> per-position sums (RootParallel::compileVisitCounts,
+// execution.h:219-231).  MO: the tree of the root's player to move decides (mosolver.h:42-46).
+template <class Game, class Slot, uint32_t kKind>
+ISMCTS_DEV void collect_roots(const SearchParams& P, uint32_t index)
+{
+    using Mask = typename Game::Mask;
+    const uint32_t pos = index / P.trees;
+    const typename Game::Prepared* prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
+    TreePool<Slot> tree;
+    tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)index << P.log2cap), P.log2cap, kKind == kMO ? Game::kMaxPlayers : 1);
+    const uint32_t root = kKind == kMO ? Game::root_player(prep) : 0;
     uint64_t* v = P.visits + (size_t)pos * Game::kMoveStride;
     uint64_t* s = P.score2 + (size_t)pos * Game::kMoveStride;
     uint64_t* a = P.avail + (size_t)pos * Game::kMoveStride;
-    for (Mask rest = load_slot(&lane.tree.slots[root]).child_mask; rest.any();) {
+    for (Mask rest = load_slot(&tree.slots[root]).child_mask; rest.any();) {
         const uint32_t move = rest.pop_lowest();
         Slot c;
-        lane.tree.find(root, move, c);
+        tree.find(root, move, c);
         atomic_add_u64(v + move, c.visits);
         if constexpr (!Slot::kExp3) {
             atomic_add_u64(s + move, c.score2);
@@ -427,6 +521,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
     lane.path = nullptr;
     lane.g.bind(scratch, scratch_stride);
     lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
+    lane.iteration_stride = 1; lane.node_counter = nullptr;
     lane.root_children = Mask::none();
     if (valid) {
         const uint32_t pos = gtid / per_position;

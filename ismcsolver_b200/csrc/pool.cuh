@@ -122,6 +122,30 @@ struct TreePool {
         }
     }
 
+    // Shared tree (tree parallelisation): the child of `parent` for `move`, created if no lane has
+    // created it yet (Node::addChild under the node mutex, node.h:44-48,121-126, without the
+    // mutex).  A slot is reserved by a compare-and-swap on its key; the winner fills in the
+    // fields nobody else writes.  `counter` numbers the nodes of the tree in creation order.
+    // The caller publishes the child in the parent's child_mask afterwards.
+    ISMCTS_DEV uint32_t find_or_insert_shared(uint32_t parent, uint32_t move, uint32_t player, uint32_t* counter)
+    {
+        const uint32_t key = slot_make_key(parent, move);
+        uint32_t i = home(key);
+        for (;;) {
+            if (i >= roots) {
+                const uint32_t old = atomic_cas_u32(&slots[i].key, 0u, key);
+                if (old == 0u) {
+                    slots[i].avail = 1;                       // ucb1.h:51
+                    slots[i].player = player;
+                    slots[i].created = atomic_add_u32(counter, 1u);
+                    return i;
+                }
+                if (old == key) return i;                     // another lane was first
+            }
+            i = (i + 1u) & mask;
+        }
+    }
+
     // addChild + newChild, node.h:44-48 / solverbase.h:74-80: a fresh node
     // (available = 1, ucb1.h:51; probability = 1, exp3.h:42).  `created` is its
     // creation index within its own tree.  Returns its slot index.

@@ -71,7 +71,7 @@ static int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32
     uint64_t scratch[Game::kHandWords];
     uint32_t ring[LaneRng::kRingWords];
     std::vector<uint32_t> path(Game::kMaxDepth);
-    lane_tree_search<Game, Slot, kKind>(P, 0, true, scratch, 1, ring, 1, path.data());
+    lane_tree_search<Game, Slot, kKind, false>(P, 0, true, scratch, 1, ring, 1, path.data());
 
     const uint32_t n_roots = L::kTrees;
     const uint32_t root_slot = kKind == kMO ? player : 0;
@@ -113,11 +113,100 @@ static int search_game(const void* root, uint32_t solver, uint32_t policy, uint6
     return search_t<Game, SlotExp<Mask>, kMO>(root, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
 }
 
+// Tree parallelisation on the host: `width` lanes share ONE tree and are advanced pass by pass in a
+// fixed interleaving (on the GPU the interleaving is whatever the hardware does).  Writes the tree
+// in creation order.
+template <class Game>
+static int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint64_t seed, ismcts_node_rec* nodes,
+                           uint32_t capacity, uint32_t* count, uint64_t* done_out)
+{
+    using Slot = SlotUcb<typename Game::Mask>;
+    using L = Lane<Game, Slot, kSO, true>;
+    uint32_t log2cap = 4;
+    while (((uint64_t)1 << log2cap) < 2 * (iterations + 2 + width)) ++log2cap;
+    std::vector<Slot> table((size_t)1 << log2cap);
+    std::memset((void*)table.data(), 0, table.size() * sizeof(Slot));
+    std::vector<double> ln(iterations + 300);
+    ln[0] = 0.0;
+    for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
+    std::vector<uint64_t> v(Game::kMoveStride), s2(Game::kMoveStride), a(Game::kMoveStride), it(1);
+    uint32_t counter = 0;
+    typename Game::Prepared prepared;
+    uint64_t prep_scratch[Game::kHandWords];
+    Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
+    SearchParams P;
+    std::memset(&P, 0, sizeof P);
+    P.prepared = &prepared; P.n_positions = 1; P.trees = 1; P.trees_total = 1; P.iterations = iterations;
+    P.seed = seed; P.exploration = 0.7; P.pool = table.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
+    P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
+    P.visits = v.data(); P.score2 = s2.data(); P.avail = a.data(); P.iters_done = it.data();
+    P.tree_thresh = g_thresh; P.tree_period = g_period; P.sched_mode = g_mode; P.sched_split_min = g_split;
+    P.lanes_per_tree = width; P.node_counters = &counter;
+    init_shared_root<Slot>(P, 0);
+    std::vector<std::unique_ptr<L>> lanes;
+    std::vector<std::vector<uint64_t>> scratch(width, std::vector<uint64_t>(Game::kHandWords));
+    std::vector<std::vector<uint32_t>> ring(width, std::vector<uint32_t>(LaneRng::kRingWords)), path(width, std::vector<uint32_t>(Game::kMaxDepth));
+    for (uint32_t i = 0; i < width; ++i) {
+        lanes.emplace_back(new L(P));
+        L& l = *lanes.back();
+        l.path = path[i].data();
+        l.g.bind(scratch[i].data(), 1);
+        l.phase = kDone; l.done = 0; l.deadline = 0; l.root_children = Game::Mask::none();
+        l.prep = &prepared;
+        l.tree.bind(table.data(), log2cap, 1);
+        l.tree_players = 1;
+        l.rng.init(seed, 0, 0, ring[i].data(), 1);
+        l.quota = (uint32_t)(iterations / width + (i < iterations % width ? 1 : 0));
+        l.first_iteration = i; l.iteration_stride = width; l.node_counter = &counter;
+        if (l.budget_left()) l.start_iteration();
+    }
+    Schedule sched;
+    sched.init(P);
+    for (uint32_t pass = 0;; ++pass) {
+        std::vector<typename L::Wants> w(width);
+        uint32_t nc = 0, nm = 0, nt = 0, alive = 0;
+        for (uint32_t i = 0; i < width; ++i) {
+            alive += lanes[i]->phase != kDone;
+            w[i] = lanes[i]->classify();
+            nc += w[i].chance; nm += w[i].move; nt += w[i].tree;
+        }
+        if (!alive) break;
+        const PassPlan plan = sched.plan_pass(nc, nm, nt, pass);
+        for (uint32_t i = 0; i < width; ++i) lanes[i]->act(w[i], plan, pass, i);
+    }
+    *done_out = 0;
+    for (uint32_t i = 0; i < width; ++i) *done_out += lanes[i]->done;
+    // dump in creation order
+    std::vector<std::pair<uint32_t, uint32_t>> members;
+    for (size_t i = 0; i < table.size(); ++i) if (table[i].key != 0) members.emplace_back(i == 0 ? 0u : table[i].created, (uint32_t)i);
+    std::sort(members.begin(), members.end());
+    *count = (uint32_t)members.size();
+    if (members.size() > capacity) return 5;
+    std::vector<uint32_t> index_of_slot(table.size(), 0);
+    for (size_t k = 0; k < members.size(); ++k) index_of_slot[members[k].second] = (uint32_t)k;
+    for (size_t k = 0; k < members.size(); ++k) {
+        const Slot& sl = table[members[k].second];
+        ismcts_node_rec& r = nodes[k];
+        if (sl.key == kRootKey) { r.parent = 0; r.move = 0; }
+        else { r.parent = index_of_slot[slot_parent_of(sl.key)]; r.move = slot_move_of(sl.key); }
+        r.player = sl.player; r.visits = sl.visits; r.score2 = sl.score2; r.avail = sl.avail;
+        r.score = 0.5 * (double)sl.score2; r.prob = 1.0;
+    }
+    return 0;
+}
+
 extern "C" {
 
 // Schedule of the search loop (when pending tree operations run); results must not depend on it.
 void emu_set_schedule(uint32_t thresh, uint32_t period) { g_thresh = thresh; g_period = period; }
 void emu_set_schedule_mode(uint32_t mode, uint32_t split_min) { g_mode = mode; g_split = split_min; }
+
+int emu_shared_search(uint32_t game, const void* root, uint64_t iterations, uint32_t width, uint64_t seed,
+                      ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* done)
+{
+    if (game == ISMCTS_GAME_KW) return shared_search_t<KwGame>(root, iterations, width, seed, nodes, capacity, count, done);
+    return shared_search_t<MnkGame>(root, iterations, width, seed, nodes, capacity, count, done);
+}
 
 // A warp of 32 lanes (32 trees of one Knockout Whist position) run pass by pass with real warp votes:
 // measures how busy the lanes are under a schedule.  stats: [0] passes, [1] passes doing chance only,
@@ -155,7 +244,8 @@ void emu_warp_sim(const void* root, uint32_t iters_per_tree, uint64_t seed, uint
         L& l = *lanes.back();
         l.path = path[i].data();
         l.g.bind(scratch[i].data(), 1);
-        l.done = 0; l.deadline = 0; l.first_iteration = 0; l.root_children = Game::Mask::none();
+        l.done = 0; l.deadline = 0; l.first_iteration = 0; l.iteration_stride = 1; l.node_counter = nullptr;
+        l.root_children = Game::Mask::none();
         l.prep = &prepared;
         l.tree.bind(pool.data() + ((size_t)i << log2cap), log2cap, 1);
         l.tree.init_roots();

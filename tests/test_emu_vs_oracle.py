@@ -25,6 +25,8 @@ def emu():
                                 C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     E.emu_set_schedule.argtypes = [C.c_uint32, C.c_uint32]
     E.emu_set_schedule_mode.argtypes = [C.c_uint32, C.c_uint32]
+    E.emu_shared_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32,
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     E.emu_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
                              C.c_uint32, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     return E
@@ -170,3 +172,43 @@ def test_result_does_not_depend_on_the_pass_plan(emu, mode, split):
             assert (got[f] == want[f]).all(), f
     finally:
         emu.emu_set_schedule_mode(0, 8)
+
+
+def emu_shared(E, game, root, iters, width, seed):
+    nodes = np.zeros(iters + width + 2, dtype=O.NODE_DTYPE)
+    n, done = C.c_uint32(), C.c_uint64()
+    assert E.emu_shared_search(game, C.byref(root), iters, width, seed, nodes.ctypes.data, len(nodes), C.byref(n),
+                               C.byref(done)) == 0
+    return nodes[:n.value], done.value
+
+
+def check_tree_invariants(nodes, iterations):
+    """What any correct tree-parallel search satisfies, whatever the interleaving of its lanes."""
+    top = nodes[1:][nodes[1:]["parent"] == 0]
+    assert int(top["visits"].sum()) == iterations            # every iteration passes through one root child
+    assert len(nodes) <= iterations + 1                      # at most one node per iteration
+    kids = np.zeros(len(nodes), dtype=np.int64)
+    for r in nodes[1:]:
+        kids[r["parent"]] += r["visits"]
+    assert (kids[1:] <= nodes[1:]["visits"]).all()          # a node is visited at least as often as its children
+    assert (nodes[1:]["score2"] <= 2 * nodes[1:]["visits"]).all() and (nodes[1:]["visits"] >= 1).all()
+    keys = set(zip(nodes[1:]["parent"].tolist(), nodes[1:]["move"].tolist()))
+    assert len(keys) == len(nodes) - 1                       # no duplicated child
+
+
+def test_shared_tree_one_lane_is_the_sequential_search(emu):
+    """Tree parallelisation with one lane in flight = the reference's sequential semantics."""
+    for game, s in ((O.GAME_KW, O.kw_deal(5, 5, 4)), (O.GAME_MNK, O.mnk_init(5, 5, 4))):
+        want = O.so_search(game, s, 1500, seed=9)
+        got, done = emu_shared(emu, game, s, 1500, 1, 9)
+        assert done == 1500 and len(got) == len(want)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), f
+
+
+@pytest.mark.parametrize("width", [2, 7, 32, 128])
+def test_shared_tree_invariants(emu, width):
+    for game, s in ((O.GAME_KW, O.kw_deal(5, 6, 4)), (O.GAME_MNK, O.mnk_init(4, 4, 3))):
+        nodes, done = emu_shared(emu, game, s, 3000, width, 11)
+        assert done == 3000
+        check_tree_invariants(nodes, 3000)

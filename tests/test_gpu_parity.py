@@ -15,6 +15,10 @@ from ismcsolver_b200 import capi
 pytestmark = pytest.mark.gpu
 
 FIELDS = ("parent", "move", "player", "visits", "score2", "avail")
+import json as _json
+import os as _os
+GOLDEN_OPENING = _json.load(open(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden",
+                                               "ref_stats.json")))["cases"][0]["state"]
 
 
 def _okw(s):
@@ -218,3 +222,75 @@ def test_so_exp3_and_mnk_mo_bit_exact(engine):
         assert len(got) == len(w)
         for f in FIELDS:
             assert (got[f] == w[f]).all(), (player, f)
+
+
+# ------------------------------------------------------------------ tree parallelisation
+
+SHARED = 1  # ISMCTS_FLAG_SHARED_TREE
+
+
+def _shared_flags(lanes):
+    return SHARED | (lanes << 8)
+
+
+def _check_tree_invariants(nodes, iterations):
+    top = nodes[1:][nodes[1:]["parent"] == 0]
+    assert int(top["visits"].sum()) == iterations
+    assert len(nodes) <= iterations + 1
+    kids = np.zeros(len(nodes), dtype=np.int64)
+    for r in nodes[1:]:
+        kids[r["parent"]] += r["visits"]
+    assert (kids[1:] <= nodes[1:]["visits"]).all()
+    assert (nodes[1:]["score2"] <= 2 * nodes[1:]["visits"]).all() and (nodes[1:]["visits"] >= 1).all()
+    assert len(set(zip(nodes[1:]["parent"].tolist(), nodes[1:]["move"].tolist()))) == len(nodes) - 1
+
+
+def test_shared_tree_one_lane_is_bit_exact(engine):
+    """CudaTreeParallel with one iteration in flight is the sequential search (every node)."""
+    for game, s, conv in ((capi.GAME_KW, capi.kw_deal(5, 5, 4), _okw), (capi.GAME_MNK, capi.mnk_init(6, 6, 4), _omnk)):
+        desc = engine.make_desc(game, 1, 1, iterations=2000, seed=9, flags=_shared_flags(1))
+        res = engine.search(desc, capi.pack_states([s]))
+        assert int(res["iterations_done"][0, 0]) == 2000
+        got = engine.dump_tree(0, 2100)
+        want = O.so_search(game, conv(s), 2000, seed=9)
+        assert len(got) == len(want)
+        for f in FIELDS:
+            assert (got[f] == want[f]).all(), f
+
+
+@pytest.mark.parametrize("lanes", [32, 128, 1024, 8192])
+def test_shared_tree_invariants_and_decision(engine, lanes):
+    """Many lanes on one tree with virtual loss (atomics): the tree is consistent whatever the
+    interleaving, and on a decisive position the decision is the sequential one."""
+    iterations = 60000
+    s = O.KwState.from_hex(GOLDEN_OPENING)      # the reference's own opening deal: K of hearts (37) in 40/40 runs
+    desc = engine.make_desc(capi.GAME_KW, 1, 1, iterations=iterations, seed=4, flags=_shared_flags(lanes))
+    res = engine.search(desc, np.frombuffer(bytes(s), dtype=np.uint8))
+    assert int(res["iterations_done"].sum()) == iterations
+    nodes = engine.dump_tree(0, iterations + 2)
+    _check_tree_invariants(nodes, iterations)
+    assert int(res["visits"][0].sum()) == iterations
+    assert int(res["best_move"][0]) == 37
+
+
+def test_shared_tree_mnk_p1_draw_or_lose(engine):
+    s = capi.mnk_init(3, 3, 3)
+    for mv in (4, 1, 5, 3, 6, 8, 7):
+        assert capi.mnk_apply(s, mv) == 0
+    for seed in range(10):
+        res = engine.search(engine.make_desc(capi.GAME_MNK, 1, 1, iterations=16, seed=seed, flags=_shared_flags(4)),
+                            capi.pack_states([s]))
+        assert int(res["best_move"][0]) == 2
+    # larger budget, many lanes: still the drawing move
+    res = engine.search(engine.make_desc(capi.GAME_MNK, 1, 1, iterations=20000, seed=1, flags=_shared_flags(2048)),
+                        capi.pack_states([s]))
+    assert int(res["best_move"][0]) == 2 and int(res["visits"][0].sum()) == 20000
+
+
+def test_shared_tree_rejects_unsupported_combinations(engine):
+    s = capi.kw_deal(1, 1, 4)
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=100, policy=capi.POLICY_EXP3,
+                                       flags=_shared_flags(32)), capi.pack_states([s]))
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=100, flags=SHARED), capi.pack_states([s]))
