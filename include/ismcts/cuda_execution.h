@@ -27,6 +27,7 @@
 #include <chrono>
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -174,6 +175,15 @@ protected:
 
     bool sharedTree() const { return m_sharedTree; }
 
+    /// Tree parallel: iterations in flight on the shared tree.  Every lane in flight adds a virtual
+    /// loss, so a small budget keeps at least four iterations per lane (16 iterations -> 4 lanes).
+    unsigned int lanesFor(std::size_t iterations) const
+    {
+        if (iterations == 0)
+            return m_parallelism;
+        return static_cast<unsigned int>(std::max<std::size_t>(1, std::min<std::size_t>(m_parallelism, iterations / 4)));
+    }
+
     /// Runs one search of `podState` (a position record of include/ismcts_b200.h) on the configured
     /// devices and merges the per-device root arrays (RootParallel::compileVisitCounts,
     /// execution.h:219-231, across devices).
@@ -218,7 +228,7 @@ protected:
             s.desc.seed = m_seed;
             s.desc.exploration = exploration;
             s.desc.dump_tree = 0xFFFFFFFFu;
-            s.desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (m_parallelism << ISMCTS_FLAG_LANES_SHIFT)) : 0;
+            s.desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (lanesFor(m_iterCount) << ISMCTS_FLAG_LANES_SHIFT)) : 0;
             s.visits.assign(stride, 0);
             s.score2.assign(stride, 0);
             s.avail.assign(stride, 0);
@@ -268,17 +278,18 @@ protected:
         return m_last;
     }
 
-    /// Reads tree `index` of the last search back from the first device (creation order).
-    std::vector<ismcts_node_rec> dumpTree(std::uint32_t index) const
+    /// Reads tree `index` of the last search back from the first device (creation order);
+    /// MO: the tree of `player`.
+    std::vector<ismcts_node_rec> dumpTree(std::uint32_t index, std::uint32_t player = 0) const
     {
         if (m_contexts.empty())
             return {};
         std::uint32_t count = 0;
         std::vector<ismcts_node_rec> nodes(1024);
-        int rc = ismcts_dump_tree(m_contexts[0]->get(), index, nodes.data(), static_cast<std::uint32_t>(nodes.size()), &count);
+        int rc = ismcts_dump_tree_of(m_contexts[0]->get(), index, player, nodes.data(), static_cast<std::uint32_t>(nodes.size()), &count);
         if (rc == ISMCTS_ERR_CAPACITY) {
             nodes.resize(count);
-            rc = ismcts_dump_tree(m_contexts[0]->get(), index, nodes.data(), count, &count);
+            rc = ismcts_dump_tree_of(m_contexts[0]->get(), index, player, nodes.data(), count, &count);
         }
         m_contexts[0]->check(rc);
         nodes.resize(count);

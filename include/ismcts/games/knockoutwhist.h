@@ -14,6 +14,7 @@
 #include "card.h"
 #include "../../ismcts_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <random>
 #include <stdexcept>

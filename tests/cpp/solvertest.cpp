@@ -1,0 +1,271 @@
+// solvertest.cpp — API conformance of the CUDA execution policies.
+//
+// Restates the assertions of the reference's test/solvertest.cpp (:64-138) — constructors and
+// getters, setters, "operator() returns a valid move" by iteration count and by time, and the
+// P1DrawOrLose position that every solver must answer with move 2 from 16 iterations — for
+// {SOSolver, MOSolver} x {CudaRootParallel, CudaTreeParallel}, plus the game checks of
+// test/gametest.cpp that concern the host game classes (:92-106,120-130,184-206).
+//
+//   solvertest            all checks; needs a CUDA device
+//   solvertest --host     only the checks that run without a device, and that a search without a
+//                         device fails loudly (no CPU fallback)
+#include <ismcts/sosolver.h>
+#include <ismcts/mosolver.h>
+#include <ismcts/games/knockoutwhist.h>
+#include <ismcts/games/mnkgame.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <string>
+
+using namespace ISMCTS;
+using namespace std::chrono_literals;
+
+static int failures = 0, checks = 0;
+#define CHECK(cond)                                                                          \
+    do {                                                                                     \
+        ++checks;                                                                            \
+        if (!(cond)) { ++failures; std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); } \
+    } while (0)
+#define CHECK_THROWS_AS(expr, Exception)                                                     \
+    do {                                                                                     \
+        ++checks;                                                                            \
+        bool caught = false;                                                                 \
+        try { expr; } catch (Exception const &) { caught = true; } catch (...) {}            \
+        if (!caught) { ++failures; std::printf("FAILED %s:%d: %s did not throw %s\n", __FILE__, __LINE__, #expr, #Exception); } \
+    } while (0)
+
+namespace
+{
+
+std::size_t const numGames = 10;
+auto const iterationTime = 5ms;
+
+// solvertest.cpp:45-60: board [[-1,1,-1],[1,0,0],[0,0,1]], player 1 to move; 2 draws, 0 loses
+struct P1DrawOrLose : public MnkGame
+{
+    P1DrawOrLose()
+    {
+        for (int move : {4, 1, 5, 3, 6, 8, 7})
+            doMove(move);
+    }
+};
+
+// a game without a device form
+struct OpaqueGame : public Game<int>
+{
+    Clone cloneAndRandomise(Player) const override { return std::make_unique<OpaqueGame>(*this); }
+    Player currentPlayer() const override { return 0; }
+    std::vector<int> validMoves() const override { return {0, 1}; }
+    void doMove(int const) override {}
+    double getResult(Player) const override { return 0; }
+};
+
+template<class Solver>
+void testConstruction()
+{
+    // solvertest.cpp:64-78
+    {
+        Solver solver {numGames};
+        CHECK(solver.iterationCount() == numGames);
+        CHECK(solver.iterationTime() == std::chrono::duration<double>::zero());
+    }
+    {
+        Solver solver {iterationTime};
+        CHECK(solver.iterationTime() == iterationTime);
+        CHECK(solver.iterationCount() == 0);
+    }
+    {
+        Solver solver;
+        CHECK(solver.iterationCount() == 1000);
+        CHECK(solver.numThreads() >= 1);
+    }
+    // solvertest.cpp:80-99
+    Solver solver {numGames};
+    solver.setIterationTime(iterationTime);
+    CHECK(solver.iterationTime() == iterationTime);
+    CHECK(solver.iterationCount() == 0);
+    solver.setIterationCount(numGames);
+    CHECK(solver.iterationTime() == std::chrono::duration<double>::zero());
+    CHECK(solver.iterationCount() == numGames);
+}
+
+template<class Game, class Move>
+bool isValid(Game const &game, Move const &move)
+{
+    auto const moves = game.validMoves();
+    return std::find(moves.begin(), moves.end(), move) != moves.end();
+}
+
+template<class Solver>
+void testKnockoutWhist()
+{
+    // solvertest.cpp:101-119
+    KnockoutWhist game {2};
+    {
+        Solver solver {numGames};
+        Card const move = solver(game);
+        CHECK(isValid(game, move));
+    }
+    {
+        Solver solver {iterationTime};
+        Card const move = solver(game);
+        CHECK(isValid(game, move));
+        CHECK(solver.lastStatistics().iterations() > 0);
+    }
+    // a full game played by the solver against itself terminates within the turn bound
+    Solver solver {2000};
+    KnockoutWhist four {4, 12345};
+    unsigned turns = 0;
+    while (!four.validMoves().empty() && turns < 6 + 4 * 28) {
+        Card const move = solver(four);
+        CHECK(isValid(four, move));
+        four.doMove(move);
+        ++turns;
+    }
+    CHECK(four.validMoves().empty());
+}
+
+template<class Solver>
+void testP1DrawOrLose()
+{
+    // solvertest.cpp:131-138
+    P1DrawOrLose game;
+    CHECK(game.currentPlayer() == 1);
+    CHECK((game.validMoves() == std::vector<int>{0, 2}));
+    for (int rep = 0; rep < 5; ++rep) {
+        Solver solver {16};
+        CHECK(solver(game) == 2);
+    }
+}
+
+template<class Solver>
+void testTrees()
+{
+    P1DrawOrLose game;
+    Solver solver {500};
+    solver.setSeed(7);
+    int const move = solver(game);
+    CHECK(move == 2);
+    auto const &stats = solver.lastStatistics();
+    CHECK(stats.iterations() == 500);
+    CHECK(stats.visits[0] + stats.visits[2] == 500);
+}
+
+void testHostOnly()
+{
+    // gametest.cpp:92-98
+    KnockoutWhist whist {2};
+    CHECK(whist.currentPlayer() == 0);
+    CHECK((whist.players() == std::vector<unsigned>{0, 1}));
+    CHECK(whist.validMoves().size() == 7);
+    // gametest.cpp:120-130
+    {
+        KnockoutWhist game {2, 99};
+        game.doMove(game.validMoves().front());
+        CHECK(game.currentPlayer() == 1);
+    }
+    {
+        KnockoutWhist game {2, 99};
+        auto const hand = game.validMoves();
+        Card missing {Card::Two, Card::Clubs};
+        for (int id = 0; id < 52; ++id) {
+            missing = Card::fromId(id);
+            if (std::find(hand.begin(), hand.end(), missing) == hand.end())
+                break;
+        }
+        CHECK_THROWS_AS(game.doMove(missing), std::out_of_range);
+    }
+    // cloneAndRandomise keeps what the observer sees (knockoutwhist.cpp:56-76)
+    {
+        KnockoutWhist game {4, 5};
+        auto clone = game.cloneAndRandomise(0);
+        auto const *c = dynamic_cast<KnockoutWhist const *>(clone.get());
+        CHECK(c != nullptr);
+        CHECK(c->state().hands[0] == game.state().hands[0]);
+        CHECK(__builtin_popcountll(c->state().hands[1]) == 7);
+        CHECK((c->state().hands[0] & c->state().hands[1]) == 0);
+    }
+    // gametest.cpp:100-106,184-206
+    MnkGame mnk;
+    CHECK(mnk.currentPlayer() == 0);
+    CHECK(mnk.validMoves().size() == 9);
+    CHECK_THROWS_AS(mnk.doMove(9), std::out_of_range);
+    int const wins[8][5] = {{0,3,1,4,2},{3,0,4,1,5},{6,0,7,1,8},{0,2,3,4,6},{1,0,4,2,7},{2,0,5,1,8},{0,1,4,2,8},{2,0,4,1,6}};
+    for (auto const &sequence : wins) {
+        MnkGame game;
+        for (int move : sequence)
+            game.doMove(move);
+        CHECK(game.validMoves().empty());
+        CHECK(game.getResult(0) == 1);
+    }
+    // node.h: the textual form of nodes (ucb1.h:41-47, docs/node.md:13-22)
+    UCBNode<int> root;
+    auto child = std::make_unique<UCBNode<int>>(6, 0);
+    child->setVisits(988);
+    child->setStatistics(988.0, 998);
+    root.addChild(std::move(child));
+    CHECK(root.treeToString() == "[M:0 by 0, V/S/A: 0/0.0/1]\n| [M:6 by 0, V/S/A: 988/988.0/998]\n");
+    CHECK(root.height() == 1);
+    CHECK(root.children().front()->depth() == 1);
+    CHECK((root.untriedMoves({5, 6, 7}) == std::vector<int>{5, 7}));
+    // an opaque host game has no device form: a clear error, not a CPU fallback
+    OpaqueGame opaque;
+    SOSolver<int, CudaRootParallel> solver {10};
+    CHECK_THROWS_AS(solver(opaque), std::invalid_argument);
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+    bool const hostOnly = argc > 1 && std::strcmp(argv[1], "--host") == 0;
+    testConstruction<SOSolver<Card, CudaRootParallel>>();
+    testConstruction<SOSolver<Card, CudaTreeParallel>>();
+    testConstruction<MOSolver<Card, CudaRootParallel>>();
+    testConstruction<MOSolver<int, CudaRootParallel, EXP3>>();
+    testHostOnly();
+    if (hostOnly) {
+        // without a device every search throws
+        KnockoutWhist game {2};
+        SOSolver<Card, CudaRootParallel> solver {10};
+        int devices = 0;
+        ismcts_ctx *probe = nullptr;
+        if (ismcts_create(0, &probe) == ISMCTS_OK) { devices = 1; ismcts_destroy(probe); }
+        if (!devices)
+            CHECK_THROWS_AS(solver(game), CudaError);
+    } else {
+        testKnockoutWhist<SOSolver<Card, CudaRootParallel>>();
+        testKnockoutWhist<SOSolver<Card, CudaTreeParallel>>();
+        testKnockoutWhist<MOSolver<Card, CudaRootParallel>>();
+        testKnockoutWhist<MOSolver<Card, CudaRootParallel, EXP3>>();
+        testP1DrawOrLose<SOSolver<int, CudaRootParallel>>();
+        testP1DrawOrLose<SOSolver<int, CudaTreeParallel>>();
+        testP1DrawOrLose<MOSolver<int, CudaRootParallel>>();
+        testTrees<SOSolver<int, CudaRootParallel>>();
+        testTrees<SOSolver<int, CudaTreeParallel>>();
+        testTrees<MOSolver<int, CudaRootParallel>>();
+        {
+            // currentTrees(): the device pool as host nodes (sosolver.h:38-41)
+            P1DrawOrLose game;
+            SOSolver<int, CudaRootParallel> solver {400, 2};
+            solver(game);
+            auto const trees = solver.currentTrees();
+            CHECK(trees.size() == 2);
+            unsigned visits = 0;
+            for (auto const &tree : trees)
+                for (auto const &node : tree->children())
+                    visits += node->visits();
+            CHECK(visits == 400);
+            CHECK(trees.front()->treeToString().find("[M:2 by 1, V/S/A: ") != std::string::npos);
+            MOSolver<int, CudaRootParallel> mo {300, 1};
+            mo(game);
+            auto const maps = mo.currentTrees();
+            CHECK(maps.size() == 1 && maps.front().size() == 2);
+        }
+    }
+    std::printf("%d checks, %d failures\n", checks, failures);
+    return failures ? 1 : 0;
+}
