@@ -35,13 +35,16 @@ ITERATIONS_PER_DECISION = 1_000_000
 DEAL_SEED = 0x1535C75B200           # printed with every line (config.deal_seed)
 # algorithmic node traffic of one KW4 iteration (select 1.28 KB + expand 232 B + backprop 80 B)
 ALGO_BYTES_PER_ITERATION = 1600.0
+# ncu (profiles/r01_c_ncu_raw.txt): warp-instructions executed and DRAM bytes per iteration of the search kernel
+NCU_WARP_INST_PER_ITERATION = 2103.0
+NCU_DRAM_BYTES_PER_ITERATION = (76.225303e9 + 27.621989e9) / 64e6
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--positions", type=int, default=64, help="root positions per step (batch)")
@@ -155,6 +158,7 @@ def b200_arm(args):
     import torch
     import torch.distributed as dist
     from ismcsolver_b200 import capi
+    from ismcsolver_b200.distributed import merge_root_arrays, shard_trees
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,17 +186,19 @@ def b200_arm(args):
     d_iters = torch.zeros(B * T, dtype=torch.int64, device="cuda")
     per = B * stride
 
+    tree_base, my_trees = shard_trees(T * world, world, rank)
+    assert my_trees == T
+
     def desc_for(step):
         # trees are sharded over ranks: rank r owns global trees [r*T, (r+1)*T) of world*T;
         # iterations per position scale with the world size (weak scaling)
         return eng.make_desc(capi.GAME_KW, B, T, iterations=args.iterations * world, seed=0xB200 + step,
-                             trees_total=T * world, tree_base=rank * T)
+                             trees_total=T * world, tree_base=tree_base)
 
     def device_step(step):
         eng.search_device(desc_for(step), d_roots.data_ptr(), d_out.data_ptr(), d_out.data_ptr() + 8 * per,
                           d_out.data_ptr() + 16 * per, d_iters.data_ptr())
-        if world > 1:
-            dist.all_reduce(d_out)
+        merge_root_arrays(d_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,8 +223,7 @@ def b200_arm(args):
         eng.search_device(desc_for(args.warmup + s), d_roots.data_ptr(), d_out.data_ptr(), d_out.data_ptr() + 8 * per,
                           d_out.data_ptr() + 16 * per, d_iters.data_ptr())
         k1.record(stream)
-        if world > 1:
-            dist.all_reduce(d_out)
+        merge_root_arrays(d_out)
         kernel_ms.append((k0, k1))
     ev1.record(stream)
     barrier()
@@ -284,14 +289,22 @@ def b200_arm(args):
             "iterations_done_last_step": iters_done,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None,
+                "traffic": NCU_DRAM_BYTES_PER_ITERATION * per_launch_iters,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel and workload "
+                                  "(profiles/r01_c_ncu_raw.txt), bytes per launch",
+                "algorithmic_bytes_per_launch": per_launch_iters * ALGO_BYTES_PER_ITERATION,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "note": "the path is bound by SM instruction issue, not HBM (see DESIGN.md); "
                         "issue-slot utilisation is in profiles/",
             },
             "issue_roofline": {
-                "peak_warp_inst_per_s": 148 * 4 * sm_max * 1e6,
-                "note": "achieved warp-instructions/s = value x warp-instructions per iteration from ncu (profiles/)",
+                "bound": "sm_issue", "unit": "warp-instructions/s",
+                "peak": 148 * 4 * sm_max * 1e6,
+                "achieved": per_launch_iters / (search_ms * 1e-3) * NCU_WARP_INST_PER_ITERATION,
+                "frac": per_launch_iters / (search_ms * 1e-3) * NCU_WARP_INST_PER_ITERATION / (148 * 4 * sm_max * 1e6),
+                "warp_inst_per_iteration": NCU_WARP_INST_PER_ITERATION,
+                "note": "the binding roofline: 148 SMs x 4 schedulers x SM clock; instructions per iteration from ncu "
+                        "smsp__inst_executed.sum (profiles/r01_c_ncu_raw.txt)",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
