@@ -68,7 +68,7 @@ ISMCTS_DEV uint64_t tree_iterations(uint64_t total, uint32_t trees_total, uint32
     return total / trees_total + ((uint64_t)tree_global < total % trees_total ? 1u : 0u);
 }
 
-enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
+enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2, kBarrier = 3 };
 
 // Which kinds of micro-step a pass performs (the same for all lanes of the warp).
 struct PassPlan { bool chance, move, tree; };
@@ -103,6 +103,9 @@ struct Schedule {
             const bool both = lo >= split_min;
             plan.chance = (both || n_chance >= n_move) && n_chance != 0;
             plan.move = (both || n_move > n_chance) && n_move != 0;
+        } else if (mode == 4 || mode == 5) {   // phases: all chance events first, then moves (4: + iteration barrier)
+            plan.chance = n_chance != 0;
+            plan.move = !plan.chance && n_move != 0;
         } else {                               // stay with a kind until few lanes want it
             const uint32_t n_cur = current == 0 ? n_chance : n_move, n_other = current == 0 ? n_move : n_chance;
             if (n_cur < split_min && n_other > n_cur) current ^= 1u;
@@ -221,7 +224,15 @@ struct Lane {
             P.playout_out[gtid] = (g.outcome() & 0xFFu) | ((plies & 0xFFFu) << 8) | ((rng.consumed() & 0xFFFu) << 20);
         }
         ++done;
-        if (budget_left()) start_iteration(); else phase = kDone;
+        if (P.sched_mode == 4) phase = kBarrier;              // wait for the other lanes of the warp
+        else if (budget_left()) start_iteration();
+        else phase = kDone;
+    }
+
+    // Iteration barrier (schedule mode 4): called when every lane still at work waits at it.
+    ISMCTS_DEV void leave_barrier()
+    {
+        if (phase == kBarrier) { if (budget_left()) start_iteration(); else phase = kDone; }
     }
 
     template <class S> ISMCTS_DEV static double slot_prob(const S& s) { if constexpr (S::kExp3) return s.prob; else return 1.0; }
@@ -379,7 +390,7 @@ struct Lane {
     ISMCTS_DEV Wants classify() const
     {
         Wants w;
-        const bool playing = phase != kDone;
+        const bool playing = phase != kDone && phase != kBarrier;
         w.chance = playing && g.chance_pending();
         w.over = playing && !w.chance && g.terminal();
         w.tree = w.over || (playing && !w.chance && phase == kSelect);
@@ -420,6 +431,7 @@ struct Lane {
                            n_tree = popc32(warp_ballot(w.tree));
             const PassPlan plan = sched.plan_pass(n_chance, n_move, n_tree, pass);
             act(w, plan, pass, gtid);
+            if (P.sched_mode == 4 && n_chance + n_move + n_tree == 0) leave_barrier();
         }
     }
 };
