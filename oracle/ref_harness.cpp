@@ -219,6 +219,7 @@ int usage()
         "ref_harness mnk-stats <hex mnk_state> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
         "ref_harness kw-playouts <hex kw_state> <count>\n"
         "ref_harness kw-time <players> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
+        "ref_harness kw-vs-random <players> <seq|root> <iterations> <threads> <games>\n"
         "ref_harness cores\n");
     return 2;
 }
@@ -390,6 +391,45 @@ int main(int argc, char **argv)
             std::cout.flush();
         }
         std::cout << "]\n";
+        return 0;
+    }
+    if (cmd == "kw-vs-random" && argc == 7) {
+        // test/benchmark.cpp:73-89,144-151: player 0 is the solver, the others move uniformly at random
+        unsigned const players = unsigned(std::atoi(argv[2]));
+        std::string const policy = argv[3];
+        std::size_t const it = std::strtoull(argv[4], nullptr, 10);
+        unsigned const threads = unsigned(std::atoi(argv[5]));
+        unsigned const games = unsigned(std::atoi(argv[6]));
+        std::vector<unsigned> wins(players, 0);
+        unsigned long decisions = 0;
+        double seconds = 0;
+        SOSolver<Card, Sequential> seq {it};
+        SOSolver<Card, RootParallel> root {it, threads};
+        for (unsigned g = 0; g < games; ++g) {
+            KnockoutWhist game {players};
+            for (;;) {
+                auto const moves = game.validMoves();
+                if (moves.empty())
+                    break;
+                if (game.currentPlayer() == 0) {
+                    auto const t0 = std::chrono::steady_clock::now();
+                    Card const move = policy == "root" ? root(game) : seq(game);
+                    seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                    ++decisions;
+                    game.doMove(move);
+                } else {
+                    game.doMove(randomElement(moves));
+                }
+            }
+            for (unsigned p = 0; p < players; ++p)
+                if (game.getResult(p) == 1)
+                    ++wins[p];
+        }
+        std::cout << "{\"games\": " << games << ", \"iterations\": " << it << ", \"decisions\": " << decisions
+                  << ", \"seconds\": " << seconds << ", \"wins\": [";
+        for (unsigned p = 0; p < players; ++p)
+            std::cout << (p ? ", " : "") << wins[p];
+        std::cout << "]}\n";
         return 0;
     }
     return usage();
