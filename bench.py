@@ -193,7 +193,7 @@ def b200_arm(args):
         # trees are sharded over ranks: rank r owns global trees [r*T, (r+1)*T) of world*T;
         # iterations per position scale with the world size (weak scaling)
         return eng.make_desc(capi.GAME_KW, B, T, iterations=args.iterations * world, seed=0xB200 + step,
-                             trees_total=T * world, tree_base=tree_base)
+                             trees_total=T * world, tree_base=tree_base, flags=capi.FLAG_KW_MAX4)
 
     def device_step(step):
         eng.search_device(desc_for(step), d_roots.data_ptr(), d_out.data_ptr(), d_out.data_ptr() + 8 * per,

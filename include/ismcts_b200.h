@@ -150,6 +150,10 @@ int ismcts_set_stream(ismcts_ctx* ctx, void* cuda_stream);
  * shared tree searched by `lanes` iterations in flight with virtual loss; lanes in bits 8..23. */
 #define ISMCTS_FLAG_SHARED_TREE 1u
 #define ISMCTS_FLAG_LANES_SHIFT 8
+/* Knockout Whist: the caller guarantees that no position has more than four players, which lets the
+ * search keep more games per SM (ismcts_search sets it itself from the host records; callers of
+ * ismcts_search_device may set it). */
+#define ISMCTS_FLAG_KW_MAX4 2u
 
 typedef struct ismcts_search_desc {
     uint32_t game;          /* ISMCTS_GAME_* */

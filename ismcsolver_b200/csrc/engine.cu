@@ -9,6 +9,7 @@
 #include "lane_search.cuh"
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
+#include "kw_jobs.cuh"
 
 #include <cuda_runtime.h>
 
@@ -74,6 +75,20 @@ __global__ void collect_roots_kernel(SearchParams P)
     if (i < P.n_positions * P.trees) collect_roots<Game, Slot, kKind>(P, i);
 }
 
+// The headline path with the game states in shared memory and K jobs (trees) per lane (kw_jobs.cuh).
+template <uint32_t K, uint32_t NP, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) kw_jobs_kernel(SearchParams P, uint32_t* paths)
+{
+    extern __shared__ uint64_t smem[];
+    KwJobs<K, NP> jobs(P);
+    jobs.bind(reinterpret_cast<uint32_t*>(smem), kThreads, blockIdx.x * (K * kThreads));
+    jobs.path_base = paths;
+    jobs.deadline = P.iterations > 0 ? 0 : global_timer_ns() + P.time_ns;
+    jobs.init_lane(threadIdx.x);
+    jobs.run(threadIdx.x);
+    jobs.finish_lane(threadIdx.x);
+}
+
 template <class Game>
 __global__ void __launch_bounds__(kBlock) playout_kernel(SearchParams P, uint32_t per_position)
 {
@@ -107,6 +122,9 @@ struct ismcts_ctx {
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
     uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
+    uint32_t* paths = nullptr;    size_t paths_bytes = 0;    // kw_jobs kernel: descent paths, one row per tree
+    int kernel_version = 2;       // 1: lane_search.cuh for everything; 2: kw_jobs.cuh for KW/SO/UCB1; ISMCTS_KERNEL
+    int jobs_per_lane = 2;        // ISMCTS_JOBS_PER_LANE (2 or 4)
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD /
     // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT override
@@ -185,6 +203,8 @@ int ismcts_create(int device, ismcts_ctx** out)
     if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(v);
     if (const char* v = std::getenv("ISMCTS_SCHED_MODE")) ctx->sched_mode = (uint32_t)std::atoi(v);
     if (const char* v = std::getenv("ISMCTS_SCHED_SPLIT")) ctx->sched_split_min = (uint32_t)std::atoi(v);
+    if (const char* v = std::getenv("ISMCTS_KERNEL")) ctx->kernel_version = std::atoi(v);
+    if (const char* v = std::getenv("ISMCTS_JOBS_PER_LANE")) ctx->jobs_per_lane = std::atoi(v);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -195,7 +215,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
-    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters);
+    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters); cudaFree(ctx->paths);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -252,11 +272,11 @@ static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
     if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
     if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
-        if ((d->flags & 0xFEu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
+        if ((d->flags & 0xFCu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
         if ((d->flags >> ISMCTS_FLAG_LANES_SHIFT) == 0) return fail(ctx, ISMCTS_ERR_INVALID, "shared tree: lanes must be > 0");
         if (d->solver != ISMCTS_SOLVER_SO || d->policy != ISMCTS_POLICY_UCB1)
             return fail(ctx, ISMCTS_ERR_INVALID, "shared trees (tree parallelisation) are available for SO-ISMCTS with UCB1");
-    } else if (d->flags != 0) {
+    } else if ((d->flags & ~ISMCTS_FLAG_KW_MAX4) != 0) {
         return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
     }
     if (d->n_positions == 0 || d->trees == 0) return fail(ctx, ISMCTS_ERR_INVALID, "n_positions and trees must be > 0");
@@ -312,6 +332,31 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
     }
 }
 
+template <uint32_t K, uint32_t NP, int kThreads, int kMinBlocks>
+static int launch_kw_jobs_variant(ismcts_ctx* ctx, const SearchParams& P, uint32_t tables)
+{
+    const size_t smem = (size_t)KwJobs<K, NP>::kWordsPerJob * K * kThreads * sizeof(uint32_t);
+    auto kernel = kw_jobs_kernel<K, NP, kThreads, kMinBlocks>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t per_cta = K * kThreads;
+    kernel<<<(tables + per_cta - 1) / per_cta, kThreads, smem, ctx->stream>>>(P, ctx->paths);
+    return ISMCTS_OK;
+}
+
+// Knockout Whist, SO-ISMCTS, UCB1, private trees: the jobs-in-shared-memory kernel.
+static int launch_kw_jobs(ismcts_ctx* ctx, const SearchParams& P, uint32_t tables, bool max4)
+{
+    int rc = ensure(ctx, ctx->paths, ctx->paths_bytes, (size_t)tables * KwGame::kMaxDepth * sizeof(uint32_t));
+    if (rc) return rc;
+    if (max4) {
+        // 26 words = 104 B per job: 512 jobs per CTA of 256 threads (K = 2), four CTAs per SM
+        if (ctx->jobs_per_lane == 4) return launch_kw_jobs_variant<4, 4, 128, 4>(ctx, P, tables);
+        return launch_kw_jobs_variant<2, 4, 256, 4>(ctx, P, tables);
+    }
+    // up to 7 players: 32 words = 128 B per job, three CTAs per SM
+    return launch_kw_jobs_variant<2, 7, 256, 3>(ctx, P, tables);
+}
+
 template <class Game>
 static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_desc* d, const void* d_roots, uint32_t lanes)
 {
@@ -329,7 +374,12 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
         ctx->launches += 3;
     } else {
         if (so && ucb) {
-            launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            if (Game::kGameId == ISMCTS_GAME_KW && ctx->kernel_version == 2) {
+                rc = launch_kw_jobs(ctx, P, tables, (d->flags & ISMCTS_FLAG_KW_MAX4) != 0);
+                if (rc) return rc;
+            } else {
+                launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            }
             collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else if (so) {
             launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
@@ -508,7 +558,15 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->roots, roots, root_bytes, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t* dv = ctx->out; uint64_t* ds = dv + per_arr; uint64_t* da = ds + per_arr; uint64_t* di = da + per_arr;
-    rc = ismcts_search_device(ctx, d, ctx->roots, dv, ds, da, di);
+    ismcts_search_desc desc = *d;
+    if (d->game == ISMCTS_GAME_KW) {
+        // positions with at most four players use the denser shared-memory layout of the jobs kernel
+        bool max4 = true;
+        for (uint32_t p = 0; p < d->n_positions; ++p)
+            max4 = max4 && ((const ismcts_kw_state*)((const uint8_t*)roots + p * state))->num_players <= 4;
+        if (max4) desc.flags |= ISMCTS_FLAG_KW_MAX4; else desc.flags &= ~ISMCTS_FLAG_KW_MAX4;
+    }
+    rc = ismcts_search_device(ctx, &desc, ctx->roots, dv, ds, da, di);
     if (rc) return rc;
     // who moves at each root (for dumps of MO searches)
     ctx->last_root_player.resize(d->n_positions);

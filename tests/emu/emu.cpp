@@ -10,6 +10,7 @@
 #include "../../ismcsolver_b200/csrc/lane_search.cuh"
 #include "../../ismcsolver_b200/csrc/kw_game.cuh"
 #include "../../ismcsolver_b200/csrc/mnk_game.cuh"
+#include "../../ismcsolver_b200/csrc/kw_jobs.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -195,11 +196,94 @@ static int shared_search_t(const void* root, uint64_t iterations, uint32_t width
     return 0;
 }
 
+// kw_jobs.cuh on the host: one CTA of `threads` lanes with K jobs each (jobs = trees 0.. of position 0),
+// advanced pass by pass with the warp votes computed over all lanes.  Writes tree `dump` in creation order.
+template <uint32_t K, uint32_t NP>
+static int kw_jobs_search_t(const void* root, uint64_t iterations_per_tree, uint32_t threads, uint32_t trees, uint64_t seed,
+                            uint32_t dump, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* passes)
+{
+    using Jobs = KwJobs<K, NP>;
+    using Slot = typename Jobs::Slot;
+    uint32_t log2cap = 4;
+    while (((uint64_t)1 << log2cap) < 2 * (iterations_per_tree + 2)) ++log2cap;
+    std::vector<Slot> pool((size_t)trees << log2cap);
+    std::memset((void*)pool.data(), 0, pool.size() * sizeof(Slot));
+    std::vector<double> ln(iterations_per_tree + 300);
+    ln[0] = 0.0;
+    for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
+    std::vector<uint64_t> v(64), s2(64), a(64), it(trees);
+    KwGame::Prepared prepared;
+    uint64_t prep_scratch[KwGame::kHandWords];
+    KwGame::prepare((const KwGame::Root*)root, &prepared, prep_scratch);
+    SearchParams P;
+    std::memset(&P, 0, sizeof P);
+    P.prepared = &prepared; P.n_positions = 1; P.trees = trees; P.trees_total = trees; P.iterations = iterations_per_tree * trees;
+    P.seed = seed; P.exploration = 0.7; P.pool = pool.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
+    P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
+    P.visits = v.data(); P.score2 = s2.data(); P.avail = a.data(); P.iters_done = it.data();
+    P.tree_thresh = g_thresh; P.tree_period = g_period; P.lanes_per_tree = 1;
+    std::vector<uint64_t> smem((size_t)Jobs::kWordsPerJob * K * threads / 2 + 8);
+    std::vector<uint32_t> paths((size_t)trees * KwGame::kMaxDepth);
+    Jobs jobs(P);
+    jobs.bind(reinterpret_cast<uint32_t*>(smem.data()), threads, 0);
+    jobs.path_base = paths.data();
+    jobs.deadline = 0;
+    for (uint32_t t = 0; t < threads; ++t) jobs.init_lane(t);
+    *passes = 0;
+    for (uint32_t pass = 0;; ++pass) {
+        uint32_t nc = 0, nm = 0, nt = 0, live = 0;
+        for (uint32_t t = 0; t < threads; ++t) {
+            const uint32_t bits = jobs.classify(t);
+            nc += bits & 1u; nm += (bits >> 1) & 1u; nt += (bits >> 2) & 1u; live += (bits >> 3) & 1u;
+        }
+        if (!live) break;
+        const uint32_t kind = Jobs::choose_kind(nc, nm, nt, P.tree_thresh, P.tree_period, pass);
+        for (uint32_t t = 0; t < threads; ++t) jobs.act(t, kind);
+        if ((pass & 3u) == 3u) for (uint32_t t = 0; t < threads; ++t) jobs.refill_pass(t);
+        ++*passes;
+    }
+    for (uint32_t t = 0; t < threads; ++t) jobs.finish_lane(t);
+    // dump tree `dump`
+    const Slot* table = pool.data() + ((size_t)dump << log2cap);
+    const size_t cap = (size_t)1 << log2cap;
+    std::vector<std::pair<uint32_t, uint32_t>> members;
+    for (size_t i = 0; i < cap; ++i) if (table[i].key != 0) members.emplace_back(i == 0 ? 0u : table[i].created, (uint32_t)i);
+    std::sort(members.begin(), members.end());
+    *count = (uint32_t)members.size();
+    if (members.size() > capacity) return 5;
+    std::vector<uint32_t> index_of_slot(cap, 0);
+    for (size_t k = 0; k < members.size(); ++k) index_of_slot[members[k].second] = (uint32_t)k;
+    for (size_t k = 0; k < members.size(); ++k) {
+        const Slot& sl = table[members[k].second];
+        ismcts_node_rec& r = nodes[k];
+        if (sl.key == kRootKey) { r.parent = 0; r.move = 0; }
+        else { r.parent = index_of_slot[slot_parent_of(sl.key)]; r.move = slot_move_of(sl.key); }
+        r.player = sl.player; r.visits = sl.visits; r.score2 = sl.score2; r.avail = sl.avail;
+        r.score = 0.5 * (double)sl.score2; r.prob = 1.0;
+    }
+    return it[dump] == iterations_per_tree ? 0 : 6;
+}
+
 extern "C" {
 
 // Schedule of the search loop (when pending tree operations run); results must not depend on it.
 void emu_set_schedule(uint32_t thresh, uint32_t period) { g_thresh = thresh; g_period = period; }
 void emu_set_schedule_mode(uint32_t mode, uint32_t split_min) { g_mode = mode; g_split = split_min; }
+
+int emu_kw_jobs_search(const void* root, uint64_t iterations_per_tree, uint32_t jobs_per_lane, uint32_t players_stored,
+                       uint32_t threads, uint32_t trees, uint64_t seed, uint32_t dump, ismcts_node_rec* nodes,
+                       uint32_t capacity, uint32_t* count, uint64_t* passes)
+{
+    if (jobs_per_lane == 2 && players_stored == 4)
+        return kw_jobs_search_t<2, 4>(root, iterations_per_tree, threads, trees, seed, dump, nodes, capacity, count, passes);
+    if (jobs_per_lane == 4 && players_stored == 4)
+        return kw_jobs_search_t<4, 4>(root, iterations_per_tree, threads, trees, seed, dump, nodes, capacity, count, passes);
+    if (jobs_per_lane == 2 && players_stored == 7)
+        return kw_jobs_search_t<2, 7>(root, iterations_per_tree, threads, trees, seed, dump, nodes, capacity, count, passes);
+    if (jobs_per_lane == 1 && players_stored == 7)
+        return kw_jobs_search_t<1, 7>(root, iterations_per_tree, threads, trees, seed, dump, nodes, capacity, count, passes);
+    return 2;
+}
 
 int emu_shared_search(uint32_t game, const void* root, uint64_t iterations, uint32_t width, uint64_t seed,
                       ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* done)
