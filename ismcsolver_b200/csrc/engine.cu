@@ -123,7 +123,7 @@ struct ismcts_ctx {
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
     uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
     uint32_t* paths = nullptr;    size_t paths_bytes = 0;    // kw_jobs kernel: descent paths, one row per tree
-    int kernel_version = 2;       // 1: lane_search.cuh for everything; 2: kw_jobs.cuh for KW/SO/UCB1; ISMCTS_KERNEL
+    int kernel_version = 1;       // 1: lane_search.cuh for everything; 2: kw_jobs.cuh (experimental) for KW/SO/UCB1; ISMCTS_KERNEL
     int jobs_per_lane = 2;        // ISMCTS_JOBS_PER_LANE (2 or 4)
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD /
