@@ -38,10 +38,11 @@ public:
         PodGame const &pod = MOSolver::podOf(rootState);
         std::vector<unsigned char> state(pod.podSize());
         pod.exportPod(state.data());
-        auto const &policy = this->config().seqTreePolicy;
+        auto const policy = this->kernelPolicy(rootState);
+        m_policyKind = policy.kind;
         m_players = rootState.players();
         auto const &result = this->search(pod.podKind(), state.data(), ISMCTS_SOLVER_MO,
-                                          std::remove_reference_t<decltype(policy)>::kernelPolicy, policy.exploration());
+                                          policy.kind, policy.exploration);
         m_treesValid = true;
         if (result.bestMove == 0xFFFFFFFFu)
             return Move{};
@@ -57,7 +58,7 @@ public:
         for (unsigned int t = 0; t < this->materialisedTrees(); ++t) {
             TreeMap map;
             for (Player p : m_players)
-                map.emplace(p, MOSolver::materialise(this->dumpTree(t, p)));
+                map.emplace(p, MOSolver::materialiseAs(m_policyKind, this->dumpTree(t, p)));
             trees.push_back(std::move(map));
         }
         return trees;
@@ -66,6 +67,7 @@ public:
 private:
     std::vector<Player> m_players;
     bool m_treesValid {false};
+    std::uint32_t m_policyKind {ISMCTS_POLICY_UCB1};
 };
 
 } // ISMCTS

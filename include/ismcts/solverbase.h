@@ -62,15 +62,38 @@ protected:
         if (!pod)
             throw std::invalid_argument("ISMCTS CUDA policies need a game with a device form (ISMCTS::PodGame); "
                                         "there is no CPU fallback");
-        if (game.currentMoveSimultaneous())
-            throw std::invalid_argument("ISMCTS CUDA policies: simultaneous-move games are not supported yet");
         return *pod;
+    }
+
+    /// Which bandit the kernels run and with which constant: the simultaneous-move policy when the
+    /// game's moves are simultaneous, else the sequential one (selectChild / newRoot / newChild,
+    /// solverbase.h:58-80).  The choice is made once per search, from the root position.
+    struct KernelPolicy { std::uint32_t kind; double exploration; };
+    KernelPolicy kernelPolicy(Game<Move> const &game) const
+    {
+        if (game.currentMoveSimultaneous())
+            return {Config::SimTreePolicy::kernelPolicy, m_config.simTreePolicy.exploration()};
+        return {Config::SeqTreePolicy::kernelPolicy, m_config.seqTreePolicy.exploration()};
+    }
+
+    /// Builds host nodes from one tree of the device pool, with the node type of the policy used.
+    static RootNode materialiseAs(std::uint32_t kernelPolicyKind, std::vector<ismcts_node_rec> const &records)
+    {
+        if (kernelPolicyKind == ISMCTS_POLICY_EXP3)
+            return materialiseWith<EXPNode<Move>>(records);
+        return materialiseWith<UCBNode<Move>>(records);
     }
 
     /// Builds host nodes from one tree of the device pool (records in creation order, root first).
     static RootNode materialise(std::vector<ismcts_node_rec> const &records)
     {
-        using SeqNode = typename SeqPolicy::Node;
+        return materialiseWith<typename SeqPolicy::Node>(records);
+    }
+
+private:
+    template<class SeqNode>
+    static RootNode materialiseWith(std::vector<ismcts_node_rec> const &records)
+    {
         if (records.empty())
             return std::make_shared<SeqNode>();
         std::vector<Node<Move> *> byIndex(records.size(), nullptr);
@@ -86,7 +109,6 @@ protected:
         return root;
     }
 
-private:
     static void fill(UCBNode<Move> *node, ismcts_node_rec const &r)
     {
         node->setVisits(r.visits);

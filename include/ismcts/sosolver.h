@@ -33,9 +33,10 @@ public:
         PodGame const &pod = SOSolver::podOf(rootState);
         std::vector<unsigned char> state(pod.podSize());
         pod.exportPod(state.data());
-        auto const &policy = this->config().seqTreePolicy;
+        auto const policy = this->kernelPolicy(rootState);
+        m_policyKind = policy.kind;
         auto const &result = this->search(pod.podKind(), state.data(), ISMCTS_SOLVER_SO,
-                                          std::remove_reference_t<decltype(policy)>::kernelPolicy, policy.exploration());
+                                          policy.kind, policy.exploration);
         m_treesValid = true;
         if (result.bestMove == 0xFFFFFFFFu)
             return Move{};
@@ -50,12 +51,13 @@ public:
         if (!m_treesValid)
             return trees;
         for (unsigned int t = 0; t < this->materialisedTrees(); ++t)
-            trees.push_back(SOSolver::materialise(this->dumpTree(t)));
+            trees.push_back(SOSolver::materialiseAs(m_policyKind, this->dumpTree(t)));
         return trees;
     }
 
 private:
     bool m_treesValid {false};
+    std::uint32_t m_policyKind {ISMCTS_POLICY_UCB1};
 };
 
 } // ISMCTS

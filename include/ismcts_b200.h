@@ -34,7 +34,7 @@ enum {
 };
 
 /* ------------------------------------------------------------------- games */
-enum { ISMCTS_GAME_KW = 0, ISMCTS_GAME_MNK = 1 };
+enum { ISMCTS_GAME_KW = 0, ISMCTS_GAME_MNK = 1, ISMCTS_GAME_GOOF = 2 };
 enum { ISMCTS_SOLVER_SO = 0, ISMCTS_SOLVER_MO = 1 };
 enum { ISMCTS_POLICY_UCB1 = 0, ISMCTS_POLICY_EXP3 = 1 };
 
@@ -79,10 +79,31 @@ typedef struct ismcts_mnk_state {
     uint8_t pad[3];
 } ismcts_mnk_state;                        /* 72 bytes */
 
+/*
+ * Two-player Goofspiel position (test/common/goofspiel.h:26-49): prize suit hearts, player 0 bids
+ * spades, player 1 clubs, player 2 is the environment that turns over the prizes and reveals the bids.
+ * Every move is simultaneous (goofspiel.cpp:80-83), so searches use the simultaneous-move policy
+ * (EXP3, config.h:20-26).  Ranks are 0..12 (Two..Ace, card.h:13-15); a card's value is Ace 1, Two 2,
+ * ... King 13 (goofspiel.cpp:17-36).  Move ids are card ids: a bid of player 0 is rank + 39, of
+ * player 1 rank + 0, a prize rank + 26, and the environment's reveal move is Card{} = 0
+ * (goofspiel.cpp:140-146).
+ */
+typedef struct ismcts_goof_state {
+    uint64_t prize_order;   /* 4 bits per prize not turned over yet, entry n_prizes-1 is next (m_prizes.back()) */
+    uint16_t hands[2];      /* bit r: the player still holds rank r (m_hands) */
+    uint8_t n_prizes;
+    uint8_t player;         /* m_player: 0, 1 or 2 */
+    uint8_t draw_prize;     /* m_drawPrize */
+    uint8_t current_prize;  /* rank of m_currentPrize */
+    uint8_t moves[2];       /* ranks bid this turn (m_moves) */
+    uint8_t scores[2];      /* m_scores */
+    uint8_t pad[4];
+} ismcts_goof_state;        /* 24 bytes */
+
 /* Size in bytes of one root position record for a game kind (0 if unknown). */
 size_t ismcts_state_size(uint32_t game);
 /* Number of move ids the per-position output arrays are strided by:
- * 64 for Knockout Whist (52 used), 256 for m,n,k. */
+ * 64 for Knockout Whist and Goofspiel (52 used), 256 for m,n,k. */
 uint32_t ismcts_move_stride(uint32_t game);
 
 /* ---------------------------------------------------------- host game helpers
@@ -111,6 +132,15 @@ void ismcts_mnk_legal(const ismcts_mnk_state* s, uint64_t legal[4]);
 int ismcts_mnk_apply(ismcts_mnk_state* s, uint32_t move);
 /* getResult*2 (mnkgame.cpp:56-59). */
 int ismcts_mnk_result2(const ismcts_mnk_state* s, uint32_t player);
+
+/* Goofspiel::Goofspiel (goofspiel.cpp:52-63): full hands, the prizes shuffled by Philox stream `stream`. */
+int ismcts_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out);
+/* validMoves (goofspiel.cpp:130-153) as a mask of move ids. */
+uint64_t ismcts_goof_legal(const ismcts_goof_state* s);
+/* doMove (goofspiel.cpp:90-117). */
+int ismcts_goof_apply(ismcts_goof_state* s, uint32_t move);
+/* getResult*2 (goofspiel.cpp:119-128). */
+int ismcts_goof_result2(const ismcts_goof_state* s, uint32_t player);
 
 /* ------------------------------------------------------------------ context */
 typedef struct ismcts_ctx ismcts_ctx;

@@ -13,7 +13,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GAME_KW, GAME_MNK = 0, 1
+GAME_KW, GAME_MNK, GAME_GOOF = 0, 1, 2
 SOLVER_SO, SOLVER_MO = 0, 1
 POLICY_UCB1, POLICY_EXP3 = 0, 1
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_ILLEGAL_MOVE, ERR_CUDA, ERR_CAPACITY = range(6)
@@ -24,6 +24,7 @@ EXPORTS = [
     "ismcts_state_size", "ismcts_move_stride",
     "ismcts_kw_deal", "ismcts_kw_legal", "ismcts_kw_apply", "ismcts_kw_result2",
     "ismcts_mnk_init", "ismcts_mnk_legal", "ismcts_mnk_apply", "ismcts_mnk_result2",
+    "ismcts_goof_init", "ismcts_goof_legal", "ismcts_goof_apply", "ismcts_goof_result2",
     "ismcts_create", "ismcts_destroy", "ismcts_last_error", "ismcts_set_stream",
     "ismcts_search", "ismcts_search_device", "ismcts_synchronize", "ismcts_dump_tree", "ismcts_dump_tree_of",
     "ismcts_playouts", "ismcts_launch_count", "ismcts_version",
@@ -47,6 +48,15 @@ class MnkState(C.Structure):
         ("stones", (C.c_uint64 * 4) * 2),
         ("m", C.c_uint8), ("n", C.c_uint8), ("k", C.c_uint8), ("player", C.c_uint8),
         ("result2", C.c_int8), ("pad", C.c_uint8 * 3),
+    ]
+
+
+class GoofState(C.Structure):
+    """ismcts_goof_state"""
+    _fields_ = [
+        ("prize_order", C.c_uint64), ("hands", C.c_uint16 * 2), ("n_prizes", C.c_uint8), ("player", C.c_uint8),
+        ("draw_prize", C.c_uint8), ("current_prize", C.c_uint8), ("moves", C.c_uint8 * 2), ("scores", C.c_uint8 * 2),
+        ("pad", C.c_uint8 * 4),
     ]
 
 
@@ -102,6 +112,11 @@ def load_library() -> C.CDLL:
     L.ismcts_mnk_legal.argtypes = [C.POINTER(MnkState), C.POINTER(u64)]
     L.ismcts_mnk_apply.argtypes = [C.POINTER(MnkState), u32]
     L.ismcts_mnk_result2.argtypes = [C.POINTER(MnkState), u32]
+    L.ismcts_goof_init.argtypes = [u64, u32, C.POINTER(GoofState)]
+    L.ismcts_goof_legal.restype = u64
+    L.ismcts_goof_legal.argtypes = [C.POINTER(GoofState)]
+    L.ismcts_goof_apply.argtypes = [C.POINTER(GoofState), u32]
+    L.ismcts_goof_result2.argtypes = [C.POINTER(GoofState), u32]
     L.ismcts_create.argtypes = [i32, C.POINTER(vp)]
     L.ismcts_destroy.restype = None
     L.ismcts_destroy.argtypes = [vp]
@@ -263,3 +278,20 @@ def mnk_legal(s: MnkState) -> list[int]:
 
 def mnk_apply(s: MnkState, move: int) -> int:
     return load_library().ismcts_mnk_apply(C.byref(s), move)
+
+
+def goof_init(seed: int, stream: int = 0) -> GoofState:
+    s = GoofState()
+    rc = load_library().ismcts_goof_init(seed, stream, C.byref(s))
+    if rc != OK:
+        raise EngineError(rc, "ismcts_goof_init")
+    return s
+
+
+def goof_legal(s: GoofState) -> list[int]:
+    mask = int(load_library().ismcts_goof_legal(C.byref(s)))
+    return [c for c in range(64) if mask >> c & 1]
+
+
+def goof_apply(s: GoofState, move: int) -> int:
+    return load_library().ismcts_goof_apply(C.byref(s), move)

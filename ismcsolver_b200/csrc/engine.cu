@@ -9,6 +9,7 @@
 #include "lane_search.cuh"
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
+#include "goof_game.cuh"
 #include "kw_jobs.cuh"
 
 #include <cuda_runtime.h>
@@ -168,12 +169,14 @@ const char* ismcts_version(void) { return "ismcsolver_b200 0.2 (sm_100a)"; }
 
 size_t ismcts_state_size(uint32_t game)
 {
-    return game == ISMCTS_GAME_KW ? sizeof(ismcts_kw_state) : game == ISMCTS_GAME_MNK ? sizeof(ismcts_mnk_state) : 0;
+    return game == ISMCTS_GAME_KW ? sizeof(ismcts_kw_state) : game == ISMCTS_GAME_MNK ? sizeof(ismcts_mnk_state)
+         : game == ISMCTS_GAME_GOOF ? sizeof(ismcts_goof_state) : 0;
 }
 
 uint32_t ismcts_move_stride(uint32_t game)
 {
-    return game == ISMCTS_GAME_KW ? KwGame::kMoveStride : game == ISMCTS_GAME_MNK ? MnkGame::kMoveStride : 0;
+    return game == ISMCTS_GAME_KW ? KwGame::kMoveStride : game == ISMCTS_GAME_MNK ? MnkGame::kMoveStride
+         : game == ISMCTS_GAME_GOOF ? GoofGame::kMoveStride : 0;
 }
 
 int ismcts_create(int device, ismcts_ctx** out)
@@ -252,23 +255,34 @@ static uint32_t ceil_log2(uint64_t x)
     return l;
 }
 
+// Runs f(tag) with tag.game() of the device game class for a game kind.
+template <class G> struct GameTag { using Game = G; };
+template <class F>
+static auto with_game(uint32_t game, F&& f)
+{
+    if (game == ISMCTS_GAME_KW) return f(GameTag<KwGame>{});
+    if (game == ISMCTS_GAME_MNK) return f(GameTag<MnkGame>{});
+    return f(GameTag<GoofGame>{});
+}
+
 static size_t slot_bytes(uint32_t game, uint32_t policy)
 {
-    if (game == ISMCTS_GAME_KW)
-        return policy == ISMCTS_POLICY_UCB1 ? sizeof(SlotUcb<KwGame::Mask>) : sizeof(SlotExp<KwGame::Mask>);
-    return policy == ISMCTS_POLICY_UCB1 ? sizeof(SlotUcb<MnkGame::Mask>) : sizeof(SlotExp<MnkGame::Mask>);
+    return with_game(game, [&](auto tag) {
+        using Mask = typename decltype(tag)::Game::Mask;
+        return policy == ISMCTS_POLICY_UCB1 ? sizeof(SlotUcb<Mask>) : sizeof(SlotExp<Mask>);
+    });
 }
 
 static uint32_t trees_per_lane(uint32_t game, uint32_t solver)
 {
     if (solver == ISMCTS_SOLVER_SO) return 1;
-    return game == ISMCTS_GAME_KW ? KwGame::kMaxPlayers : MnkGame::kMaxPlayers;
+    return with_game(game, [](auto tag) { return (uint32_t) decltype(tag)::Game::kMaxPlayers; });
 }
 
 static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
 {
     if (!ctx || !d) return ISMCTS_ERR_INVALID;
-    if (d->game != ISMCTS_GAME_KW && d->game != ISMCTS_GAME_MNK) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    if (d->game > ISMCTS_GAME_GOOF) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
     if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
     if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
@@ -469,8 +483,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     ctx->last_log2cap = log2cap; ctx->last_lanes = tables; ctx->last_game = d->game;
     ctx->last_solver = d->solver; ctx->last_policy = d->policy;
 
-    if (d->game == ISMCTS_GAME_KW) return launch_search<KwGame>(ctx, P, d, d_roots, lanes);
-    return launch_search<MnkGame>(ctx, P, d, d_roots, lanes);
+    return with_game(d->game, [&](auto tag) { return launch_search<typename decltype(tag)::Game>(ctx, P, d, d_roots, lanes); });
 }
 
 // One lane's table -> node records of the tree rooted at slot `root`, in creation order.
@@ -521,11 +534,11 @@ extern "C" int ismcts_dump_tree_of(ismcts_ctx* ctx, uint32_t dump_index, uint32_
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const bool ucb = ctx->last_policy == ISMCTS_POLICY_UCB1;
-    if (ctx->last_game == ISMCTS_GAME_KW)
-        return ucb ? dump_tree_t<SlotUcb<KwGame::Mask>>(ctx, dump_index, player, nodes, capacity, count)
-                   : dump_tree_t<SlotExp<KwGame::Mask>>(ctx, dump_index, player, nodes, capacity, count);
-    return ucb ? dump_tree_t<SlotUcb<MnkGame::Mask>>(ctx, dump_index, player, nodes, capacity, count)
-               : dump_tree_t<SlotExp<MnkGame::Mask>>(ctx, dump_index, player, nodes, capacity, count);
+    return with_game(ctx->last_game, [&](auto tag) {
+        using Mask = typename decltype(tag)::Game::Mask;
+        return ucb ? dump_tree_t<SlotUcb<Mask>>(ctx, dump_index, player, nodes, capacity, count)
+                   : dump_tree_t<SlotExp<Mask>>(ctx, dump_index, player, nodes, capacity, count);
+    });
 }
 
 extern "C" int ismcts_dump_tree(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes, uint32_t capacity,
@@ -573,7 +586,8 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     for (uint32_t p = 0; p < d->n_positions; ++p) {
         const uint8_t* rec = (const uint8_t*)roots + p * state;
         ctx->last_root_player[p] = d->game == ISMCTS_GAME_KW ? ((const ismcts_kw_state*)rec)->player
-                                                            : ((const ismcts_mnk_state*)rec)->player;
+                                 : d->game == ISMCTS_GAME_MNK ? ((const ismcts_mnk_state*)rec)->player
+                                                              : ((const ismcts_goof_state*)rec)->player;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(out->visits, dv, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (out->score2) CUDA_TRY(ctx, cudaMemcpyAsync(out->score2, ds, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -599,7 +613,7 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
                                uint32_t per_position, uint64_t seed, uint32_t* out_result)
 {
     if (!ctx || !roots || !out_result || n_positions == 0 || per_position == 0) return ISMCTS_ERR_INVALID;
-    if (game != ISMCTS_GAME_KW && game != ISMCTS_GAME_MNK) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    if (game > ISMCTS_GAME_GOOF) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t root_bytes = (size_t)n_positions * ismcts_state_size(game);
     const size_t n = (size_t)n_positions * per_position;
@@ -614,12 +628,14 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
     P.n_positions = n_positions; P.seed = seed; P.playout_out = ctx->play_out;
     P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
     P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
-    rc = game == ISMCTS_GAME_KW ? launch_prepare<KwGame>(ctx, ctx->roots, n_positions)
-                                : launch_prepare<MnkGame>(ctx, ctx->roots, n_positions);
+    rc = with_game(game, [&](auto tag) { return launch_prepare<typename decltype(tag)::Game>(ctx, ctx->roots, n_positions); });
     if (rc) return rc;
     P.prepared = ctx->prepared;
-    if (game == ISMCTS_GAME_KW) playout_kernel<KwGame><<<grid, kBlock, block_smem<KwGame>(), ctx->stream>>>(P, per_position);
-    else playout_kernel<MnkGame><<<grid, kBlock, block_smem<MnkGame>(), ctx->stream>>>(P, per_position);
+    with_game(game, [&](auto tag) {
+        using Game = typename decltype(tag)::Game;
+        playout_kernel<Game><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
+        return 0;
+    });
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out_result, ctx->play_out, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -8,6 +8,7 @@
 #include "philox.cuh"
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
+#include "goof_game.cuh"
 
 #include <cstring>
 
@@ -127,6 +128,73 @@ int ismcts_kw_result2(const ismcts_kw_state* s, uint32_t player)
 {
     if (!s || s->alive_mask == 0) return 0;
     return player == ctz32(s->alive_mask) ? 2 : 0; // getResult, knockoutwhist.cpp:117-120
+}
+
+// ---- Goofspiel (test/common/goofspiel.{h,cpp})
+
+namespace {
+void goof_store(const GoofGame& g, uint32_t n, ismcts_goof_state* s)
+{
+    std::memset(s, 0, sizeof *s);
+    s->hands[0] = (uint16_t)(g.hands & 0x1FFFu); s->hands[1] = (uint16_t)((g.hands >> 16) & 0x1FFFu);
+    s->n_prizes = (uint8_t)n;
+    s->prize_order = n < 16 ? g.order & ((((uint64_t)1 << (4 * n)) - 1u)) : g.order;
+    s->player = (uint8_t)g.player; s->draw_prize = (uint8_t)g.draw_prize; s->current_prize = (uint8_t)g.current_prize;
+    s->moves[0] = (uint8_t)g.move0; s->moves[1] = (uint8_t)g.move1;
+    s->scores[0] = (uint8_t)g.score0; s->scores[1] = (uint8_t)g.score1;
+}
+} // namespace
+
+int ismcts_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out)
+{
+    if (!out) return ISMCTS_ERR_INVALID;
+    // Goofspiel::Goofspiel, goofspiel.cpp:52-63: entry i of the shuffled prizes is a uniformly random prize not placed yet
+    std::memset(out, 0, sizeof *out);
+    uint32_t ring[LaneRng::kRingWords];
+    LaneRng rng;
+    rng.init(seed, stream, kDealTree, ring, 1);
+    rng.begin_iteration(kDealIteration);
+    uint32_t left = 0x1FFFu;
+    for (uint32_t i = 0; i < 13; ++i) {
+        const uint32_t r = kth_bit32(left, rng.below(popc32(left)));
+        left &= ~(1u << r);
+        out->prize_order |= (uint64_t)r << (4 * i);
+        if (rng.low()) rng.refill();
+    }
+    out->hands[0] = out->hands[1] = 0x1FFF;
+    out->n_prizes = 13; out->player = 2; out->draw_prize = 1;
+    return ISMCTS_OK;
+}
+
+uint64_t ismcts_goof_legal(const ismcts_goof_state* s)
+{
+    if (!s) return 0;
+    GoofGame g;
+    g.load(s);
+    // the position as its own player to move sees it: the environment knows which prize comes next
+    if (g.draw_pending()) g.chance_step((uint32_t)((g.order >> (4 * (g.n_prizes() - 1u))) & 15u));
+    return g.legal().w;
+}
+
+int ismcts_goof_apply(ismcts_goof_state* s, uint32_t move)
+{
+    if (!s) return ISMCTS_ERR_INVALID;
+    GoofGame g;
+    g.load(s);
+    uint32_t n = s->n_prizes;
+    if (g.draw_pending()) { g.chance_step((uint32_t)((g.order >> (4 * (n - 1u))) & 15u)); --n; }
+    if (move >= 64 || !((g.legal().w >> move) & 1u)) return ISMCTS_ERR_ILLEGAL_MOVE;
+    g.play(move);
+    goof_store(g, n, s);
+    return ISMCTS_OK;
+}
+
+int ismcts_goof_result2(const ismcts_goof_state* s, uint32_t player)
+{
+    if (!s) return 0;
+    GoofGame g;
+    g.load(s);
+    return (int)g.result2(player);
 }
 
 int ismcts_mnk_init(uint32_t m, uint32_t n, uint32_t k, ismcts_mnk_state* out)

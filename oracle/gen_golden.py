@@ -98,6 +98,23 @@ def main():
         cases.append({"name": "p1-draw-or-lose", "game": "mnk", "state": s.hex(), "solver": solver, "policy": "seq",
                       "iterations": 16, "threads": 1, "reps": 100, **summarise(rows, 256)})
         print("p1-draw-or-lose", solver, cases[-1]["best_counts"], flush=True)
+    # Goofspiel: every move is simultaneous -> EXP3 (solverbase.h:58-64).  Player 0 to move after the first
+    # prize, and player 1 to move after player 0's (hidden) bid (goofspiel.cpp:76-78).
+    for prize, bid, solver in [(11, -1, "so"), (11, 10, "so"), (5, -1, "mo"), (0, 3, "mo")]:
+        g = O.GoofState()
+        rest = [r for r in range(13) if r != prize]
+        g.prize_order = sum(r << (4 * i) for i, r in enumerate(rest))
+        g.n_prizes = 12
+        g.hands[0] = g.hands[1] = 0x1FFF
+        g.current_prize = prize
+        g.player, g.draw_prize = 0, 0
+        if bid >= 0:
+            g.moves[0] = bid
+            g.player = 1
+        rows = json.loads(O.ref_harness("goof-stats", prize, bid, solver, 3000, 60))
+        cases.append({"name": f"goof-prize{prize}-bid{bid}", "game": "goof", "state": g.hex(), "solver": solver + "-sim",
+                      "policy": "seq", "iterations": 3000, "threads": 1, "reps": 60, **summarise(rows, 64)})
+        print(cases[-1]["name"], solver, cases[-1]["best_counts"], flush=True)
     # the reference's own game code: uniform random playouts from its opening position
     play = json.loads(O.ref_harness("kw-playouts", ref_opening, 200000))
     out = {"generator": "oracle/gen_golden.py", "reference": "sfranzen/ismcsolver (unmodified, g++ -O3 -DNDEBUG)",

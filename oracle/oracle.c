@@ -338,11 +338,131 @@ static int omnk_apply(omnk* g, int move, rng* r)
 /* getResult, mnkgame.cpp:56-59. */
 static int omnk_result2(const omnk* g, int player) { return player == 0 ? g->result2 : 2 - g->result2; }
 
+/* ================================================================ Goofspiel */
+
+typedef struct ogoof {
+    unsigned char hand[2][13];
+    unsigned char prize_left[13];
+    int order[13], n;          /* prizes not turned over, order[n-1] next (m_prizes.back()) */
+    int known_order;           /* the observer is the environment: no reshuffle (goofspiel.cpp:69-71) */
+    int next_prize;            /* the prize the environment turns over next, -1 = not determined yet */
+    int current_prize, moves[2], scores[2], player, draw_prize;
+    int hidden_bid_pending;    /* observer 1: player 0's bid is still to be randomised (goofspiel.cpp:76-78) */
+} ogoof;
+
+static int goof_value(int rank) { return rank == 12 ? 1 : rank + 2; } /* goofspiel.cpp:17-36 */
+
+static void ogoof_from_pod(ogoof* g, const ismcts_goof_state* s)
+{
+    memset(g, 0, sizeof *g);
+    for (int p = 0; p < 2; ++p)
+        for (int r = 0; r < 13; ++r) g->hand[p][r] = (unsigned char)((s->hands[p] >> r) & 1);
+    g->n = s->n_prizes;
+    for (int i = 0; i < g->n; ++i) { g->order[i] = (int)((s->prize_order >> (4 * i)) & 15); g->prize_left[g->order[i]] = 1; }
+    g->known_order = 1; /* a position as it is: the order is what it is until a determinisation hides it */
+    g->next_prize = -1;
+    g->current_prize = s->current_prize; g->moves[0] = s->moves[0]; g->moves[1] = s->moves[1];
+    g->scores[0] = s->scores[0]; g->scores[1] = s->scores[1]; g->player = s->player; g->draw_prize = s->draw_prize;
+}
+
+static void ogoof_to_pod(const ogoof* g, ismcts_goof_state* s)
+{
+    memset(s, 0, sizeof *s);
+    for (int p = 0; p < 2; ++p)
+        for (int r = 0; r < 13; ++r) if (g->hand[p][r]) s->hands[p] |= (uint16_t)(1u << r);
+    s->n_prizes = (uint8_t)g->n;
+    for (int i = 0; i < g->n; ++i) s->prize_order |= (uint64_t)g->order[i] << (4 * i);
+    s->current_prize = (uint8_t)g->current_prize; s->moves[0] = (uint8_t)g->moves[0]; s->moves[1] = (uint8_t)g->moves[1];
+    s->scores[0] = (uint8_t)g->scores[0]; s->scores[1] = (uint8_t)g->scores[1];
+    s->player = (uint8_t)g->player; s->draw_prize = (uint8_t)g->draw_prize;
+}
+
+/* The environment's next prize: the back of the known order, or — after a determinisation for a
+ * player, who does not know the order (goofspiel.cpp:69-71) — a uniformly random remaining prize
+ * (shuffling all remaining prizes at once and turning them over one by one is the same distribution). */
+static void ogoof_draw_prize(ogoof* g, rng* r)
+{
+    int prize;
+    if (g->known_order) {
+        (void)rng_below(r, 1);
+        if (r->cnt) r->cnt->chance_picks++;
+        prize = g->order[g->n - 1];
+        g->prize_left[prize] = 0;
+    } else {
+        prize = set_draw(g->prize_left, 13, r);
+    }
+    int k = 0;
+    for (int i = 0; i < g->n; ++i) if (g->order[i] != prize) g->order[k++] = g->order[i];
+    g->n = k;
+    g->next_prize = prize;
+}
+
+/* validMoves, goofspiel.cpp:130-153. */
+static int ogoof_legal(const ogoof* g, uint16_t* moves)
+{
+    int n = 0;
+    if (g->player == 0) { for (int r = 0; r < 13; ++r) if (g->hand[0][r]) moves[n++] = (uint16_t)(39 + r); }
+    else if (g->player == 1) { for (int r = 0; r < 13; ++r) if (g->hand[1][r]) moves[n++] = (uint16_t)r; }
+    else if (!g->draw_prize) moves[n++] = 0;                       /* the dummy reveal move Card{} */
+    else if (g->next_prize >= 0) moves[n++] = (uint16_t)(26 + g->next_prize);
+    return n;
+}
+
+/* doMove + handleP2Turn, goofspiel.cpp:90-117. */
+static int ogoof_apply(ogoof* g, int move, rng* r)
+{
+    if (r && r->cnt) r->cnt->plies++;
+    if (g->player < 2) {
+        const int rank = move - (g->player == 0 ? 39 : 0);
+        if (rank < 0 || rank > 12 || !g->hand[g->player][rank]) return ISMCTS_ERR_ILLEGAL_MOVE;
+        g->moves[g->player] = rank;
+        g->player++;
+        return 0;
+    }
+    if (g->draw_prize) {
+        if (g->next_prize < 0 || move != 26 + g->next_prize) return ISMCTS_ERR_ILLEGAL_MOVE;
+        g->current_prize = g->next_prize;
+        g->next_prize = -1;
+        g->player = 0;
+        g->draw_prize = 0;
+        return 0;
+    }
+    if (g->moves[0] != g->moves[1]) {
+        const int w = goof_value(g->moves[0]) > goof_value(g->moves[1]) ? 0 : 1;
+        g->scores[w] += goof_value(g->current_prize);
+    }
+    g->hand[0][g->moves[0]] = 0;
+    g->hand[1][g->moves[1]] = 0;
+    g->draw_prize = 1;
+    if (g->n > 0 && r) ogoof_draw_prize(g, r);
+    return 0;
+}
+
+/* getResult, goofspiel.cpp:119-128. */
+static int ogoof_result2(const ogoof* g, int player)
+{
+    if (player == 2) return 0;
+    if (g->scores[0] == g->scores[1]) return 1;
+    return g->scores[player] > g->scores[1 - player] ? 2 : 0;
+}
+
+/* cloneAndRandomise, goofspiel.cpp:65-81. */
+static void ogoof_determinise(ogoof* g, int observer, rng* r)
+{
+    g->known_order = observer == 2;
+    if (observer == 1) {
+        unsigned char pick[13];
+        memcpy(pick, g->hand[0], sizeof pick);
+        g->moves[0] = set_draw(pick, 13, r);
+    }
+    if (g->player == 2 && g->draw_prize && g->next_prize < 0 && g->n > 0) ogoof_draw_prize(g, r);
+}
+
 /* ============================================================ generic game */
 
 typedef struct ogame {
     uint32_t kind;
-    union { okw kw; omnk mnk; } u;
+    union { okw kw; omnk mnk; ogoof goof; } u;
 } ogame;
 
 static int og_load(ogame* g, uint32_t kind, const void* root)
@@ -350,27 +470,46 @@ static int og_load(ogame* g, uint32_t kind, const void* root)
     g->kind = kind;
     if (kind == ISMCTS_GAME_KW) okw_from_pod(&g->u.kw, (const ismcts_kw_state*)root);
     else if (kind == ISMCTS_GAME_MNK) omnk_from_pod(&g->u.mnk, (const ismcts_mnk_state*)root);
+    else if (kind == ISMCTS_GAME_GOOF) ogoof_from_pod(&g->u.goof, (const ismcts_goof_state*)root);
     else return ISMCTS_ERR_INVALID;
     return 0;
 }
-static int og_player(const ogame* g) { return g->kind == ISMCTS_GAME_KW ? g->u.kw.player : g->u.mnk.player; }
+static int og_player(const ogame* g)
+{ return g->kind == ISMCTS_GAME_KW ? g->u.kw.player : g->kind == ISMCTS_GAME_MNK ? g->u.mnk.player : g->u.goof.player; }
 static int og_legal(const ogame* g, uint16_t* mv)
-{ return g->kind == ISMCTS_GAME_KW ? okw_legal(&g->u.kw, mv) : omnk_legal(&g->u.mnk, mv); }
+{
+    if (g->kind == ISMCTS_GAME_KW) return okw_legal(&g->u.kw, mv);
+    if (g->kind == ISMCTS_GAME_MNK) return omnk_legal(&g->u.mnk, mv);
+    return ogoof_legal(&g->u.goof, mv);
+}
 static void og_apply(ogame* g, int mv, rng* r)
-{ if (g->kind == ISMCTS_GAME_KW) okw_apply(&g->u.kw, mv, r); else omnk_apply(&g->u.mnk, mv, r); }
+{
+    if (g->kind == ISMCTS_GAME_KW) okw_apply(&g->u.kw, mv, r);
+    else if (g->kind == ISMCTS_GAME_MNK) omnk_apply(&g->u.mnk, mv, r);
+    else ogoof_apply(&g->u.goof, mv, r);
+}
 static int og_result2(const ogame* g, int p)
-{ return g->kind == ISMCTS_GAME_KW ? okw_result2(&g->u.kw, p) : omnk_result2(&g->u.mnk, p); }
+{
+    if (g->kind == ISMCTS_GAME_KW) return okw_result2(&g->u.kw, p);
+    if (g->kind == ISMCTS_GAME_MNK) return omnk_result2(&g->u.mnk, p);
+    return ogoof_result2(&g->u.goof, p);
+}
 static void og_determinise(ogame* g, int obs, rng* r)
-{ if (g->kind == ISMCTS_GAME_KW) okw_determinise(&g->u.kw, obs, r); /* m,n,k: plain copy, mnkgame.cpp:34-37 */ }
+{
+    if (g->kind == ISMCTS_GAME_KW) okw_determinise(&g->u.kw, obs, r);
+    else if (g->kind == ISMCTS_GAME_GOOF) ogoof_determinise(&g->u.goof, obs, r);
+    /* m,n,k: plain copy, mnkgame.cpp:34-37 */
+}
 /* players(), knockoutwhist.cpp:90-93 / mnkgame.cpp:76-79 */
 static int og_players(const ogame* g, int* out)
 {
     int n = 0;
     if (g->kind == ISMCTS_GAME_KW) { for (int p = 0; p < g->u.kw.np; ++p) if (g->u.kw.alive[p]) out[n++] = p; }
+    else if (g->kind == ISMCTS_GAME_GOOF) { out[0] = 0; out[1] = 1; out[2] = 2; n = 3; } /* goofspiel.cpp:124-128 */
     else { out[0] = 0; out[1] = 1; n = 2; }
     return n;
 }
-static uint32_t og_stride(uint32_t kind) { return kind == ISMCTS_GAME_KW ? 64u : 256u; }
+static uint32_t og_stride(uint32_t kind) { return kind == ISMCTS_GAME_MNK ? 256u : 64u; }
 
 /* ======================================================== exported game API */
 
@@ -461,6 +600,62 @@ int orc_mnk_result2(const ismcts_mnk_state* s, uint32_t player)
     return omnk_result2(&g, (int)player);
 }
 
+int orc_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out)
+{
+    /* Goofspiel::Goofspiel, goofspiel.cpp:52-63: the prizes are shuffled; entry i of the order is a
+       uniformly random prize not placed yet */
+    ogoof g;
+    memset(&g, 0, sizeof g);
+    rng r = generator_rng(seed, stream, 0xFFFFFFFFu, 0xFFFFFFFFu, 0);
+    unsigned char left[13];
+    memset(left, 1, sizeof left);
+    for (int p = 0; p < 2; ++p) for (int k = 0; k < 13; ++k) g.hand[p][k] = 1;
+    for (int i = 0; i < 13; ++i) { g.order[i] = set_draw(left, 13, &r); g.prize_left[g.order[i]] = 1; }
+    g.n = 13; g.player = 2; g.draw_prize = 1; g.next_prize = -1;
+    ogoof_to_pod(&g, out);
+    return 0;
+}
+
+/* A position as its own player to move sees it: the environment knows which prize comes next. */
+static void ogoof_face_up(ogoof* g)
+{
+    if (g->player == 2 && g->draw_prize && g->n > 0) {
+        g->next_prize = g->order[g->n - 1];
+    }
+}
+
+uint64_t orc_goof_legal(const ismcts_goof_state* s)
+{
+    ogoof g; uint16_t mv[16]; uint64_t mask = 0;
+    ogoof_from_pod(&g, s);
+    ogoof_face_up(&g);
+    const int n = ogoof_legal(&g, mv);
+    for (int i = 0; i < n; ++i) mask |= (uint64_t)1 << mv[i];
+    return mask;
+}
+
+int orc_goof_apply(ismcts_goof_state* s, uint32_t move)
+{
+    ogoof g;
+    ogoof_from_pod(&g, s);
+    ogoof_face_up(&g);
+    if (g.player == 2 && g.draw_prize && g.next_prize >= 0) {
+        /* turning the prize over removes it from the order */
+        g.prize_left[g.next_prize] = 0;
+        g.n--;
+    }
+    const int rc = ogoof_apply(&g, (int)move, NULL);
+    if (rc) return rc;
+    ogoof_to_pod(&g, s);
+    return 0;
+}
+
+int orc_goof_result2(const ismcts_goof_state* s, uint32_t player)
+{
+    ogoof g; ogoof_from_pod(&g, s);
+    return ogoof_result2(&g, (int)player);
+}
+
 /* ================================================================= playout */
 
 /* simulate, solverbase.h:36-43 with RandomElement (utility.h:69-83): uniform
@@ -489,6 +684,8 @@ uint32_t orc_playout(uint32_t game, const void* root, uint64_t seed, uint32_t po
     if (game == ISMCTS_GAME_KW) {
         winner = 0xFF;
         for (int p = 0; p < g.u.kw.np; ++p) if (g.u.kw.alive[p]) { winner = (uint32_t)p; break; }
+    } else if (game == ISMCTS_GAME_GOOF) {
+        winner = (uint32_t)ogoof_result2(&g.u.goof, 0);
     } else {
         winner = (uint32_t)(g.u.mnk.result2 & 0xFF);
     }

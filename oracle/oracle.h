@@ -46,6 +46,11 @@ void orc_mnk_legal(const ismcts_mnk_state* s, uint64_t legal[4]);
 int orc_mnk_apply(ismcts_mnk_state* s, uint32_t move);
 int orc_mnk_result2(const ismcts_mnk_state* s, uint32_t player);
 
+int orc_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out);
+uint64_t orc_goof_legal(const ismcts_goof_state* s);
+int orc_goof_apply(ismcts_goof_state* s, uint32_t move);
+int orc_goof_result2(const ismcts_goof_state* s, uint32_t player);
+
 /* One determinise + rollout (no tree); result packed as ismcts_playouts does. */
 uint32_t orc_playout(uint32_t game, const void* root, uint64_t seed, uint32_t pos, uint32_t tree,
                      uint32_t iteration);

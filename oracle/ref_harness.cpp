@@ -19,6 +19,7 @@
 #include <ismcts/mosolver.h>
 #include "common/knockoutwhist.h"
 #include "common/mnkgame.h"
+#include "common/goofspiel.h"
 
 #include "../include/ismcts_b200.h"
 
@@ -220,6 +221,7 @@ int usage()
         "ref_harness kw-playouts <hex kw_state> <count>\n"
         "ref_harness kw-time <players> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
         "ref_harness kw-vs-random <players> <seq|root> <iterations> <threads> <games>\n"
+        "ref_harness goof-stats <prize rank 0-12> <player 0 bid rank or -1> <so|mo> <iterations> <reps>\n"
         "ref_harness cores\n");
     return 2;
 }
@@ -389,6 +391,45 @@ int main(int argc, char **argv)
             std::cout << (r ? ", " : "") << "{\"seconds\": " << secs << ", \"iterations\": " << it
                       << ", \"best\": " << best << "}";
             std::cout.flush();
+        }
+        std::cout << "]\n";
+        return 0;
+    }
+    if (cmd == "goof-stats" && argc == 7) {
+        // Goofspiel keeps its state private: take fresh games until the first prize is the wanted one,
+        // then (optionally) let player 0 bid.  Every move is simultaneous, so the solvers select with
+        // EXP3 (solverbase.h:58-64).  Root statistics of the player to move, as for kw-stats.
+        int const prize = std::atoi(argv[2]), bid = std::atoi(argv[3]);
+        std::string const solver = argv[4];
+        std::size_t const it = std::strtoull(argv[5], nullptr, 10);
+        unsigned const reps = unsigned(std::atoi(argv[6]));
+        std::cout << "[";
+        for (unsigned r = 0; r < reps; ++r) {
+            std::unique_ptr<Goofspiel> game;
+            for (;;) {
+                game = std::make_unique<Goofspiel>();
+                if (int(game->validMoves().front().rank) == prize)
+                    break;
+            }
+            game->doMove(game->validMoves().front());
+            if (bid >= 0)
+                game->doMove(Card{Card::Rank(bid), Card::Spades});
+            std::ostringstream oss;
+            oss.precision(17);
+            int best = -1;
+            if (solver == "so") {
+                SOSolver<Card, Sequential> s {it};
+                best = int(s(*game));
+                printRootStats<Card>(s.currentTrees(), oss);
+            } else {
+                MOSolver<Card, Sequential> s {it};
+                best = int(s(*game));
+                std::vector<std::shared_ptr<Node<Card>>> roots;
+                for (auto const &map : s.currentTrees())
+                    roots.push_back(map.at(game->currentPlayer()));
+                printRootStats<Card>(roots, oss);
+            }
+            std::cout << (r ? ",\n " : "") << "{\"best\": " << best << ", \"seconds\": 0, \"root\": " << oss.str() << "}";
         }
         std::cout << "]\n";
         return 0;

@@ -13,6 +13,7 @@
 #include <ismcts/mosolver.h>
 #include <ismcts/games/knockoutwhist.h>
 #include <ismcts/games/mnkgame.h>
+#include <ismcts/games/goofspiel.h>
 
 #include <chrono>
 #include <cstdio>
@@ -129,6 +130,36 @@ void testKnockoutWhist()
 }
 
 template<class Solver>
+void testGoofspiel()
+{
+    // solvertest.cpp:121-128: simultaneous tree policy; advance to a regular player first
+    Goofspiel game;
+    game.doMove(game.validMoves().front());
+    {
+        Solver solver {numGames};
+        Card const move = solver(game);
+        CHECK(isValid(game, move));
+    }
+    {
+        Solver solver {iterationTime};
+        Card const move = solver(game);
+        CHECK(isValid(game, move));
+    }
+    // a whole game: the environment's moves are searched as well (one legal move each)
+    Solver solver {500};
+    Goofspiel full {42};
+    unsigned turns = 0;
+    while (!full.validMoves().empty() && turns < 60) {
+        Card const move = solver(full);
+        CHECK(isValid(full, move));
+        full.doMove(move);
+        ++turns;
+    }
+    CHECK(turns == 52);
+    CHECK(full.getResult(0) + full.getResult(1) == 1.0);
+}
+
+template<class Solver>
 void testP1DrawOrLose()
 {
     // solvertest.cpp:131-138
@@ -201,6 +232,35 @@ void testHostOnly()
         CHECK(game.validMoves().empty());
         CHECK(game.getResult(0) == 1);
     }
+    // gametest.cpp:108-114,209-257
+    {
+        Goofspiel goof;
+        CHECK(goof.currentPlayer() == 2);
+        CHECK((goof.players() == std::vector<unsigned>{0, 1, 2}));
+        CHECK(goof.validMoves().size() == 1);
+        goof.doMove(goof.validMoves().front());
+        CHECK(goof.currentPlayer() == 0);
+        CHECK(goof.validMoves().size() == 13);
+        Goofspiel equal = goof;
+        for (int i = 0; i < 3; ++i)
+            equal.doMove(equal.validMoves().front());
+        CHECK(equal.getResult(0) == equal.getResult(1));
+        Goofspiel unequal = goof;
+        for (int i : {0, 1})
+            unequal.doMove(unequal.validMoves()[i]);
+        unequal.doMove(unequal.validMoves().front());
+        CHECK(unequal.getResult(0) == 0);
+        CHECK(unequal.getResult(1) != 0);
+        unsigned turns = 0;
+        while (!goof.validMoves().empty() && turns <= 13) {
+            if (goof.currentPlayer() == 0)
+                ++turns;
+            goof.doMove(goof.validMoves().front());
+        }
+        CHECK(turns == 13);
+        CHECK(goof.validMoves().empty());
+        CHECK(goof.currentMoveSimultaneous());
+    }
     // node.h: the textual form of nodes (ucb1.h:41-47, docs/node.md:13-22)
     UCBNode<int> root;
     auto child = std::make_unique<UCBNode<int>>(6, 0);
@@ -241,6 +301,8 @@ int main(int argc, char **argv)
         testKnockoutWhist<SOSolver<Card, CudaTreeParallel>>();
         testKnockoutWhist<MOSolver<Card, CudaRootParallel>>();
         testKnockoutWhist<MOSolver<Card, CudaRootParallel, EXP3>>();
+        testGoofspiel<SOSolver<Card, CudaRootParallel>>();
+        testGoofspiel<MOSolver<Card, CudaRootParallel>>();
         testP1DrawOrLose<SOSolver<int, CudaRootParallel>>();
         testP1DrawOrLose<SOSolver<int, CudaTreeParallel>>();
         testP1DrawOrLose<MOSolver<int, CudaRootParallel>>();

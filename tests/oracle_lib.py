@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_HARNESS = os.path.join(ORACLE_DIR, "_ref", "ref_harness")
 
-GAME_KW, GAME_MNK = 0, 1
+GAME_KW, GAME_MNK, GAME_GOOF = 0, 1, 2
 SOLVER_SO, SOLVER_MO = 0, 1
 POLICY_UCB1, POLICY_EXP3 = 0, 1
 
@@ -72,7 +72,30 @@ class MnkState(C.Structure):
         return bytes(self).hex()
 
 
-assert C.sizeof(KwState) == 96 and C.sizeof(MnkState) == 72
+class GoofState(C.Structure):
+    """Mirror of ismcts_goof_state."""
+    _fields_ = [
+        ("prize_order", C.c_uint64),
+        ("hands", C.c_uint16 * 2),
+        ("n_prizes", C.c_uint8),
+        ("player", C.c_uint8),
+        ("draw_prize", C.c_uint8),
+        ("current_prize", C.c_uint8),
+        ("moves", C.c_uint8 * 2),
+        ("scores", C.c_uint8 * 2),
+        ("pad", C.c_uint8 * 4),
+    ]
+
+    def copy(self) -> "GoofState":
+        out = GoofState()
+        C.memmove(C.byref(out), C.byref(self), C.sizeof(GoofState))
+        return out
+
+    def hex(self) -> str:
+        return bytes(self).hex()
+
+
+assert C.sizeof(KwState) == 96 and C.sizeof(MnkState) == 72 and C.sizeof(GoofState) == 24
 
 NODE_DTYPE = np.dtype([
     ("parent", "<u4"), ("move", "<u4"), ("player", "<u4"), ("visits", "<u4"),
@@ -121,6 +144,11 @@ def lib() -> C.CDLL:
         L.orc_mnk_legal.argtypes = [C.POINTER(MnkState), C.POINTER(u64)]
         L.orc_mnk_apply.argtypes = [C.POINTER(MnkState), u32]
         L.orc_mnk_result2.argtypes = [C.POINTER(MnkState), u32]
+        L.orc_goof_init.argtypes = [u64, u32, C.POINTER(GoofState)]
+        L.orc_goof_legal.restype = u64
+        L.orc_goof_legal.argtypes = [C.POINTER(GoofState)]
+        L.orc_goof_apply.argtypes = [C.POINTER(GoofState), u32]
+        L.orc_goof_result2.argtypes = [C.POINTER(GoofState), u32]
         L.orc_playout.restype = u32
         L.orc_playout.argtypes = [u32, vp, u64, u32, u32, u32]
         L.orc_so_search.argtypes = [u32, vp, u32, dbl, u64, u32, u32, u64, vp, u32, C.POINTER(u32),
@@ -139,7 +167,26 @@ def lib() -> C.CDLL:
 
 
 def move_stride(game: int) -> int:
-    return 64 if game == GAME_KW else 256
+    return 256 if game == GAME_MNK else 64
+
+
+def goof_init(seed: int, stream: int = 0) -> GoofState:
+    s = GoofState()
+    lib().orc_goof_init(seed, stream, C.byref(s))
+    return s
+
+
+def goof_legal(s: GoofState) -> list[int]:
+    mask = lib().orc_goof_legal(C.byref(s))
+    return [c for c in range(64) if mask >> c & 1]
+
+
+def goof_apply(s: GoofState, move: int) -> int:
+    return lib().orc_goof_apply(C.byref(s), move)
+
+
+def goof_result2(s: GoofState, player: int) -> int:
+    return lib().orc_goof_result2(C.byref(s), player)
 
 
 def kw_deal(seed: int, stream: int, players: int = 4) -> KwState:

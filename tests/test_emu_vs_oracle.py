@@ -212,3 +212,49 @@ def test_shared_tree_invariants(emu, width):
         nodes, done = emu_shared(emu, game, s, 3000, width, 11)
         assert done == 3000
         check_tree_invariants(nodes, 3000)
+
+
+def _goof_positions(count, seed=0):
+    rnd = np.random.default_rng(seed)
+    out = []
+    stream = 0
+    while len(out) < count:
+        s = O.goof_init(17, stream)
+        stream += 1
+        for _ in range(int(rnd.integers(0, 40))):
+            legal = O.goof_legal(s)
+            if not legal:
+                break
+            O.goof_apply(s, int(rnd.choice(legal)))
+        if O.goof_legal(s):
+            out.append(s)
+    return out
+
+
+def test_goofspiel_playouts(emu):
+    for s in _goof_positions(25):
+        for it in range(40):
+            assert O.playout(O.GAME_GOOF, s, 9, 0, 0, it) == emu.emu_playout(O.GAME_GOOF, C.byref(s), 9, 0, it)
+
+
+@pytest.mark.parametrize("policy", [O.POLICY_EXP3, O.POLICY_UCB1])
+def test_goofspiel_search_every_node(emu, policy):
+    """Simultaneous moves -> EXP3 (solverbase.h:58-64); all three observers, incl. the hidden bid seen from
+    player 1 (goofspiel.cpp:76-78) and the environment that knows the order of the prizes."""
+    fields = EXP_FIELDS if policy == O.POLICY_EXP3 else FIELDS
+    seen = set()
+    for s in _goof_positions(12, seed=3):
+        seen.add(int(s.player))
+        want = O.so_search(O.GAME_GOOF, s, 500, seed=4, policy=policy)
+        got = emu_any(emu, O.GAME_GOOF, s, O.SOLVER_SO, policy, 500, 4, 0)
+        assert len(got) == len(want)
+        for f in fields:
+            assert (got[f] == want[f]).all(), ("so", f)
+        trees = O.mo_search(O.GAME_GOOF, s, 300, seed=5, policy=policy)
+        assert sorted(trees) == [0, 1, 2]
+        for p, want in trees.items():
+            got = emu_any(emu, O.GAME_GOOF, s, O.SOLVER_MO, policy, 300, 5, p)
+            assert len(got) == len(want)
+            for f in fields:
+                assert (got[f] == want[f]).all(), ("mo", p, f)
+    assert seen == {0, 1, 2}

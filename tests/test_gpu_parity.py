@@ -294,3 +294,52 @@ def test_shared_tree_rejects_unsupported_combinations(engine):
                                        flags=_shared_flags(32)), capi.pack_states([s]))
     with pytest.raises(capi.EngineError):
         engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=100, flags=SHARED), capi.pack_states([s]))
+
+
+# ------------------------------------------------------------------ Goofspiel (simultaneous moves, EXP3)
+
+def _goof_positions(count, seed=0):
+    rnd = np.random.default_rng(seed)
+    out, stream = [], 0
+    while len(out) < count:
+        s = capi.goof_init(17, stream)
+        stream += 1
+        for _ in range(int(rnd.integers(0, 40))):
+            legal = capi.goof_legal(s)
+            if not legal:
+                break
+            capi.goof_apply(s, int(rnd.choice(legal)))
+        if capi.goof_legal(s):
+            out.append(s)
+    return out
+
+
+def _ogoof(s):
+    return O.GoofState.from_buffer_copy(bytes(s))
+
+
+def test_goofspiel_playouts_and_trees_bit_exact(engine):
+    states = _goof_positions(9, seed=3)
+    assert {int(s.player) for s in states} == {0, 1, 2}
+    got = engine.playouts(capi.GAME_GOOF, capi.pack_states(states), len(states), 256, seed=11)
+    for i, s in enumerate(states):
+        want = np.array([O.playout(O.GAME_GOOF, _ogoof(s), 11, i, 0, j) for j in range(256)], dtype=np.uint32)
+        assert (got[i] == want).all(), i
+    per = 700
+    for solver in (capi.SOLVER_SO, capi.SOLVER_MO):
+        desc = engine.make_desc(capi.GAME_GOOF, len(states), 2, iterations=2 * per, seed=6, solver=solver,
+                                policy=capi.POLICY_EXP3)
+        res = engine.search(desc, capi.pack_states(states))
+        assert (res["iterations_done"] == per).all()
+        for i, s in enumerate(states):
+            for t in range(2):
+                if solver == capi.SOLVER_SO:
+                    wants = {None: O.so_search(O.GAME_GOOF, _ogoof(s), per, seed=6, pos=i, tree=t, policy=O.POLICY_EXP3)}
+                else:
+                    wants = O.mo_search(O.GAME_GOOF, _ogoof(s), per, seed=6, pos=i, tree=t, policy=O.POLICY_EXP3)
+                for player, want in wants.items():
+                    got_nodes = engine.dump_tree(i * 2 + t, 4 * per, player=player)
+                    assert len(got_nodes) == len(want)
+                    for f in EXP_FIELDS:
+                        assert (got_nodes[f] == want[f]).all(), (solver, i, t, player, f)
+            assert int(res["best_move"][i]) in capi.goof_legal(s)        # solvertest.cpp:121-128

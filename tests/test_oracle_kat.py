@@ -326,3 +326,72 @@ def test_mo_trees_have_identical_shape_on_kw():
         for f in ("parent", "move", "player", "visits", "score2"):
             assert (trees[p][f] == base[f]).all()
     assert len(base) == 501
+
+
+# ------------------------------------------------------------------ Goofspiel
+
+class OracleGoof:
+    init = staticmethod(O.goof_init)
+    legal = staticmethod(O.goof_legal)
+    apply = staticmethod(O.goof_apply)
+    result2 = staticmethod(O.goof_result2)
+
+
+class ProductGoof:
+    init = staticmethod(capi.goof_init)
+    legal = staticmethod(capi.goof_legal)
+    apply = staticmethod(capi.goof_apply)
+
+    @staticmethod
+    def result2(s, p):
+        return capi.load_library().ismcts_goof_result2(C.byref(s), p)
+
+
+GOOF_IMPLS = [OracleGoof, ProductGoof]
+
+
+@pytest.mark.parametrize("impl", GOOF_IMPLS)
+def test_goofspiel_constructed_properly(impl):
+    # gametest.cpp:108-114
+    s = impl.init(3)
+    assert s.player == 2 and len(impl.legal(s)) == 1
+    assert 26 <= impl.legal(s)[0] < 39                      # a heart
+
+
+@pytest.mark.parametrize("impl", GOOF_IMPLS)
+def test_goofspiel_do_move(impl):
+    # gametest.cpp:209-257
+    s = impl.init(4)
+    assert impl.apply(s, impl.legal(s)[0]) == 0 and s.player == 0          # the first prize
+    assert impl.legal(s) == list(range(39, 52))                             # 13 spades
+    t = type(s).from_buffer_copy(bytes(s))
+    assert impl.apply(t, 39) == 0 and t.player == 1 and impl.legal(t) == list(range(13))   # 13 clubs
+    # equal bids give equal scores
+    e = type(s).from_buffer_copy(bytes(s))
+    for _ in range(3):
+        assert impl.apply(e, impl.legal(e)[0]) == 0
+    assert impl.result2(e, 0) == impl.result2(e, 1) == 1
+    # unequal bids: player 0 bids the Two, player 1 the Three -> player 1 takes the prize
+    u = type(s).from_buffer_copy(bytes(s))
+    assert impl.apply(u, impl.legal(u)[0]) == 0 and impl.apply(u, impl.legal(u)[1]) == 0
+    assert impl.apply(u, impl.legal(u)[0]) == 0
+    assert impl.result2(u, 0) == 0 and impl.result2(u, 1) == 2 and impl.result2(u, 2) == 0
+    # an illegal bid is rejected
+    assert impl.apply(s, 5) == capi.ERR_ILLEGAL_MOVE
+    # a game takes 13 turns
+    turns = 0
+    while impl.legal(s):
+        turns += s.player == 0
+        assert impl.apply(s, impl.legal(s)[0]) == 0
+    assert turns == 13
+
+
+@pytest.mark.parametrize("impl", GOOF_IMPLS)
+def test_goofspiel_ace_is_low(impl):
+    # goofspiel.cpp:17-36: the Ace is worth 1, the King 13
+    s = impl.init(5)
+    impl.apply(s, impl.legal(s)[0])
+    assert impl.apply(s, 39 + 12) == 0      # player 0 bids the Ace (value 1)
+    assert impl.apply(s, 0) == 0            # player 1 bids the Two (value 2)
+    assert impl.apply(s, 0) == 0            # reveal
+    assert impl.result2(s, 1) == 2
