@@ -34,7 +34,7 @@ enum {
 };
 
 /* ------------------------------------------------------------------- games */
-enum { ISMCTS_GAME_KW = 0, ISMCTS_GAME_MNK = 1, ISMCTS_GAME_GOOF = 2 };
+enum { ISMCTS_GAME_KW = 0, ISMCTS_GAME_MNK = 1, ISMCTS_GAME_GOOF = 2, ISMCTS_GAME_PHANTOM = 3 };
 enum { ISMCTS_SOLVER_SO = 0, ISMCTS_SOLVER_MO = 1 };
 enum { ISMCTS_POLICY_UCB1 = 0, ISMCTS_POLICY_EXP3 = 1 };
 
@@ -100,10 +100,25 @@ typedef struct ismcts_goof_state {
     uint8_t pad[4];
 } ismcts_goof_state;        /* 24 bytes */
 
+/*
+ * Phantom m,n,k-game position (test/common/phantommnkgame.h:12-36): the m,n,k-game in which the players
+ * do not see each other's stones.  avail[p] are the cells player p still believes free (m_available);
+ * trying an occupied one only removes it from that set and the same player moves again
+ * (phantommnkgame.cpp:83-105).
+ */
+typedef struct ismcts_phantom_state {
+    uint64_t stones[2][4];
+    uint64_t avail[2][4];
+    uint8_t m, n, k;
+    uint8_t player;
+    int8_t result2;
+    uint8_t pad[3];
+} ismcts_phantom_state;    /* 136 bytes */
+
 /* Size in bytes of one root position record for a game kind (0 if unknown). */
 size_t ismcts_state_size(uint32_t game);
 /* Number of move ids the per-position output arrays are strided by:
- * 64 for Knockout Whist and Goofspiel (52 used), 256 for m,n,k. */
+ * 64 for Knockout Whist and Goofspiel (52 used), 256 for m,n,k and phantom m,n,k. */
 uint32_t ismcts_move_stride(uint32_t game);
 
 /* ---------------------------------------------------------- host game helpers
@@ -141,6 +156,15 @@ uint64_t ismcts_goof_legal(const ismcts_goof_state* s);
 int ismcts_goof_apply(ismcts_goof_state* s, uint32_t move);
 /* getResult*2 (goofspiel.cpp:119-128). */
 int ismcts_goof_result2(const ismcts_goof_state* s, uint32_t player);
+
+/* PhantomMnkGame::PhantomMnkGame(m,n,k) (phantommnkgame.cpp:12-19). */
+int ismcts_phantom_init(uint32_t m, uint32_t n, uint32_t k, ismcts_phantom_state* out);
+/* validMoves (phantommnkgame.cpp:107-110): the cells the player to move believes free. */
+void ismcts_phantom_legal(const ismcts_phantom_state* s, uint64_t legal[4]);
+/* doMove (phantommnkgame.cpp:83-105). */
+int ismcts_phantom_apply(ismcts_phantom_state* s, uint32_t move);
+/* getResult*2 (mnkgame.cpp:56-59). */
+int ismcts_phantom_result2(const ismcts_phantom_state* s, uint32_t player);
 
 /* ------------------------------------------------------------------ context */
 typedef struct ismcts_ctx ismcts_ctx;

@@ -13,7 +13,7 @@ import numpy as np
 
 from .build import LIB_PATH
 
-GAME_KW, GAME_MNK, GAME_GOOF = 0, 1, 2
+GAME_KW, GAME_MNK, GAME_GOOF, GAME_PHANTOM = 0, 1, 2, 3
 SOLVER_SO, SOLVER_MO = 0, 1
 POLICY_UCB1, POLICY_EXP3 = 0, 1
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_ILLEGAL_MOVE, ERR_CUDA, ERR_CAPACITY = range(6)
@@ -25,6 +25,7 @@ EXPORTS = [
     "ismcts_kw_deal", "ismcts_kw_legal", "ismcts_kw_apply", "ismcts_kw_result2",
     "ismcts_mnk_init", "ismcts_mnk_legal", "ismcts_mnk_apply", "ismcts_mnk_result2",
     "ismcts_goof_init", "ismcts_goof_legal", "ismcts_goof_apply", "ismcts_goof_result2",
+    "ismcts_phantom_init", "ismcts_phantom_legal", "ismcts_phantom_apply", "ismcts_phantom_result2",
     "ismcts_create", "ismcts_destroy", "ismcts_last_error", "ismcts_set_stream",
     "ismcts_search", "ismcts_search_device", "ismcts_synchronize", "ismcts_dump_tree", "ismcts_dump_tree_of",
     "ismcts_playouts", "ismcts_launch_count", "ismcts_version",
@@ -57,6 +58,15 @@ class GoofState(C.Structure):
         ("prize_order", C.c_uint64), ("hands", C.c_uint16 * 2), ("n_prizes", C.c_uint8), ("player", C.c_uint8),
         ("draw_prize", C.c_uint8), ("current_prize", C.c_uint8), ("moves", C.c_uint8 * 2), ("scores", C.c_uint8 * 2),
         ("pad", C.c_uint8 * 4),
+    ]
+
+
+class PhantomState(C.Structure):
+    """ismcts_phantom_state"""
+    _fields_ = [
+        ("stones", (C.c_uint64 * 4) * 2), ("avail", (C.c_uint64 * 4) * 2),
+        ("m", C.c_uint8), ("n", C.c_uint8), ("k", C.c_uint8), ("player", C.c_uint8),
+        ("result2", C.c_int8), ("pad", C.c_uint8 * 3),
     ]
 
 
@@ -112,6 +122,11 @@ def load_library() -> C.CDLL:
     L.ismcts_mnk_legal.argtypes = [C.POINTER(MnkState), C.POINTER(u64)]
     L.ismcts_mnk_apply.argtypes = [C.POINTER(MnkState), u32]
     L.ismcts_mnk_result2.argtypes = [C.POINTER(MnkState), u32]
+    L.ismcts_phantom_init.argtypes = [u32, u32, u32, C.POINTER(PhantomState)]
+    L.ismcts_phantom_legal.restype = None
+    L.ismcts_phantom_legal.argtypes = [C.POINTER(PhantomState), C.POINTER(u64)]
+    L.ismcts_phantom_apply.argtypes = [C.POINTER(PhantomState), u32]
+    L.ismcts_phantom_result2.argtypes = [C.POINTER(PhantomState), u32]
     L.ismcts_goof_init.argtypes = [u64, u32, C.POINTER(GoofState)]
     L.ismcts_goof_legal.restype = u64
     L.ismcts_goof_legal.argtypes = [C.POINTER(GoofState)]
@@ -295,3 +310,21 @@ def goof_legal(s: GoofState) -> list[int]:
 
 def goof_apply(s: GoofState, move: int) -> int:
     return load_library().ismcts_goof_apply(C.byref(s), move)
+
+
+def phantom_init(m: int = 3, n: int = 3, k: int = 3) -> PhantomState:
+    s = PhantomState()
+    rc = load_library().ismcts_phantom_init(m, n, k, C.byref(s))
+    if rc != OK:
+        raise EngineError(rc, "ismcts_phantom_init")
+    return s
+
+
+def phantom_legal(s: PhantomState) -> list[int]:
+    legal = (C.c_uint64 * 4)()
+    load_library().ismcts_phantom_legal(C.byref(s), legal)
+    return [c for c in range(256) if legal[c >> 6] >> (c & 63) & 1]
+
+
+def phantom_apply(s: PhantomState, move: int) -> int:
+    return load_library().ismcts_phantom_apply(C.byref(s), move)

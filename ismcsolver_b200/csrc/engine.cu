@@ -10,6 +10,7 @@
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
 #include "goof_game.cuh"
+#include "phantom_game.cuh"
 #include "kw_jobs.cuh"
 
 #include <cuda_runtime.h>
@@ -170,13 +171,13 @@ const char* ismcts_version(void) { return "ismcsolver_b200 0.2 (sm_100a)"; }
 size_t ismcts_state_size(uint32_t game)
 {
     return game == ISMCTS_GAME_KW ? sizeof(ismcts_kw_state) : game == ISMCTS_GAME_MNK ? sizeof(ismcts_mnk_state)
-         : game == ISMCTS_GAME_GOOF ? sizeof(ismcts_goof_state) : 0;
+         : game == ISMCTS_GAME_GOOF ? sizeof(ismcts_goof_state) : game == ISMCTS_GAME_PHANTOM ? sizeof(ismcts_phantom_state) : 0;
 }
 
 uint32_t ismcts_move_stride(uint32_t game)
 {
     return game == ISMCTS_GAME_KW ? KwGame::kMoveStride : game == ISMCTS_GAME_MNK ? MnkGame::kMoveStride
-         : game == ISMCTS_GAME_GOOF ? GoofGame::kMoveStride : 0;
+         : game == ISMCTS_GAME_GOOF ? GoofGame::kMoveStride : game == ISMCTS_GAME_PHANTOM ? PhantomGame::kMoveStride : 0;
 }
 
 int ismcts_create(int device, ismcts_ctx** out)
@@ -262,6 +263,7 @@ static auto with_game(uint32_t game, F&& f)
 {
     if (game == ISMCTS_GAME_KW) return f(GameTag<KwGame>{});
     if (game == ISMCTS_GAME_MNK) return f(GameTag<MnkGame>{});
+    if (game == ISMCTS_GAME_PHANTOM) return f(GameTag<PhantomGame>{});
     return f(GameTag<GoofGame>{});
 }
 
@@ -282,7 +284,7 @@ static uint32_t trees_per_lane(uint32_t game, uint32_t solver)
 static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
 {
     if (!ctx || !d) return ISMCTS_ERR_INVALID;
-    if (d->game > ISMCTS_GAME_GOOF) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    if (d->game > ISMCTS_GAME_PHANTOM) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
     if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
     if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
@@ -587,7 +589,8 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
         const uint8_t* rec = (const uint8_t*)roots + p * state;
         ctx->last_root_player[p] = d->game == ISMCTS_GAME_KW ? ((const ismcts_kw_state*)rec)->player
                                  : d->game == ISMCTS_GAME_MNK ? ((const ismcts_mnk_state*)rec)->player
-                                                              : ((const ismcts_goof_state*)rec)->player;
+                                 : d->game == ISMCTS_GAME_PHANTOM ? ((const ismcts_phantom_state*)rec)->player
+                                                                  : ((const ismcts_goof_state*)rec)->player;
     }
     CUDA_TRY(ctx, cudaMemcpyAsync(out->visits, dv, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (out->score2) CUDA_TRY(ctx, cudaMemcpyAsync(out->score2, ds, per_arr * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -613,7 +616,7 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
                                uint32_t per_position, uint64_t seed, uint32_t* out_result)
 {
     if (!ctx || !roots || !out_result || n_positions == 0 || per_position == 0) return ISMCTS_ERR_INVALID;
-    if (game > ISMCTS_GAME_GOOF) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    if (game > ISMCTS_GAME_PHANTOM) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t root_bytes = (size_t)n_positions * ismcts_state_size(game);
     const size_t n = (size_t)n_positions * per_position;

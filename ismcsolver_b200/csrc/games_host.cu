@@ -9,6 +9,7 @@
 #include "kw_game.cuh"
 #include "mnk_game.cuh"
 #include "goof_game.cuh"
+#include "phantom_game.cuh"
 
 #include <cstring>
 
@@ -128,6 +129,44 @@ int ismcts_kw_result2(const ismcts_kw_state* s, uint32_t player)
 {
     if (!s || s->alive_mask == 0) return 0;
     return player == ctz32(s->alive_mask) ? 2 : 0; // getResult, knockoutwhist.cpp:117-120
+}
+
+// ---- phantom m,n,k (test/common/phantommnkgame.{h,cpp})
+
+int ismcts_phantom_init(uint32_t m, uint32_t n, uint32_t k, ismcts_phantom_state* out)
+{
+    if (!out || m == 0 || n == 0 || m * n > ISMCTS_MNK_MAX_CELLS || m > 255 || n > 255 || k > 255) return ISMCTS_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->m = (uint8_t)m; out->n = (uint8_t)n; out->k = (uint8_t)k; out->result2 = -1;
+    for (uint32_t c = 0; c < m * n; ++c)
+        for (int p = 0; p < 2; ++p) out->avail[p][c >> 6] |= (uint64_t)1 << (c & 63);
+    return ISMCTS_OK;
+}
+
+void ismcts_phantom_legal(const ismcts_phantom_state* s, uint64_t legal[4])
+{
+    for (int i = 0; i < 4; ++i) legal[i] = s ? s->avail[s->player & 1][i] : 0;
+}
+
+int ismcts_phantom_apply(ismcts_phantom_state* s, uint32_t move)
+{
+    if (!s) return ISMCTS_ERR_INVALID;
+    uint64_t scratch[PhantomGame::kHandWords];
+    PhantomGame g;
+    g.bind(scratch, 1);
+    g.load(s);
+    // phantommnkgame.cpp:85-88: the move must be one the player still believes possible
+    if (move >= (uint32_t)s->m * s->n || !g.legal().test(move)) return ISMCTS_ERR_ILLEGAL_MOVE;
+    g.play(move);
+    for (uint32_t i = 0; i < 8; ++i) { s->stones[i >> 2][i & 3] = scratch[i]; s->avail[i >> 2][i & 3] = scratch[8 + i]; }
+    s->player = (uint8_t)g.player; s->result2 = (int8_t)g.res2;
+    return ISMCTS_OK;
+}
+
+int ismcts_phantom_result2(const ismcts_phantom_state* s, uint32_t player)
+{
+    if (!s) return 0;
+    return player == 0 ? s->result2 : 2 - s->result2;
 }
 
 // ---- Goofspiel (test/common/goofspiel.{h,cpp})

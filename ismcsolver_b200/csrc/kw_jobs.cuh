@@ -212,7 +212,7 @@ struct KwJobs {
                 rollout = true;
                 break;
             }
-            uint32_t best = 0, best_created = 0xFFFFFFFFu;
+            uint32_t best = 0, best_created = 0xFFFFFFFFu, stored = who;
             double best_u = -1.0;
             Mask best_kids = Mask::none();
             move = 0;
@@ -224,11 +224,11 @@ struct KwJobs {
                 tree.slots[ci].avail = c.avail;
                 const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[c.avail], P.exploration);
                 if (u > best_u || (u == best_u && c.created < best_created)) {
-                    best_u = u; best = ci; best_created = c.created; move = m; best_kids = c.child_mask;
+                    best_u = u; best = ci; best_created = c.created; move = m; best_kids = c.child_mask; stored = c.player;
                 }
             }
             cur = best; kids = best_kids;
-            path[depth++] = cur | (who << 24);
+            path[depth++] = cur | (stored << 24);
             g.step(move);
             if (g.chance_pending()) break;
         }

@@ -333,7 +333,10 @@ struct Lane {
                     node_children[t] = Mask::none();
                 }
             }
-            if (!kMulti && !kExp3) path[depth++] = node[0] | (who << 24);
+            // the reward is credited from the point of view of the player stored in the node (ucb1.h:53-56),
+            // which is the mover when the node was created — in games where the same move can be made by
+            // different players in different determinisations (phantom m,n,k) not necessarily today's mover
+            if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : chosen.player) << 24);
             g.step(move);
             if (expand) { phase = kRollout; return; }
             if (g.chance_pending()) return;
@@ -350,7 +353,7 @@ struct Lane {
                 const uint32_t who = g.current_player();
                 const Mask kids = Mask::load_shared(&tree.slots[node[0]].child_mask); // other lanes add children
                 const Mask untried = legal.minus(kids);
-                uint32_t move, next;
+                uint32_t move, next, stored = 0;
                 const bool expand = untried.any();
                 if (expand) {
                     move = untried.kth(rng.below(untried.count()));
@@ -370,12 +373,12 @@ struct Lane {
                         atomic_add_u32(&tree.slots[ci].avail, 1u);                 // markAvailable, ucb1.h:71-72
                         const uint32_t avail = c.avail + 1u < P.ln_count ? c.avail + 1u : P.ln_count - 1u;
                         const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[avail], P.exploration);
-                        if (u > best_u || (u == best_u && c.created < best_created)) { best_u = u; best_created = c.created; next = ci; move = m; }
+                        if (u > best_u || (u == best_u && c.created < best_created)) { best_u = u; best_created = c.created; next = ci; move = m; stored = c.player; }
                     }
                     red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[next]), 1u);  // virtual loss
                 }
                 node[0] = next;
-                path[depth++] = next | (who << 24);
+                path[depth++] = next | ((expand ? who : stored) << 24);
                 g.step(move);
                 if (expand) { phase = kRollout; return; }
                 if (g.chance_pending()) return;

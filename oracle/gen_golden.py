@@ -115,6 +115,20 @@ def main():
         cases.append({"name": f"goof-prize{prize}-bid{bid}", "game": "goof", "state": g.hex(), "solver": solver + "-sim",
                       "policy": "seq", "iterations": 3000, "threads": 1, "reps": 60, **summarise(rows, 64)})
         print(cases[-1]["name"], solver, cases[-1]["best_counts"], flush=True)
+    # phantom m,n,k: positions reached by move sequences; the hidden stones are too few to complete a line, so
+    # the reference's "ensure a non-winning state" replay (phantommnkgame.cpp:57-81) never restarts and its
+    # determinisation is exactly the uniform one
+    for name, dims, seq in [("phantom3-gametest", (3, 3, 3), [4, 4, 0, 6, 2]),        # gametest.cpp:264-279
+                            ("phantom4", (4, 4, 3), [5, 5, 10, 6, 0, 9]),
+                            ("phantom5", (5, 5, 4), [12, 12, 6, 7, 18, 8, 13, 16])]:
+        s = O.phantom_init(*dims)
+        for mv in seq:
+            assert O.phantom_apply(s, mv) == 0
+        for solver, it in (("so", 3000), ("mo", 3000)):
+            rows = json.loads(O.ref_harness("phantom-stats", s.hex(), solver, "seq", it, 1, 30))
+            cases.append({"name": name, "game": "phantom", "state": s.hex(), "solver": solver, "policy": "seq",
+                          "iterations": it, "threads": 1, "reps": 30, **summarise(rows, 256)})
+            print(name, solver, cases[-1]["best_counts"], flush=True)
     # the reference's own game code: uniform random playouts from its opening position
     play = json.loads(O.ref_harness("kw-playouts", ref_opening, 200000))
     out = {"generator": "oracle/gen_golden.py", "reference": "sfranzen/ismcsolver (unmodified, g++ -O3 -DNDEBUG)",

@@ -338,6 +338,103 @@ static int omnk_apply(omnk* g, int move, rng* r)
 /* getResult, mnkgame.cpp:56-59. */
 static int omnk_result2(const omnk* g, int player) { return player == 0 ? g->result2 : 2 - g->result2; }
 
+/* ============================================================ phantom m,n,k */
+
+typedef struct ophantom {
+    omnk b;                    /* board, m, n, k, player, result2 */
+    unsigned char avail[2][256];
+} ophantom;
+
+static void ophantom_from_pod(ophantom* g, const ismcts_phantom_state* s)
+{
+    ismcts_mnk_state base;
+    memset(&base, 0, sizeof base);
+    memcpy(base.stones, s->stones, sizeof base.stones);
+    base.m = s->m; base.n = s->n; base.k = s->k; base.player = s->player; base.result2 = s->result2;
+    omnk_from_pod(&g->b, &base);
+    for (int p = 0; p < 2; ++p)
+        for (int c = 0; c < 256; ++c) g->avail[p][c] = (unsigned char)((s->avail[p][c >> 6] >> (c & 63)) & 1);
+}
+
+static void ophantom_to_pod(const ophantom* g, ismcts_phantom_state* s)
+{
+    ismcts_mnk_state base;
+    omnk_to_pod(&g->b, &base);
+    memset(s, 0, sizeof *s);
+    memcpy(s->stones, base.stones, sizeof base.stones);
+    s->m = base.m; s->n = base.n; s->k = base.k; s->player = base.player; s->result2 = base.result2;
+    for (int p = 0; p < 2; ++p)
+        for (int c = 0; c < 256; ++c) if (g->avail[p][c]) s->avail[p][c >> 6] |= (uint64_t)1 << (c & 63);
+}
+
+/* validMoves, phantommnkgame.cpp:107-110. */
+static int ophantom_legal(const ophantom* g, uint16_t* moves)
+{
+    int n = 0;
+    for (int c = 0; c < g->b.m * g->b.n; ++c) if (g->avail[g->b.player][c]) moves[n++] = (uint16_t)c;
+    return n;
+}
+
+static int ophantom_wins(const omnk* b, int move, int p)
+{
+    return omnk_run(b, move, 0, 1, p) || omnk_run(b, move, 1, 0, p) || omnk_run(b, move, 1, 1, p) || omnk_run(b, move, -1, 1, p);
+}
+
+/* doMove, phantommnkgame.cpp:83-105. */
+static int ophantom_apply(ophantom* g, int move, rng* r)
+{
+    omnk* b = &g->b;
+    const int p = b->player;
+    if (move < 0 || move >= b->m * b->n || !g->avail[p][move]) return ISMCTS_ERR_ILLEGAL_MOVE;
+    if (r && r->cnt) r->cnt->plies++;
+    g->avail[p][move] = 0;
+    if (b->board[move] >= 0) return 0;            /* occupied by the opponent: noted, the same player moves again */
+    b->board[move] = (signed char)p;
+    if (ophantom_wins(b, move, p)) {
+        b->result2 = 2 * (1 - p);
+        memset(g->avail, 0, sizeof g->avail);
+    } else {
+        int empty = 0;
+        for (int c = 0; c < b->m * b->n; ++c) empty += b->board[c] < 0;
+        if (empty) b->player = 1 - p; else b->result2 = 1;
+    }
+    return 0;
+}
+
+/* cloneAndRandomise, phantommnkgame.cpp:21-81.  The observer knows its own stones, the cells it
+ * still believes free and how many stones the opponent has placed.  The opponent's stones it has not
+ * run into are taken back and as many are put on random cells it cannot rule out, such that no stone
+ * completes a winning line when it is placed (phantommnkgame.cpp:70-73 "ensure a non-winning state");
+ * a sample that would is discarded and drawn again (the reference restarts recursively). */
+static void ophantom_determinise(ophantom* g, int observer, rng* r)
+{
+    omnk* b = &g->b;
+    const int opp = 1 - observer, cells = b->m * b->n;
+    unsigned char cand[256] = {0};
+    int num = 0;
+    for (int c = 0; c < cells; ++c) {
+        if (b->board[c] == opp && g->avail[observer][c]) { b->board[c] = -1; g->avail[opp][c] = 1; ++num; } /* undoMoves :37-55 */
+        if (b->board[c] < 0) cand[c] = 1;
+    }
+    if (num == 0) return;
+    for (;;) {
+        unsigned char pool[256], placed[256] = {0};
+        memcpy(pool, cand, sizeof pool);
+        int ok = 1;
+        for (int i = 0; i < num && ok; ++i) {
+            const int c = set_draw(pool, 256, r);
+            b->board[c] = (signed char)opp;
+            placed[c] = 1;
+            if (ophantom_wins(b, c, opp)) ok = 0;
+        }
+        if (ok) {
+            for (int c = 0; c < cells; ++c) if (placed[c]) g->avail[opp][c] = 0;
+            return;
+        }
+        for (int c = 0; c < cells; ++c) if (placed[c]) b->board[c] = -1;
+    }
+}
+
 /* ================================================================ Goofspiel */
 
 typedef struct ogoof {
@@ -462,7 +559,7 @@ static void ogoof_determinise(ogoof* g, int observer, rng* r)
 
 typedef struct ogame {
     uint32_t kind;
-    union { okw kw; omnk mnk; ogoof goof; } u;
+    union { okw kw; omnk mnk; ogoof goof; ophantom ph; } u;
 } ogame;
 
 static int og_load(ogame* g, uint32_t kind, const void* root)
@@ -471,33 +568,41 @@ static int og_load(ogame* g, uint32_t kind, const void* root)
     if (kind == ISMCTS_GAME_KW) okw_from_pod(&g->u.kw, (const ismcts_kw_state*)root);
     else if (kind == ISMCTS_GAME_MNK) omnk_from_pod(&g->u.mnk, (const ismcts_mnk_state*)root);
     else if (kind == ISMCTS_GAME_GOOF) ogoof_from_pod(&g->u.goof, (const ismcts_goof_state*)root);
+    else if (kind == ISMCTS_GAME_PHANTOM) ophantom_from_pod(&g->u.ph, (const ismcts_phantom_state*)root);
     else return ISMCTS_ERR_INVALID;
     return 0;
 }
 static int og_player(const ogame* g)
-{ return g->kind == ISMCTS_GAME_KW ? g->u.kw.player : g->kind == ISMCTS_GAME_MNK ? g->u.mnk.player : g->u.goof.player; }
+{
+    return g->kind == ISMCTS_GAME_KW ? g->u.kw.player : g->kind == ISMCTS_GAME_MNK ? g->u.mnk.player
+         : g->kind == ISMCTS_GAME_GOOF ? g->u.goof.player : g->u.ph.b.player;
+}
 static int og_legal(const ogame* g, uint16_t* mv)
 {
     if (g->kind == ISMCTS_GAME_KW) return okw_legal(&g->u.kw, mv);
     if (g->kind == ISMCTS_GAME_MNK) return omnk_legal(&g->u.mnk, mv);
+    if (g->kind == ISMCTS_GAME_PHANTOM) return ophantom_legal(&g->u.ph, mv);
     return ogoof_legal(&g->u.goof, mv);
 }
 static void og_apply(ogame* g, int mv, rng* r)
 {
     if (g->kind == ISMCTS_GAME_KW) okw_apply(&g->u.kw, mv, r);
     else if (g->kind == ISMCTS_GAME_MNK) omnk_apply(&g->u.mnk, mv, r);
+    else if (g->kind == ISMCTS_GAME_PHANTOM) ophantom_apply(&g->u.ph, mv, r);
     else ogoof_apply(&g->u.goof, mv, r);
 }
 static int og_result2(const ogame* g, int p)
 {
     if (g->kind == ISMCTS_GAME_KW) return okw_result2(&g->u.kw, p);
     if (g->kind == ISMCTS_GAME_MNK) return omnk_result2(&g->u.mnk, p);
+    if (g->kind == ISMCTS_GAME_PHANTOM) return omnk_result2(&g->u.ph.b, p);
     return ogoof_result2(&g->u.goof, p);
 }
 static void og_determinise(ogame* g, int obs, rng* r)
 {
     if (g->kind == ISMCTS_GAME_KW) okw_determinise(&g->u.kw, obs, r);
     else if (g->kind == ISMCTS_GAME_GOOF) ogoof_determinise(&g->u.goof, obs, r);
+    else if (g->kind == ISMCTS_GAME_PHANTOM) ophantom_determinise(&g->u.ph, obs, r);
     /* m,n,k: plain copy, mnkgame.cpp:34-37 */
 }
 /* players(), knockoutwhist.cpp:90-93 / mnkgame.cpp:76-79 */
@@ -509,7 +614,7 @@ static int og_players(const ogame* g, int* out)
     else { out[0] = 0; out[1] = 1; n = 2; }
     return n;
 }
-static uint32_t og_stride(uint32_t kind) { return kind == ISMCTS_GAME_MNK ? 256u : 64u; }
+static uint32_t og_stride(uint32_t kind) { return kind == ISMCTS_GAME_MNK || kind == ISMCTS_GAME_PHANTOM ? 256u : 64u; }
 
 /* ======================================================== exported game API */
 
@@ -600,6 +705,34 @@ int orc_mnk_result2(const ismcts_mnk_state* s, uint32_t player)
     return omnk_result2(&g, (int)player);
 }
 
+int orc_phantom_init(uint32_t m, uint32_t n, uint32_t k, ismcts_phantom_state* out)
+{
+    if (m == 0 || n == 0 || m * n > 256) return ISMCTS_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    out->m = (uint8_t)m; out->n = (uint8_t)n; out->k = (uint8_t)k; out->result2 = -1;
+    for (uint32_t c = 0; c < m * n; ++c) for (int p = 0; p < 2; ++p) out->avail[p][c >> 6] |= (uint64_t)1 << (c & 63);
+    return 0;
+}
+
+void orc_phantom_legal(const ismcts_phantom_state* s, uint64_t legal[4])
+{
+    for (int i = 0; i < 4; ++i) legal[i] = s->avail[s->player & 1][i];
+}
+
+int orc_phantom_apply(ismcts_phantom_state* s, uint32_t move)
+{
+    ophantom g; ophantom_from_pod(&g, s);
+    const int rc = ophantom_apply(&g, (int)move, NULL);
+    if (rc) return rc;
+    ophantom_to_pod(&g, s);
+    return 0;
+}
+
+int orc_phantom_result2(const ismcts_phantom_state* s, uint32_t player)
+{
+    return player == 0 ? s->result2 : 2 - s->result2;
+}
+
 int orc_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out)
 {
     /* Goofspiel::Goofspiel, goofspiel.cpp:52-63: the prizes are shuffled; entry i of the order is a
@@ -686,6 +819,8 @@ uint32_t orc_playout(uint32_t game, const void* root, uint64_t seed, uint32_t po
         for (int p = 0; p < g.u.kw.np; ++p) if (g.u.kw.alive[p]) { winner = (uint32_t)p; break; }
     } else if (game == ISMCTS_GAME_GOOF) {
         winner = (uint32_t)ogoof_result2(&g.u.goof, 0);
+    } else if (game == ISMCTS_GAME_PHANTOM) {
+        winner = (uint32_t)(g.u.ph.b.result2 & 0xFF);
     } else {
         winner = (uint32_t)(g.u.mnk.result2 & 0xFF);
     }

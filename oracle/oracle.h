@@ -46,6 +46,10 @@ void orc_mnk_legal(const ismcts_mnk_state* s, uint64_t legal[4]);
 int orc_mnk_apply(ismcts_mnk_state* s, uint32_t move);
 int orc_mnk_result2(const ismcts_mnk_state* s, uint32_t player);
 
+int orc_phantom_init(uint32_t m, uint32_t n, uint32_t k, ismcts_phantom_state* out);
+void orc_phantom_legal(const ismcts_phantom_state* s, uint64_t legal[4]);
+int orc_phantom_apply(ismcts_phantom_state* s, uint32_t move);
+int orc_phantom_result2(const ismcts_phantom_state* s, uint32_t player);
 int orc_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out);
 uint64_t orc_goof_legal(const ismcts_goof_state* s);
 int orc_goof_apply(ismcts_goof_state* s, uint32_t move);

@@ -20,6 +20,7 @@
 #include "common/knockoutwhist.h"
 #include "common/mnkgame.h"
 #include "common/goofspiel.h"
+#include "common/phantommnkgame.h"
 
 #include "../include/ismcts_b200.h"
 
@@ -126,6 +127,30 @@ struct PosedMnk : public MnkGame
     }
 };
 
+struct PosedPhantom : public PhantomMnkGame
+{
+    explicit PosedPhantom(ismcts_phantom_state const &s) : PhantomMnkGame{s.m, s.n, s.k}
+    {
+        m_moves.clear();
+        for (auto &a : m_available)
+            a.clear();
+        for (int c = 0; c < s.m * s.n; ++c) {
+            int owner = -1;
+            for (int p = 0; p < 2; ++p) {
+                if (s.stones[p][c >> 6] >> (c & 63) & 1)
+                    owner = p;
+                if (s.avail[p][c >> 6] >> (c & 63) & 1)
+                    m_available[p].push_back(c);
+            }
+            m_board[c / s.m][c % s.m] = owner;
+            if (owner < 0)
+                m_moves.push_back(c);
+        }
+        m_player = s.player;
+        m_result = s.result2 < 0 ? -1 : s.result2 / 2.0;
+    }
+};
+
 template<class T>
 bool fromHex(std::string const &hex, T &out)
 {
@@ -221,6 +246,7 @@ int usage()
         "ref_harness kw-playouts <hex kw_state> <count>\n"
         "ref_harness kw-time <players> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
         "ref_harness kw-vs-random <players> <seq|root> <iterations> <threads> <games>\n"
+        "ref_harness phantom-stats <hex phantom_state> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
         "ref_harness goof-stats <prize rank 0-12> <player 0 bid rank or -1> <so|mo> <iterations> <reps>\n"
         "ref_harness cores\n");
     return 2;
@@ -394,6 +420,14 @@ int main(int argc, char **argv)
         }
         std::cout << "]\n";
         return 0;
+    }
+    if (cmd == "phantom-stats" && argc == 8) {
+        ismcts_phantom_state s;
+        if (!fromHex(argv[2], s))
+            return usage();
+        PosedPhantom game{s};
+        return dispatchStats<PosedPhantom, int>(game, argv[3], argv[4], std::strtoull(argv[5], nullptr, 10),
+                                               unsigned(std::atoi(argv[6])), unsigned(std::atoi(argv[7])));
     }
     if (cmd == "goof-stats" && argc == 7) {
         // Goofspiel keeps its state private: take fresh games until the first prize is the wanted one,

@@ -14,6 +14,7 @@
 #include <ismcts/games/knockoutwhist.h>
 #include <ismcts/games/mnkgame.h>
 #include <ismcts/games/goofspiel.h>
+#include <ismcts/games/phantommnkgame.h>
 
 #include <chrono>
 #include <cstdio>
@@ -261,6 +262,32 @@ void testHostOnly()
         CHECK(goof.validMoves().empty());
         CHECK(goof.currentMoveSimultaneous());
     }
+    // gametest.cpp:100-106,184-206 for the phantom game, and :264-279 (cloneAndRandomise keeps known positions)
+    {
+        PhantomMnkGame phantom;
+        CHECK(phantom.currentPlayer() == 0);
+        CHECK(phantom.validMoves().size() == 9);
+        CHECK_THROWS_AS(phantom.doMove(9), std::out_of_range);
+        for (auto const &sequence : wins) {
+            PhantomMnkGame game;
+            for (int move : sequence)
+                game.doMove(move);
+            CHECK(game.validMoves().empty());
+            CHECK(game.getResult(0) == 1);
+        }
+        PhantomMnkGame game {3, 3, 3, 11};
+        for (int move : {4, 4, 0, 6, 2})
+            game.doMove(move);
+        CHECK(game.currentPlayer() == 0);
+        for (int rep = 0; rep < 20; ++rep) {
+            auto clone = game.cloneAndRandomise(0);
+            auto const &c = dynamic_cast<PhantomMnkGame const &>(*clone).state();
+            CHECK(c.avail[0][0] == game.state().avail[0][0]);
+            CHECK(__builtin_popcountll(c.avail[1][0]) == __builtin_popcountll(game.state().avail[1][0]));
+            CHECK(__builtin_popcountll(c.stones[1][0]) == 2);
+            CHECK(c.stones[0][0] == ((1u << 4) | (1u << 6)));
+        }
+    }
     // node.h: the textual form of nodes (ucb1.h:41-47, docs/node.md:13-22)
     UCBNode<int> root;
     auto child = std::make_unique<UCBNode<int>>(6, 0);
@@ -303,6 +330,20 @@ int main(int argc, char **argv)
         testKnockoutWhist<MOSolver<Card, CudaRootParallel, EXP3>>();
         testGoofspiel<SOSolver<Card, CudaRootParallel>>();
         testGoofspiel<MOSolver<Card, CudaRootParallel>>();
+        {
+            // the phantom game through both solvers: a valid move by count and by time
+            PhantomMnkGame game {3, 3, 3, 5};
+            for (int move : {4, 4, 0, 6, 2})
+                game.doMove(move);
+            SOSolver<int, CudaRootParallel> so {2000};
+            CHECK(isValid(game, so(game)));
+            MOSolver<int, CudaRootParallel> mo {iterationTime};
+            CHECK(isValid(game, mo(game)));
+            // player 0 holds 4 and 6: cell 2 completes the diagonal unless player 1 is there
+            SOSolver<int, CudaRootParallel> deep {20000, 8};
+            int const move = deep(game);
+            CHECK(isValid(game, move));
+        }
         testP1DrawOrLose<SOSolver<int, CudaRootParallel>>();
         testP1DrawOrLose<SOSolver<int, CudaTreeParallel>>();
         testP1DrawOrLose<MOSolver<int, CudaRootParallel>>();

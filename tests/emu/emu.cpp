@@ -11,6 +11,7 @@
 #include "../../ismcsolver_b200/csrc/kw_game.cuh"
 #include "../../ismcsolver_b200/csrc/mnk_game.cuh"
 #include "../../ismcsolver_b200/csrc/goof_game.cuh"
+#include "../../ismcsolver_b200/csrc/phantom_game.cuh"
 #include "../../ismcsolver_b200/csrc/kw_jobs.cuh"
 
 #include <chrono>
@@ -552,6 +553,7 @@ uint32_t emu_playout(uint32_t game, const void* root, uint64_t seed, uint32_t po
 {
     if (game == ISMCTS_GAME_KW) return playout_t<KwGame>(root, seed, pos, iteration);
     if (game == ISMCTS_GAME_GOOF) return playout_t<GoofGame>(root, seed, pos, iteration);
+    if (game == ISMCTS_GAME_PHANTOM) return playout_t<PhantomGame>(root, seed, pos, iteration);
     return playout_t<MnkGame>(root, seed, pos, iteration);
 }
 
@@ -572,6 +574,8 @@ int emu_search(uint32_t game, const void* root, uint32_t solver, uint32_t policy
         return search_game<KwGame>(root, solver, policy, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
     if (game == ISMCTS_GAME_GOOF)
         return search_game<GoofGame>(root, solver, policy, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
+    if (game == ISMCTS_GAME_PHANTOM)
+        return search_game<PhantomGame>(root, solver, policy, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
     return search_game<MnkGame>(root, solver, policy, iterations, seed, pos, tree, exploration, player, nodes, capacity, count);
 }
 

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_HARNESS = os.path.join(ORACLE_DIR, "_ref", "ref_harness")
 
-GAME_KW, GAME_MNK, GAME_GOOF = 0, 1, 2
+GAME_KW, GAME_MNK, GAME_GOOF, GAME_PHANTOM = 0, 1, 2, 3
 SOLVER_SO, SOLVER_MO = 0, 1
 POLICY_UCB1, POLICY_EXP3 = 0, 1
 
@@ -95,7 +95,26 @@ class GoofState(C.Structure):
         return bytes(self).hex()
 
 
+class PhantomState(C.Structure):
+    """Mirror of ismcts_phantom_state."""
+    _fields_ = [
+        ("stones", (C.c_uint64 * 4) * 2),
+        ("avail", (C.c_uint64 * 4) * 2),
+        ("m", C.c_uint8), ("n", C.c_uint8), ("k", C.c_uint8), ("player", C.c_uint8),
+        ("result2", C.c_int8), ("pad", C.c_uint8 * 3),
+    ]
+
+    def copy(self) -> "PhantomState":
+        out = PhantomState()
+        C.memmove(C.byref(out), C.byref(self), C.sizeof(PhantomState))
+        return out
+
+    def hex(self) -> str:
+        return bytes(self).hex()
+
+
 assert C.sizeof(KwState) == 96 and C.sizeof(MnkState) == 72 and C.sizeof(GoofState) == 24
+assert C.sizeof(PhantomState) == 136
 
 NODE_DTYPE = np.dtype([
     ("parent", "<u4"), ("move", "<u4"), ("player", "<u4"), ("visits", "<u4"),
@@ -144,6 +163,11 @@ def lib() -> C.CDLL:
         L.orc_mnk_legal.argtypes = [C.POINTER(MnkState), C.POINTER(u64)]
         L.orc_mnk_apply.argtypes = [C.POINTER(MnkState), u32]
         L.orc_mnk_result2.argtypes = [C.POINTER(MnkState), u32]
+        L.orc_phantom_init.argtypes = [u32, u32, u32, C.POINTER(PhantomState)]
+        L.orc_phantom_legal.argtypes = [C.POINTER(PhantomState), C.POINTER(u64)]
+        L.orc_phantom_legal.restype = None
+        L.orc_phantom_apply.argtypes = [C.POINTER(PhantomState), u32]
+        L.orc_phantom_result2.argtypes = [C.POINTER(PhantomState), u32]
         L.orc_goof_init.argtypes = [u64, u32, C.POINTER(GoofState)]
         L.orc_goof_legal.restype = u64
         L.orc_goof_legal.argtypes = [C.POINTER(GoofState)]
@@ -167,7 +191,27 @@ def lib() -> C.CDLL:
 
 
 def move_stride(game: int) -> int:
-    return 256 if game == GAME_MNK else 64
+    return 256 if game in (GAME_MNK, GAME_PHANTOM) else 64
+
+
+def phantom_init(m: int = 3, n: int = 3, k: int = 3) -> PhantomState:
+    s = PhantomState()
+    assert lib().orc_phantom_init(m, n, k, C.byref(s)) == 0
+    return s
+
+
+def phantom_legal(s: PhantomState) -> list[int]:
+    legal = (C.c_uint64 * 4)()
+    lib().orc_phantom_legal(C.byref(s), legal)
+    return [c for c in range(256) if legal[c >> 6] >> (c & 63) & 1]
+
+
+def phantom_apply(s: PhantomState, move: int) -> int:
+    return lib().orc_phantom_apply(C.byref(s), move)
+
+
+def phantom_result2(s: PhantomState, player: int) -> int:
+    return lib().orc_phantom_result2(C.byref(s), player)
 
 
 def goof_init(seed: int, stream: int = 0) -> GoofState:

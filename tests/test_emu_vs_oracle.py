@@ -258,3 +258,43 @@ def test_goofspiel_search_every_node(emu, policy):
             for f in fields:
                 assert (got[f] == want[f]).all(), ("mo", p, f)
     assert seen == {0, 1, 2}
+
+
+def _phantom_positions(count, seed=0):
+    rnd = np.random.default_rng(seed)
+    out = []
+    dims = [(3, 3, 3), (4, 4, 3), (6, 5, 4), (9, 9, 5)]
+    while len(out) < count:
+        s = O.phantom_init(*dims[len(out) % len(dims)])
+        for _ in range(int(rnd.integers(0, 14))):
+            legal = O.phantom_legal(s)
+            if not legal:
+                break
+            O.phantom_apply(s, int(rnd.choice(legal)))
+        if O.phantom_legal(s):
+            out.append(s)
+    return out
+
+
+def test_phantom_playouts(emu):
+    for s in _phantom_positions(24):
+        for it in range(30):
+            assert O.playout(O.GAME_PHANTOM, s, 9, 0, 0, it) == emu.emu_playout(O.GAME_PHANTOM, C.byref(s), 9, 0, it)
+
+
+@pytest.mark.parametrize("policy", [O.POLICY_UCB1, O.POLICY_EXP3])
+def test_phantom_search_every_node(emu, policy):
+    """Partially observable moves: the same tree move can be made by different players in different
+    determinisations; rewards are credited by the player stored in the node (ucb1.h:53-56)."""
+    fields = EXP_FIELDS if policy == O.POLICY_EXP3 else FIELDS
+    for s in _phantom_positions(10, seed=2):
+        want = O.so_search(O.GAME_PHANTOM, s, 600, seed=4, policy=policy)
+        got = emu_any(emu, O.GAME_PHANTOM, s, O.SOLVER_SO, policy, 600, 4, 0)
+        assert len(got) == len(want)
+        for f in fields:
+            assert (got[f] == want[f]).all(), ("so", f)
+        for p, want in O.mo_search(O.GAME_PHANTOM, s, 300, seed=5, policy=policy).items():
+            got = emu_any(emu, O.GAME_PHANTOM, s, O.SOLVER_MO, policy, 300, 5, p)
+            assert len(got) == len(want)
+            for f in fields:
+                assert (got[f] == want[f]).all(), ("mo", p, f)

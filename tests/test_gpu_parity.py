@@ -343,3 +343,42 @@ def test_goofspiel_playouts_and_trees_bit_exact(engine):
                     for f in EXP_FIELDS:
                         assert (got_nodes[f] == want[f]).all(), (solver, i, t, player, f)
             assert int(res["best_move"][i]) in capi.goof_legal(s)        # solvertest.cpp:121-128
+
+
+# ------------------------------------------------------------------ phantom m,n,k (partially observable moves)
+
+def test_phantom_playouts_and_trees_bit_exact(engine):
+    rnd = np.random.default_rng(4)
+    states = []
+    dims = [(3, 3, 3), (4, 4, 3), (6, 5, 4), (9, 9, 5)]
+    while len(states) < 8:
+        s = capi.phantom_init(*dims[len(states) % 4])
+        for _ in range(int(rnd.integers(0, 14))):
+            legal = capi.phantom_legal(s)
+            if not legal:
+                break
+            capi.phantom_apply(s, int(rnd.choice(legal)))
+        if capi.phantom_legal(s):
+            states.append(s)
+    conv = lambda s: O.PhantomState.from_buffer_copy(bytes(s))
+    got = engine.playouts(capi.GAME_PHANTOM, capi.pack_states(states), len(states), 128, seed=13)
+    for i, s in enumerate(states):
+        want = np.array([O.playout(O.GAME_PHANTOM, conv(s), 13, i, 0, j) for j in range(128)], dtype=np.uint32)
+        assert (got[i] == want).all(), i
+    per = 500
+    for solver in (capi.SOLVER_SO, capi.SOLVER_MO):
+        desc = engine.make_desc(capi.GAME_PHANTOM, len(states), 2, iterations=2 * per, seed=8, solver=solver)
+        res = engine.search(desc, capi.pack_states(states))
+        assert (res["iterations_done"] == per).all()
+        for i, s in enumerate(states):
+            for t in range(2):
+                if solver == capi.SOLVER_SO:
+                    wants = {None: O.so_search(O.GAME_PHANTOM, conv(s), per, seed=8, pos=i, tree=t)}
+                else:
+                    wants = O.mo_search(O.GAME_PHANTOM, conv(s), per, seed=8, pos=i, tree=t)
+                for player, want in wants.items():
+                    nodes = engine.dump_tree(i * 2 + t, 4 * per + 8, player=player)
+                    assert len(nodes) == len(want)
+                    for f in FIELDS:
+                        assert (nodes[f] == want[f]).all(), (solver, i, t, player, f)
+            assert int(res["best_move"][i]) in capi.phantom_legal(s)

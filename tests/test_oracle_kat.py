@@ -395,3 +395,69 @@ def test_goofspiel_ace_is_low(impl):
     assert impl.apply(s, 0) == 0            # player 1 bids the Two (value 2)
     assert impl.apply(s, 0) == 0            # reveal
     assert impl.result2(s, 1) == 2
+
+
+# ------------------------------------------------------------------ phantom m,n,k
+
+class OraclePhantom:
+    init = staticmethod(O.phantom_init)
+    legal = staticmethod(O.phantom_legal)
+    apply = staticmethod(O.phantom_apply)
+    result2 = staticmethod(O.phantom_result2)
+
+
+class ProductPhantom:
+    init = staticmethod(capi.phantom_init)
+    legal = staticmethod(capi.phantom_legal)
+    apply = staticmethod(capi.phantom_apply)
+
+    @staticmethod
+    def result2(s, p):
+        return capi.load_library().ismcts_phantom_result2(C.byref(s), p)
+
+
+PHANTOM_IMPLS = [OraclePhantom, ProductPhantom]
+
+
+@pytest.mark.parametrize("impl", PHANTOM_IMPLS)
+def test_phantom_constructed_and_do_move(impl):
+    # gametest.cpp:100-106,184-193 (TEMPLATE_TEST_CASE over MnkGame and PhantomMnkGame)
+    s = impl.init(3, 3, 3)
+    assert s.player == 0 and impl.legal(s) == list(range(9))
+    assert impl.apply(s, 4) == 0 and s.player == 1
+    assert impl.apply(s, 9) == capi.ERR_ILLEGAL_MOVE
+
+
+@pytest.mark.parametrize("impl", PHANTOM_IMPLS)
+@pytest.mark.parametrize("seq", MNK_P0_WINS)
+def test_phantom_k_in_a_row_wins(impl, seq):
+    # gametest.cpp:195-206
+    s = impl.init(3, 3, 3)
+    for mv in seq:
+        assert impl.apply(s, mv) == 0
+    assert impl.legal(s) == [] and impl.result2(s, 0) == 2 and impl.result2(s, 1) == 0
+
+
+@pytest.mark.parametrize("impl", PHANTOM_IMPLS)
+def test_phantom_occupied_cell_costs_no_turn(impl):
+    # phantommnkgame.cpp:83-105: trying an occupied cell only removes it from the player's list
+    s = impl.init(3, 3, 3)
+    assert impl.apply(s, 4) == 0 and s.player == 1
+    assert impl.apply(s, 4) == 0 and s.player == 1            # occupied by player 0: player 1 moves again
+    assert 4 not in impl.legal(s) and len(impl.legal(s)) == 8
+    assert impl.apply(s, 4) == capi.ERR_ILLEGAL_MOVE           # already struck off
+    assert impl.apply(s, 0) == 0 and s.player == 0
+    assert 0 in impl.legal(s)                                  # player 0 does not know about it
+
+
+def test_phantom_determinisation_keeps_known_positions():
+    # gametest.cpp:264-279: after 4,4,0,6,2 player 0 knows none of player 1's stones
+    s = O.phantom_init(3, 3, 3)
+    for mv in (4, 4, 0, 6, 2):
+        assert O.phantom_apply(s, mv) == 0
+    assert s.player == 0
+    # every iteration's determinisation keeps player 0's stones and places two stones for player 1:
+    # the root children of a search are exactly player 0's believed-free cells
+    nodes = O.so_search(O.GAME_PHANTOM, s, 400, seed=3)
+    top = nodes[1:][nodes[1:]["parent"] == 0]
+    assert sorted(top["move"].tolist()) == O.phantom_legal(s) == [0, 1, 2, 3, 5, 7, 8]
