@@ -398,13 +398,13 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
             }
             collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else if (so) {
-            launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
+            launch_search_variant<Game, SlotExp<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
             collect_roots_kernel<Game, SlotExp<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else if (ucb) {
-            launch_search_variant<Game, SlotUcb<Mask>, kMO, false>(ctx, P, grid);
+            launch_search_variant<Game, SlotUcb<Mask>, kMO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
             collect_roots_kernel<Game, SlotUcb<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else {
-            launch_search_variant<Game, SlotExp<Mask>, kMO, false>(ctx, P, grid);
+            launch_search_variant<Game, SlotExp<Mask>, kMO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
             collect_roots_kernel<Game, SlotExp<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
         }
         ctx->launches += 2;
