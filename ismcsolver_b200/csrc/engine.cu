@@ -49,7 +49,7 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
 
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
-template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
+template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks, bool kLockstep = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams P)
 {
     extern __shared__ uint64_t smem[];
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
-    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, scratch, kBlock, ring, kBlock, path);
+    lane_tree_search<Game, Slot, kKind, kShared, kLockstep>(P, gtid, gtid < lanes, scratch, kBlock, ring, kBlock, path);
 }
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
@@ -337,6 +337,13 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
     const size_t smem = block_smem<Game>();
     if constexpr (kTuned) {
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
+        if (ctx->sched_mode == 6) {
+            switch (ctx->min_blocks) {
+            case 4: search_kernel<Game, Slot, kKind, false, 4, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+            case 6: search_kernel<Game, Slot, kKind, false, 6, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+            default: search_kernel<Game, Slot, kKind, false, 8, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+            }
+        }
         switch (ctx->min_blocks) {
         case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;

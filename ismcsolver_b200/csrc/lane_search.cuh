@@ -437,13 +437,67 @@ struct Lane {
             if (P.sched_mode == 4 && n_chance + n_move + n_tree == 0) leave_barrier();
         }
     }
+
+    // ---- the lock-step loop (Schedule::kLockstep): the warp does ONE kind of step at a time
+    //
+    // All lanes of a warp start their iterations together and stay in the same phase of the
+    // iteration: every pending chance event is drained (the determinisation, a re-deal: the same
+    // number of cards for every lane of a position, up to the number of players still in), then the
+    // descent runs level by level, then every lane plays rollout moves until its round (or game)
+    // ends, then the chance events of the round end, and so on; the lanes backpropagate and start
+    // the next iteration together.  A lane that has nothing to do in a phase idles, but each phase
+    // is a tight loop over one code path with nothing to classify or vote on except its exit.
+    ISMCTS_DEV bool wants_chance() const { return phase != kDone && g.chance_pending(); }
+    ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !g.chance_pending() && !g.terminal(); }
+    ISMCTS_DEV bool wants_move() const { return phase == kRollout && !g.chance_pending() && !g.terminal(); }
+
+    // Refills the Philox rings of the lanes that have room, every fourth step of the warp: lanes that
+    // take part in a phase consume one word per step, so they refill in the same steps.
+    ISMCTS_DEV void tick_rng(uint32_t& tick)
+    {
+        if ((tick++ & 3u) == 0u && phase != kDone && rng.low()) rng.refill();
+    }
+
+    ISMCTS_DEV void run_lockstep(uint32_t gtid)
+    {
+        uint32_t tick = 0;
+        for (;;) {
+            if (!warp_any(phase != kDone)) break;
+            if (warp_any(wants_chance())) {
+                do {
+                    tick_rng(tick);
+                    if (wants_chance()) {
+                        const Mask set = g.chance_set();
+                        g.chance_step(set.kth(rng.below(set.count())));
+                    }
+                } while (warp_any(wants_chance()));
+            }
+            if (kTree && warp_any(wants_descent())) {
+                if (wants_descent()) { if (kShared) descend_shared(); else descend(); }
+                continue;
+            }
+            if (warp_any(wants_move())) {
+                do {
+                    tick_rng(tick);
+                    if (wants_move()) {
+                        const Mask set = g.legal();
+                        ++plies;
+                        g.play(set.kth(rng.below(set.count())));
+                    }
+                } while (warp_any(wants_move()));
+                continue;
+            }
+            // every lane still at work has reached the end of its game
+            if (phase != kDone) finish_iteration(gtid);
+        }
+    }
 };
 
 // The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees, or — tree
 // parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
 // lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
 // statistics of the root children are collected afterwards by collect_roots.
-template <class Game, class Slot, uint32_t kKind, bool kShared>
+template <class Game, class Slot, uint32_t kKind, bool kShared, bool kLockstep = false>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
                                  uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
@@ -480,7 +534,7 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
         }
         if (lane.budget_left()) lane.start_iteration();
     }
-    lane.run(gtid);
+    if (kLockstep) lane.run_lockstep(gtid); else lane.run(gtid);
     if (!valid) return;
     if (kShared) atomic_add_u64(P.iters_done + tree_index, lane.done);
     else P.iters_done[tree_index] = lane.done;
