@@ -11,7 +11,6 @@
 #include "mnk_game.cuh"
 #include "goof_game.cuh"
 #include "phantom_game.cuh"
-#include "kw_jobs.cuh"
 
 #include <cuda_runtime.h>
 
@@ -77,28 +76,14 @@ __global__ void collect_roots_kernel(SearchParams P)
     if (i < P.n_positions * P.trees) collect_roots<Game, Slot, kKind>(P, i);
 }
 
-// The headline path with the game states in shared memory and K jobs (trees) per lane (kw_jobs.cuh).
-template <uint32_t K, uint32_t NP, int kThreads, int kMinBlocks>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) kw_jobs_kernel(SearchParams P, uint32_t* paths)
-{
-    extern __shared__ uint64_t smem[];
-    KwJobs<K, NP> jobs(P);
-    jobs.bind(reinterpret_cast<uint32_t*>(smem), kThreads, blockIdx.x * (K * kThreads));
-    jobs.path_base = paths;
-    jobs.deadline = P.iterations > 0 ? 0 : global_timer_ns() + P.time_ns;
-    jobs.init_lane(threadIdx.x);
-    jobs.run(threadIdx.x);
-    jobs.finish_lane(threadIdx.x);
-}
-
-template <class Game>
+template <class Game, bool kLockstep>
 __global__ void __launch_bounds__(kBlock) playout_kernel(SearchParams P, uint32_t per_position)
 {
     extern __shared__ uint64_t smem[];
     uint64_t* scratch = smem + threadIdx.x;
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    lane_playout<Game>(P, gtid, gtid < P.n_positions * per_position, per_position, scratch, kBlock, ring, kBlock);
+    lane_playout<Game, kLockstep>(P, gtid, gtid < P.n_positions * per_position, per_position, scratch, kBlock, ring, kBlock);
 }
 
 } // namespace ismcts
@@ -124,9 +109,6 @@ struct ismcts_ctx {
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
     uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
-    uint32_t* paths = nullptr;    size_t paths_bytes = 0;    // kw_jobs kernel: descent paths, one row per tree
-    int kernel_version = 1;       // 1: lane_search.cuh for everything; 2: kw_jobs.cuh (experimental) for KW/SO/UCB1; ISMCTS_KERNEL
-    int jobs_per_lane = 2;        // ISMCTS_JOBS_PER_LANE (2 or 4)
 
     // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD /
     // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT override
@@ -207,8 +189,6 @@ int ismcts_create(int device, ismcts_ctx** out)
     if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(v);
     if (const char* v = std::getenv("ISMCTS_SCHED_MODE")) ctx->sched_mode = (uint32_t)std::atoi(v);
     if (const char* v = std::getenv("ISMCTS_SCHED_SPLIT")) ctx->sched_split_min = (uint32_t)std::atoi(v);
-    if (const char* v = std::getenv("ISMCTS_KERNEL")) ctx->kernel_version = std::atoi(v);
-    if (const char* v = std::getenv("ISMCTS_JOBS_PER_LANE")) ctx->jobs_per_lane = std::atoi(v);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -219,7 +199,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
-    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters); cudaFree(ctx->paths);
+    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -335,9 +315,10 @@ template <class Game, class Slot, uint32_t kKind, bool kTuned>
 static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32_t grid)
 {
     const size_t smem = block_smem<Game>();
+    const bool lockstep = ctx->sched_mode == 6;
     if constexpr (kTuned) {
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
-        if (ctx->sched_mode == 6) {
+        if (lockstep) {
             switch (ctx->min_blocks) {
             case 4: search_kernel<Game, Slot, kKind, false, 4, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
             case 6: search_kernel<Game, Slot, kKind, false, 6, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
@@ -346,38 +327,13 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
         }
         switch (ctx->min_blocks) {
         case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         }
     } else {
-        search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
+        if (lockstep) search_kernel<Game, Slot, kKind, false, 4, true><<<grid, kBlock, smem, ctx->stream>>>(P);
+        else search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
     }
-}
-
-template <uint32_t K, uint32_t NP, int kThreads, int kMinBlocks>
-static int launch_kw_jobs_variant(ismcts_ctx* ctx, const SearchParams& P, uint32_t tables)
-{
-    const size_t smem = (size_t)KwJobs<K, NP>::kWordsPerJob * K * kThreads * sizeof(uint32_t);
-    auto kernel = kw_jobs_kernel<K, NP, kThreads, kMinBlocks>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t per_cta = K * kThreads;
-    kernel<<<(tables + per_cta - 1) / per_cta, kThreads, smem, ctx->stream>>>(P, ctx->paths);
-    return ISMCTS_OK;
-}
-
-// Knockout Whist, SO-ISMCTS, UCB1, private trees: the jobs-in-shared-memory kernel.
-static int launch_kw_jobs(ismcts_ctx* ctx, const SearchParams& P, uint32_t tables, bool max4)
-{
-    int rc = ensure(ctx, ctx->paths, ctx->paths_bytes, (size_t)tables * KwGame::kMaxDepth * sizeof(uint32_t));
-    if (rc) return rc;
-    if (max4) {
-        // 26 words = 104 B per job: 512 jobs per CTA of 256 threads (K = 2), four CTAs per SM
-        if (ctx->jobs_per_lane == 4) return launch_kw_jobs_variant<4, 4, 128, 4>(ctx, P, tables);
-        return launch_kw_jobs_variant<2, 4, 256, 4>(ctx, P, tables);
-    }
-    // up to 7 players: 32 words = 128 B per job, three CTAs per SM
-    return launch_kw_jobs_variant<2, 7, 256, 3>(ctx, P, tables);
 }
 
 template <class Game>
@@ -392,26 +348,22 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
     const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
         init_shared_roots_kernel<SlotUcb<Mask>><<<tgrid, 128, 0, ctx->stream>>>(P);
-        search_kernel<Game, SlotUcb<Mask>, kSO, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
+        if (ctx->sched_mode == 6) search_kernel<Game, SlotUcb<Mask>, kSO, true, 4, true><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
+        else search_kernel<Game, SlotUcb<Mask>, kSO, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
         collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         ctx->launches += 3;
     } else {
         if (so && ucb) {
-            if (Game::kGameId == ISMCTS_GAME_KW && ctx->kernel_version == 2) {
-                rc = launch_kw_jobs(ctx, P, tables, (d->flags & ISMCTS_FLAG_KW_MAX4) != 0);
-                if (rc) return rc;
-            } else {
-                launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
-            }
+            launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
             collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else if (so) {
-            launch_search_variant<Game, SlotExp<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
             collect_roots_kernel<Game, SlotExp<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else if (ucb) {
-            launch_search_variant<Game, SlotUcb<Mask>, kMO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            launch_search_variant<Game, SlotUcb<Mask>, kMO, false>(ctx, P, grid);
             collect_roots_kernel<Game, SlotUcb<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else {
-            launch_search_variant<Game, SlotExp<Mask>, kMO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            launch_search_variant<Game, SlotExp<Mask>, kMO, false>(ctx, P, grid);
             collect_roots_kernel<Game, SlotExp<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
         }
         ctx->launches += 2;
@@ -643,7 +595,8 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
     P.prepared = ctx->prepared;
     with_game(game, [&](auto tag) {
         using Game = typename decltype(tag)::Game;
-        playout_kernel<Game><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
+        if (ctx->sched_mode == 6) playout_kernel<Game, true><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
+        else playout_kernel<Game, false><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
         return 0;
     });
     ctx->launches++;

@@ -298,6 +298,85 @@ struct KwGame {
     {
         if (mode != kPlay) chance_step(b); else play(b);
     }
+
+    // ---- phases of the lock-step loop (lane_search.cuh, run_lockstep): the same transitions as
+    // chance_step() and play(), drawn in the same order from the same stream, as tight loops over
+    // ONE kind of step with the state of that kind in registers.
+    static constexpr bool kPhased = true;
+
+    // Every pending chance event of the warp: the tie-breaks (at most one per lane, they start
+    // a deal), then the deals card by card.  The hand being dealt is collected in registers
+    // and stored when it is complete.  `active`: the lane takes part (it may still have nothing
+    // pending).
+    template <class Rng>
+    ISMCTS_DEV void chance_phase(Rng& rng, bool active)
+    {
+        if (warp_any(active && mode == kTie)) {
+            if (active && mode == kTie) chance_step(kth_bit32((uint32_t)pool, rng.below(popc32((uint32_t)pool))));
+        }
+        uint64_t from = pool, hand_acc = 0;
+        uint32_t left = popc64(from);
+        for (uint32_t s = 0; warp_any(active && mode == kDeal); ++s) {
+            if ((s & 3u) == 0u && active && rng.low()) rng.refill();
+            if (active && mode == kDeal) {
+                const uint64_t bit = (uint64_t)1 << kth_bit64(from, rng.below_waiting(left));
+                --left;
+                from &= ~bit;
+                hand_acc |= bit;
+                if (--deal_left == 0) {
+                    set_hand(deal_player, hand(deal_player) | hand_acc);
+                    hand_acc = 0;
+                    if (need) {
+                        const uint32_t shift = ctz32(need) & ~3u;
+                        deal_player = shift >> 2;
+                        deal_left = (need >> shift) & 15u;
+                        need &= ~(15u << shift);
+                    } else {
+                        mode = kPlay;
+                        pool = from;
+                    }
+                }
+            }
+        }
+    }
+
+    // Rollout moves (simulate, solverbase.h:36-43) for the lanes with `rolling` until their
+    // round ends (a chance event becomes pending) or their game does.  `plies` counts the moves.
+    template <class Rng>
+    ISMCTS_DEV void play_phase(Rng& rng, bool rolling, uint32_t& plies)
+    {
+        // the round winner calls trumps: one of the four suits
+        if (warp_any(rolling && mode == kPlay && tricks_left != 0 && request_trump)) {
+            if (rolling && mode == kPlay && tricks_left != 0 && request_trump) { ++plies; play(13u * rng.below(4)); }
+        }
+        // the hand of the player to move (lanes that do not take part may hold no game at all)
+        uint64_t h = rolling && mode == kPlay && tricks_left != 0 ? hand(player) : 0;
+        for (uint32_t s = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++s) {
+            if ((s & 3u) == 0u && rolling && rng.low()) rng.refill();
+            if (rolling && mode == kPlay && tricks_left != 0) {
+                // validMoves, knockoutwhist.cpp:122-136: follow suit if possible (with one card
+                // in hand both cases give the same set)
+                const uint64_t follow = h & (kSuit << (13u * lead_suit));
+                const uint64_t set = trick_len != 0 && follow != 0 ? follow : h;
+                const uint32_t b = kth_bit64(set, rng.below_waiting(popc64(set)));
+                ++plies;
+                // doMove, :95-115
+                set_hand(player, h & ~((uint64_t)1 << b));
+                fold_trick(trick_len, player, b);
+                ++trick_len;
+                player = next_alive(player);
+                if (trick_len == popc32(alive4)) {            // finishTrick, :155-161
+                    tricks += 1u << (4 * win_player);
+                    const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
+                    best = taken > best ? taken : best;
+                    trick_len = 0;
+                    player = win_player;
+                }
+                h = hand(player);
+                if (h == 0) finish_round();
+            }
+        }
+    }
 };
 
 } // namespace ismcts

@@ -117,6 +117,10 @@ struct Schedule {
     }
 };
 
+// Games that bring their own phase loops for the lock-step schedule (chance_phase, play_phase).
+template <class G> constexpr auto game_is_phased(int) -> decltype(G::kPhased) { return G::kPhased; }
+template <class G> constexpr bool game_is_phased(long) { return false; }
+
 // Solver kinds of a lane.  kPlayout: determinise + rollout only
 // (SolverBase::simulate after cloneAndRandomise), one iteration per lane, no tree.
 enum LaneKind : uint32_t { kPlayout = 0, kSO = 1, kMO = 2 };
@@ -463,7 +467,9 @@ struct Lane {
         uint32_t tick = 0;
         for (;;) {
             if (!warp_any(phase != kDone)) break;
-            if (warp_any(wants_chance())) {
+            if constexpr (game_is_phased<Game>(0)) {
+                g.chance_phase(rng, phase != kDone);
+            } else if (warp_any(wants_chance())) {
                 do {
                     tick_rng(tick);
                     if (wants_chance()) {
@@ -477,14 +483,18 @@ struct Lane {
                 continue;
             }
             if (warp_any(wants_move())) {
-                do {
-                    tick_rng(tick);
-                    if (wants_move()) {
-                        const Mask set = g.legal();
-                        ++plies;
-                        g.play(set.kth(rng.below(set.count())));
-                    }
-                } while (warp_any(wants_move()));
+                if constexpr (game_is_phased<Game>(0)) {
+                    g.play_phase(rng, phase == kRollout, plies);
+                } else {
+                    do {
+                        tick_rng(tick);
+                        if (wants_move()) {
+                            const Mask set = g.legal();
+                            ++plies;
+                            g.play(set.kth(rng.below(set.count())));
+                        }
+                    } while (warp_any(wants_move()));
+                }
                 continue;
             }
             // every lane still at work has reached the end of its game
@@ -581,7 +591,7 @@ ISMCTS_DEV void collect_roots(const SearchParams& P, uint32_t index)
 }
 
 // Determinise + rollout only: playout `gtid % per_position` of position `gtid / per_position`.
-template <class Game>
+template <class Game, bool kLockstep = false>
 ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, uint32_t per_position, uint64_t* scratch,
                              uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride)
 {
@@ -599,7 +609,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
         lane.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
         lane.start_iteration();
     }
-    lane.run(gtid);
+    if (kLockstep) lane.run_lockstep(gtid); else lane.run(gtid);
 }
 
 } // namespace ismcts

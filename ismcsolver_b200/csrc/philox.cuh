@@ -33,63 +33,68 @@ ISMCTS_DEV void philox4x32_10(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3
 }
 
 // The stream of one lane.  Generated words wait in a small ring in shared memory
-// (one 4-byte column per thread, 8 rows): the search loop refills all lanes of a
-// warp at the same passes (every fourth), so the ten Philox rounds are executed
-// with all lanes active although the lanes consume their words at different
-// rates and start their iterations at different times.
+// (one 4-byte column per thread, 8 rows; word d of the iteration sits in row
+// d % 8): the search loop refills all lanes of a warp in the same steps, so the
+// ten Philox rounds are executed with all lanes active although the lanes
+// consume their words at different rates.
 struct LaneRng {
     static constexpr uint32_t kRingWords = 8;
     uint32_t k0, k1;      // key = seed
     uint32_t c1, c2, c3;  // iteration, tree, position
     uint32_t next_block;  // next block (d / 4) to generate
-    uint32_t head, count; // ring read position, words waiting
-    uint32_t* ring;       // ring[(i % 8) * stride]
+    uint32_t d;           // next word to hand out; words [d, 4 * next_block) wait in the ring
+    uint32_t* ring;       // ring[(d % 8) * stride]
     uint32_t stride;
 
     ISMCTS_DEV void init(uint64_t seed, uint32_t pos, uint32_t tree, uint32_t* ring_base, uint32_t ring_stride)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        c1 = 0; c2 = tree; c3 = pos; next_block = 0; head = 0; count = 0;
+        c1 = 0; c2 = tree; c3 = pos; next_block = 0; d = 0;
         ring = ring_base; stride = ring_stride;
     }
 
-    // Generates the next block of four words into the ring.
+    // Generates the next block of four words into its half of the ring.
     ISMCTS_DEV void refill()
     {
         uint32_t w[4];
         philox4x32_10(next_block, c1, c2, c3, k0, k1, w);
+        uint32_t* half = ring + (next_block & 1u) * 4u * stride;
         ++next_block;
-        const uint32_t at = head + count;
 #pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) ring[((at + i) & (kRingWords - 1)) * stride] = w[i];
-        count += 4;
+        for (uint32_t i = 0; i < 4; ++i) half[i * stride] = w[i];
     }
 
-    // Starts the stream of `iteration` at word 0 (or at word `d` for the host helpers).
-    ISMCTS_DEV void begin_iteration(uint32_t iteration, uint32_t d = 0)
+    // Starts the stream of `iteration` at word 0 (or at word `at` for the host helpers).
+    ISMCTS_DEV void begin_iteration(uint32_t iteration, uint32_t at = 0)
     {
-        c1 = iteration; next_block = d >> 2; head = 0; count = 0;
+        c1 = iteration; next_block = at >> 2; d = at;
         refill();
-        head = d & 3u; count -= d & 3u;
     }
 
-    ISMCTS_DEV bool low() const { return count < 4; }   // room for one more block
-    ISMCTS_DEV uint32_t consumed() const { return next_block * 4 - count; } // = d, words handed out
+    ISMCTS_DEV uint32_t waiting() const { return 4u * next_block - d; }
+    ISMCTS_DEV bool low() const { return waiting() <= 4u; }   // room for one more block
+    ISMCTS_DEV uint32_t consumed() const { return d; }         // words handed out
 
-    // Next 32-bit word of the stream.  The search loop refills all lanes together
-    // whenever low(), at least once per four passes, so a word is normally waiting;
-    // a lane that draws several words in one pass (an EXP3 descent draws one per
-    // level) generates the block it needs here.
+    // Next word when one is known to wait: the loops refill every lane that is low() at least
+    // every fourth step and draw at most one word per step.
+    ISMCTS_DEV uint32_t word_waiting()
+    {
+        const uint32_t w = ring[(d & (kRingWords - 1)) * stride];
+        ++d;
+        return w;
+    }
+
+    // Next 32-bit word of the stream; generates the block it needs when nothing waits (a lane
+    // that draws several words in one step: an EXP3 descent draws one per level).
     ISMCTS_DEV uint32_t word()
     {
-        if (count == 0) refill();
-        const uint32_t w = ring[(head & (kRingWords - 1)) * stride];
-        ++head; --count;
-        return w;
+        if (waiting() == 0) refill();
+        return word_waiting();
     }
 
     // Uniform integer in [0, n) — always consumes exactly one word.
     ISMCTS_DEV uint32_t below(uint32_t n) { return mulhi32(word(), n); }
+    ISMCTS_DEV uint32_t below_waiting(uint32_t n) { return mulhi32(word_waiting(), n); }
 };
 
 } // namespace ismcts

@@ -16,7 +16,7 @@ FIELDS = ("parent", "move", "player", "visits", "score2", "avail")
 
 
 @pytest.fixture(scope="module")
-def emu():
+def emu_lib():
     subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
     E = C.CDLL(os.path.join(EMU_DIR, "libemu.so"))
     E.emu_playout.restype = C.c_uint32
@@ -30,6 +30,15 @@ def emu():
     E.emu_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
                              C.c_uint32, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
     return E
+
+
+@pytest.fixture(params=[6, 0], ids=["lockstep", "microsteps"])
+def emu(emu_lib, request):
+    """Every test runs under both loops of lane_search.cuh: the lock-step loop (the default of the
+    library) and the micro-step loop."""
+    emu_lib.emu_set_schedule_mode(request.param, 8)
+    yield emu_lib
+    emu_lib.emu_set_schedule_mode(6, 8)
 
 
 def emu_search(E, game, root, iters, seed, pos, tree, exploration=0.7):
@@ -171,7 +180,7 @@ def test_result_does_not_depend_on_the_pass_plan(emu, mode, split):
         for f in FIELDS:
             assert (got[f] == want[f]).all(), f
     finally:
-        emu.emu_set_schedule_mode(0, 8)
+        emu.emu_set_schedule_mode(6, 8)
 
 
 def emu_shared(E, game, root, iters, width, seed):
