@@ -37,8 +37,7 @@ ISMCTS_DEV uint64_t global_timer_ns()
     return t;
 }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
-// Warp votes over all 32 lanes (every lane of a warp runs the search loop, see lane_search.cuh).
-ISMCTS_DEV uint32_t warp_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+// Warp vote over all 32 lanes (every lane of a warp runs the search loop, see lane_search.cuh).
 ISMCTS_DEV bool warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 // Shared-tree (tree-parallel) primitives: slot reservation, child publication, counters.
 ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value) { return atomicCAS(p, expect, value); }
@@ -63,8 +62,10 @@ ISMCTS_DEV uint64_t global_timer_ns()
     return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
                std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-ISMCTS_DEV uint32_t warp_ballot(bool p) { return p ? 1u : 0u; } // host build: a "warp" of one lane
-ISMCTS_DEV bool warp_any(bool p) { return p; }
+// host build: a "warp" of one lane, unless a test harness that runs several lanes (tests/emu:
+// fibers) installs its vote
+inline bool (*g_host_warp_any)(bool) = nullptr;
+ISMCTS_DEV bool warp_any(bool p) { return g_host_warp_any ? g_host_warp_any(p) : p; }
 ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value)
 {
     const uint32_t old = *p;

@@ -48,7 +48,7 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
 
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
-template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks, bool kLockstep = false>
+template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams P)
 {
     extern __shared__ uint64_t smem[];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
-    lane_tree_search<Game, Slot, kKind, kShared, kLockstep>(P, gtid, gtid < lanes, scratch, kBlock, ring, kBlock, path);
+    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, scratch, kBlock, ring, kBlock, path);
 }
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
@@ -76,14 +76,14 @@ __global__ void collect_roots_kernel(SearchParams P)
     if (i < P.n_positions * P.trees) collect_roots<Game, Slot, kKind>(P, i);
 }
 
-template <class Game, bool kLockstep>
+template <class Game>
 __global__ void __launch_bounds__(kBlock) playout_kernel(SearchParams P, uint32_t per_position)
 {
     extern __shared__ uint64_t smem[];
     uint64_t* scratch = smem + threadIdx.x;
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    lane_playout<Game, kLockstep>(P, gtid, gtid < P.n_positions * per_position, per_position, scratch, kBlock, ring, kBlock);
+    lane_playout<Game>(P, gtid, gtid < P.n_positions * per_position, per_position, scratch, kBlock, ring, kBlock);
 }
 
 } // namespace ismcts
@@ -110,10 +110,6 @@ struct ismcts_ctx {
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
     uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
 
-    // schedule of the search loop (lane_search.cuh); ISMCTS_TREE_THRESH / ISMCTS_TREE_PERIOD /
-    // ISMCTS_SCHED_MODE / ISMCTS_SCHED_SPLIT override
-    uint32_t tree_thresh = 12, tree_period = 32;
-    uint32_t sched_mode = 0, sched_split_min = 8;
     int min_blocks = 8;          // resident CTAs per SM the SO/UCB1 Knockout Whist kernel is compiled for; ISMCTS_MIN_BLOCKS
 
     // geometry of the last search (for ismcts_dump_tree)
@@ -183,12 +179,7 @@ int ismcts_create(int device, ismcts_ctx** out)
                                                       cudaGetErrorString(cudaGetLastError()));
     }
     ctx->stream = ctx->own_stream;
-    if (const char* v = std::getenv("ISMCTS_TREE_THRESH")) ctx->tree_thresh = std::max(1, std::atoi(v));
-    if (const char* v = std::getenv("ISMCTS_TREE_PERIOD")) ctx->tree_period = std::max(1, std::atoi(v));
-    while (ctx->tree_period & (ctx->tree_period - 1)) ++ctx->tree_period; // a power of two
     if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(v);
-    if (const char* v = std::getenv("ISMCTS_SCHED_MODE")) ctx->sched_mode = (uint32_t)std::atoi(v);
-    if (const char* v = std::getenv("ISMCTS_SCHED_SPLIT")) ctx->sched_split_min = (uint32_t)std::atoi(v);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -315,24 +306,15 @@ template <class Game, class Slot, uint32_t kKind, bool kTuned>
 static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32_t grid)
 {
     const size_t smem = block_smem<Game>();
-    const bool lockstep = ctx->sched_mode == 6;
     if constexpr (kTuned) {
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
-        if (lockstep) {
-            switch (ctx->min_blocks) {
-            case 4: search_kernel<Game, Slot, kKind, false, 4, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-            case 6: search_kernel<Game, Slot, kKind, false, 6, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-            default: search_kernel<Game, Slot, kKind, false, 8, true><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-            }
-        }
         switch (ctx->min_blocks) {
         case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         }
     } else {
-        if (lockstep) search_kernel<Game, Slot, kKind, false, 4, true><<<grid, kBlock, smem, ctx->stream>>>(P);
-        else search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
+        search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
     }
 }
 
@@ -348,8 +330,7 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
     const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
         init_shared_roots_kernel<SlotUcb<Mask>><<<tgrid, 128, 0, ctx->stream>>>(P);
-        if (ctx->sched_mode == 6) search_kernel<Game, SlotUcb<Mask>, kSO, true, 4, true><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
-        else search_kernel<Game, SlotUcb<Mask>, kSO, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
+        search_kernel<Game, SlotUcb<Mask>, kSO, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
         collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         ctx->launches += 3;
     } else {
@@ -437,8 +418,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.max_nodes = (uint32_t)std::min<uint64_t>(((uint64_t)1 << (log2cap - 1)), (uint64_t)per_lane * (ctx->ln_count - 2));
     P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
-    P.playout_out = nullptr; P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
-    P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
+    P.playout_out = nullptr;
     P.lanes_per_tree = width; P.node_counters = ctx->counters;
 
     ctx->last_log2cap = log2cap; ctx->last_lanes = tables; ctx->last_game = d->game;
@@ -588,15 +568,12 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
     SearchParams P;
     std::memset(&P, 0, sizeof P);
     P.n_positions = n_positions; P.seed = seed; P.playout_out = ctx->play_out;
-    P.tree_thresh = ctx->tree_thresh; P.tree_period = ctx->tree_period;
-    P.sched_mode = ctx->sched_mode; P.sched_split_min = ctx->sched_split_min;
     rc = with_game(game, [&](auto tag) { return launch_prepare<typename decltype(tag)::Game>(ctx, ctx->roots, n_positions); });
     if (rc) return rc;
     P.prepared = ctx->prepared;
     with_game(game, [&](auto tag) {
         using Game = typename decltype(tag)::Game;
-        if (ctx->sched_mode == 6) playout_kernel<Game, true><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
-        else playout_kernel<Game, false><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
+        playout_kernel<Game><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P, per_position);
         return 0;
     });
     ctx->launches++;

@@ -9,20 +9,24 @@
 // exactly the reference's sequential semantics per tree; root parallelism
 // (execution.h:181-232) comes from the trees being independent.
 //
-// How it is mapped to the GPU.  An iteration is a sequence of micro-steps of two
-// kinds.  (1) Random micro-steps: "remove a uniformly random member from a bit
-// set" — a determinisation or re-deal card, a tie-break, a rollout move; about
-// 150 per Knockout Whist iteration, a few dozen instructions each, identical
-// code for every lane whatever iteration or phase it is in.  (2) Tree
-// operations: the UCB descent with the expansion (once per iteration) and the
-// backpropagation with the start of the next iteration (once per iteration);
-// memory-bound and divergent.  Every pass of the loop performs one random
-// micro-step for all lanes that need one; lanes that need a tree operation wait
-// until enough of them are pending (or a few passes have gone by) and then do
-// them together.  Lanes never wait for the longest playout of their warp: a
-// lane that finishes an iteration starts its next one while its neighbours are
-// still rolling out.  The result of a tree does not depend on this schedule —
-// each lane performs exactly the sequential sequence of operations.
+// How it is mapped to the GPU: the lock-step loop.  The 32 lanes of a warp start their
+// iterations together and stay in the same PHASE of the iteration, so that the warp runs one
+// short code path at a time with (nearly) all lanes active:
+//   1. chance events — the determinisation (cloneAndRandomise) at the start, later the
+//      re-deals and tie-breaks a move triggers: every lane draws until nothing is pending;
+//   2. descent — UCB1 / EXP3 selection and the expansion, level by level (lanes leave the
+//      loop at different depths; a move that triggers chance events sends the warp to 1);
+//   3. rollout — every lane plays uniformly random moves until its round or game ends
+//      (chance events of the round end: back to 1);
+//   4. backpropagation and the start of the next iteration, together.
+// A lane with nothing to do in a phase idles: in Knockout Whist the lanes of a position deal
+// the same number of cards per player and play the same number of tricks per round, they
+// differ in the number of players still in and in the number of rounds (measured: 73 % of
+// the lane-steps are useful).  The loop this replaced let every lane do whatever step it
+// needed in every pass; a pass then executed the union of all code paths with half of the
+// lanes active in each and was 2.2x (Knockout Whist, SO) to 3.6x (MO, EXP3; m,n,k) slower
+// (profiles/r01_lockstep.md).  The result of a tree does not depend on the schedule — each
+// lane performs exactly the sequential sequence of operations of its tree.
 #pragma once
 
 #include "devdefs.cuh"
@@ -52,10 +56,6 @@ struct SearchParams {
     uint64_t* avail;
     uint64_t* iters_done;    // [n_positions * trees]
     uint32_t* playout_out;   // playout-only launches: one packed result per thread
-    uint32_t tree_thresh;    // run the pending tree operations when this many lanes of the warp wait ...
-    uint32_t tree_period;    // ... or at the latest every tree_period passes (a power of two)
-    uint32_t sched_mode;     // Schedule::mode
-    uint32_t sched_split_min;
     // tree parallelisation: `lanes_per_tree` lanes search ONE tree together (1 = private trees)
     uint32_t lanes_per_tree;
     uint32_t* node_counters; // [n_positions * trees] nodes created per shared tree (root included)
@@ -68,54 +68,7 @@ ISMCTS_DEV uint64_t tree_iterations(uint64_t total, uint32_t trees_total, uint32
     return total / trees_total + ((uint64_t)tree_global < total % trees_total ? 1u : 0u);
 }
 
-enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2, kBarrier = 3 };
-
-// Which kinds of micro-step a pass performs (the same for all lanes of the warp).
-struct PassPlan { bool chance, move, tree; };
-
-// The schedule of a warp: decides from the numbers of lanes waiting for a chance
-// event, a rollout move and a tree operation what the next pass does.  A pass
-// that does one kind only runs one short code path with the waiting lanes
-// active; a pass that does several kinds runs the paths one after the other.
-// The result of a search does not depend on the schedule (tests/emu checks that).
-struct Schedule {
-    uint32_t tree_thresh, tree_period, mode, split_min;
-    uint32_t current; // kind the warp is running (hysteresis modes)
-
-    ISMCTS_DEV void init(const SearchParams& P)
-    {
-        tree_thresh = P.tree_thresh; tree_period = P.tree_period; mode = P.sched_mode; split_min = P.sched_split_min;
-        current = 0;
-    }
-
-    ISMCTS_DEV PassPlan plan_pass(uint32_t n_chance, uint32_t n_move, uint32_t n_tree, uint32_t pass)
-    {
-        PassPlan plan;
-        plan.tree = n_tree != 0 && (n_tree >= tree_thresh || (pass & (tree_period - 1u)) == tree_period - 1u ||
-                                    n_chance + n_move == 0);
-        if (mode == 0) {                       // every kind every pass
-            plan.chance = n_chance != 0; plan.move = n_move != 0;
-        } else if (mode == 1) {                // the kind more lanes wait for
-            plan.chance = n_chance >= n_move && n_chance != 0;
-            plan.move = !plan.chance && n_move != 0;
-        } else if (mode == 2) {                // majority, but both when the minority is large enough
-            const uint32_t lo = n_chance < n_move ? n_chance : n_move;
-            const bool both = lo >= split_min;
-            plan.chance = (both || n_chance >= n_move) && n_chance != 0;
-            plan.move = (both || n_move > n_chance) && n_move != 0;
-        } else if (mode == 4 || mode == 5) {   // phases: all chance events first, then moves (4: + iteration barrier)
-            plan.chance = n_chance != 0;
-            plan.move = !plan.chance && n_move != 0;
-        } else {                               // stay with a kind until few lanes want it
-            const uint32_t n_cur = current == 0 ? n_chance : n_move, n_other = current == 0 ? n_move : n_chance;
-            if (n_cur < split_min && n_other > n_cur) current ^= 1u;
-            plan.chance = current == 0 && n_chance != 0;
-            plan.move = current == 1 && n_move != 0;
-            if (!plan.chance && !plan.move) { plan.chance = n_chance != 0; plan.move = n_move != 0 && !plan.chance; }
-        }
-        return plan;
-    }
-};
+enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
 
 // Games that bring their own phase loops for the lock-step schedule (chance_phase, play_phase).
 template <class G> constexpr auto game_is_phased(int) -> decltype(G::kPhased) { return G::kPhased; }
@@ -228,15 +181,8 @@ struct Lane {
             P.playout_out[gtid] = (g.outcome() & 0xFFu) | ((plies & 0xFFFu) << 8) | ((rng.consumed() & 0xFFFu) << 20);
         }
         ++done;
-        if (P.sched_mode == 4) phase = kBarrier;              // wait for the other lanes of the warp
-        else if (budget_left()) start_iteration();
+        if (budget_left()) start_iteration();
         else phase = kDone;
-    }
-
-    // Iteration barrier (schedule mode 4): called when every lane still at work waits at it.
-    ISMCTS_DEV void leave_barrier()
-    {
-        if (phase == kBarrier) { if (budget_left()) start_iteration(); else phase = kDone; }
     }
 
     template <class S> ISMCTS_DEV static double slot_prob(const S& s) { if constexpr (S::kExp3) return s.prob; else return 1.0; }
@@ -390,67 +336,7 @@ struct Lane {
         }
     }
 
-    // ---- one pass of the loop, in two halves so that the warp votes sit between them
-
-    struct Wants { bool chance, move, tree, over; };
-
-    ISMCTS_DEV Wants classify() const
-    {
-        Wants w;
-        const bool playing = phase != kDone && phase != kBarrier;
-        w.chance = playing && g.chance_pending();
-        w.over = playing && !w.chance && g.terminal();
-        w.tree = w.over || (playing && !w.chance && phase == kSelect);
-        w.move = playing && !w.chance && !w.tree;
-        return w;
-    }
-
-    ISMCTS_DEV void act(const Wants& w, const PassPlan& plan, uint32_t pass, uint32_t gtid)
-    {
-        const bool do_chance = plan.chance && w.chance, do_move = plan.move && w.move;
-        if (do_chance || do_move) {
-            // One random micro-step.  Chance: a determinisation (cloneAndRandomise) or re-deal card or
-            // a tie-break.  Move: simulate, solverbase.h:36-43 with RandomElement, utility.h:69-83.
-            // Both are "the k-th member of a set", drawn by code the two kinds share.
-            const Mask set = do_chance ? g.chance_set() : g.legal();
-            const uint32_t b = set.kth(rng.below(set.count()));
-            if (do_chance) g.chance_step(b);
-            else { ++plies; g.play(b); }
-        }
-        if (plan.tree && w.tree) {
-            if (w.over) finish_iteration(gtid);
-            else if (kShared) descend_shared();
-            else descend();
-        }
-        if ((pass & 3u) == 3u && phase != kDone && rng.low()) rng.refill();
-    }
-
-    // The loop.  Every pass performs, for the whole warp, the kinds of micro-step the
-    // schedule (plan_pass) picks from the numbers of lanes waiting for each kind.
-    ISMCTS_DEV void run(uint32_t gtid)
-    {
-        Schedule sched;
-        sched.init(P);
-        for (uint32_t pass = 0;; ++pass) {
-            if (!warp_any(phase != kDone)) break;
-            const Wants w = classify();
-            const uint32_t n_chance = popc32(warp_ballot(w.chance)), n_move = popc32(warp_ballot(w.move)),
-                           n_tree = popc32(warp_ballot(w.tree));
-            const PassPlan plan = sched.plan_pass(n_chance, n_move, n_tree, pass);
-            act(w, plan, pass, gtid);
-            if (P.sched_mode == 4 && n_chance + n_move + n_tree == 0) leave_barrier();
-        }
-    }
-
-    // ---- the lock-step loop (Schedule::kLockstep): the warp does ONE kind of step at a time
-    //
-    // All lanes of a warp start their iterations together and stay in the same phase of the
-    // iteration: every pending chance event is drained (the determinisation, a re-deal: the same
-    // number of cards for every lane of a position, up to the number of players still in), then the
-    // descent runs level by level, then every lane plays rollout moves until its round (or game)
-    // ends, then the chance events of the round end, and so on; the lanes backpropagate and start
-    // the next iteration together.  A lane that has nothing to do in a phase idles, but each phase
-    // is a tight loop over one code path with nothing to classify or vote on except its exit.
+    // ---- the lock-step loop (see the head of this file)
     ISMCTS_DEV bool wants_chance() const { return phase != kDone && g.chance_pending(); }
     ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !g.chance_pending() && !g.terminal(); }
     ISMCTS_DEV bool wants_move() const { return phase == kRollout && !g.chance_pending() && !g.terminal(); }
@@ -462,7 +348,7 @@ struct Lane {
         if ((tick++ & 3u) == 0u && phase != kDone && rng.low()) rng.refill();
     }
 
-    ISMCTS_DEV void run_lockstep(uint32_t gtid)
+    ISMCTS_DEV void run(uint32_t gtid)
     {
         uint32_t tick = 0;
         for (;;) {
@@ -507,7 +393,7 @@ struct Lane {
 // parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
 // lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
 // statistics of the root children are collected afterwards by collect_roots.
-template <class Game, class Slot, uint32_t kKind, bool kShared, bool kLockstep = false>
+template <class Game, class Slot, uint32_t kKind, bool kShared>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
                                  uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
@@ -544,7 +430,7 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
         }
         if (lane.budget_left()) lane.start_iteration();
     }
-    if (kLockstep) lane.run_lockstep(gtid); else lane.run(gtid);
+    lane.run(gtid);
     if (!valid) return;
     if (kShared) atomic_add_u64(P.iters_done + tree_index, lane.done);
     else P.iters_done[tree_index] = lane.done;
@@ -591,7 +477,7 @@ ISMCTS_DEV void collect_roots(const SearchParams& P, uint32_t index)
 }
 
 // Determinise + rollout only: playout `gtid % per_position` of position `gtid / per_position`.
-template <class Game, bool kLockstep = false>
+template <class Game>
 ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, uint32_t per_position, uint64_t* scratch,
                              uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride)
 {
@@ -609,7 +495,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
         lane.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
         lane.start_iteration();
     }
-    if (kLockstep) lane.run_lockstep(gtid); else lane.run(gtid);
+    lane.run(gtid);
 }
 
 } // namespace ismcts

@@ -16,36 +16,25 @@ FIELDS = ("parent", "move", "player", "visits", "score2", "avail")
 
 
 @pytest.fixture(scope="module")
-def emu_lib():
+def emu():
     subprocess.run(["make", "-C", EMU_DIR], check=True, capture_output=True)
     E = C.CDLL(os.path.join(EMU_DIR, "libemu.so"))
     E.emu_playout.restype = C.c_uint32
     E.emu_playout.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
-    E.emu_so_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double,
-                                C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
-    E.emu_set_schedule.argtypes = [C.c_uint32, C.c_uint32]
-    E.emu_set_schedule_mode.argtypes = [C.c_uint32, C.c_uint32]
     E.emu_shared_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     E.emu_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
-                             C.c_uint32, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32,
+                             C.POINTER(C.c_uint32)]
     return E
 
 
-@pytest.fixture(params=[6, 0], ids=["lockstep", "microsteps"])
-def emu(emu_lib, request):
-    """Every test runs under both loops of lane_search.cuh: the lock-step loop (the default of the
-    library) and the micro-step loop."""
-    emu_lib.emu_set_schedule_mode(request.param, 8)
-    yield emu_lib
-    emu_lib.emu_set_schedule_mode(6, 8)
-
-
-def emu_search(E, game, root, iters, seed, pos, tree, exploration=0.7):
+def emu_search(E, game, root, iters, seed, pos, tree, exploration=0.7, width=1, dump=0):
+    """SO-ISMCTS + UCB1; a warp of `width` lanes searches trees tree..tree+width-1, lane `dump` is returned."""
     nodes = np.zeros(iters + 2, dtype=O.NODE_DTYPE)
     n = C.c_uint32()
-    assert E.emu_so_search(game, C.byref(root), iters, seed, pos, tree, exploration, nodes.ctypes.data, iters + 2,
-                           C.byref(n)) == 0
+    assert E.emu_search(game, C.byref(root), O.SOLVER_SO, O.POLICY_UCB1, iters, seed, pos, tree, width, dump,
+                        exploration, 0, nodes.ctypes.data, iters + 2, C.byref(n)) == 0
     return nodes[:n.value]
 
 
@@ -110,28 +99,43 @@ def test_exploration_constant_is_used(emu):
             assert (got[f] == want[f]).all(), (c, f)
 
 
-@pytest.mark.parametrize("thresh,period", [(1, 1), (1, 7), (8, 3), (40, 16), (40, 64)])
-def test_result_does_not_depend_on_the_schedule(emu, thresh, period):
-    """lane_search.cuh defers tree operations and batches them; when they run must not matter."""
-    try:
-        emu.emu_set_schedule(thresh, period)
-        s = O.kw_deal(3, 3, 4)
-        want = O.so_search(O.GAME_KW, s, 1200, seed=8)
-        got = emu_search(emu, O.GAME_KW, s, 1200, 8, 0, 0)
+@pytest.mark.parametrize("width,dump", [(2, 1), (7, 0), (32, 31), (32, 13)])
+def test_a_tree_does_not_depend_on_the_other_lanes_of_its_warp(emu, width, dump):
+    """The lock-step loop of lane_search.cuh makes the lanes of a warp wait for each other in every
+    phase; what a lane computes must be what it computes alone."""
+    s = O.kw_deal(3, 3, 4)
+    want = O.so_search(O.GAME_KW, s, 400, seed=8, pos=0, tree=dump)
+    got = emu_search(emu, O.GAME_KW, s, 400, 8, 0, 0, width=width, dump=dump)
+    assert len(got) == len(want)
+    for f in FIELDS:
+        assert (got[f] == want[f]).all(), f
+
+
+def test_a_warp_of_lanes_mid_game_and_seven_players(emu):
+    """Lanes whose rounds end at different times (different numbers of players still in)."""
+    s = O.kw_deal(11, 2, 7)
+    rnd = np.random.default_rng(4)
+    ctr = [0]
+    for _ in range(37):
+        legal = O.kw_legal(s)
+        if not legal:
+            break
+        O.kw_apply(s, int(rnd.choice(legal)), 11, 2, ctr)
+    assert O.kw_legal(s)
+    for dump in (0, 9):
+        want = O.so_search(O.GAME_KW, s, 300, seed=5, pos=0, tree=dump)
+        got = emu_search(emu, O.GAME_KW, s, 300, 5, 0, 0, width=12, dump=dump)
+        assert len(got) == len(want)
         for f in FIELDS:
             assert (got[f] == want[f]).all(), f
-        for it in range(60):
-            assert O.playout(O.GAME_KW, s, 5, 2, 0, it) == emu.emu_playout(O.GAME_KW, C.byref(s), 5, 2, it)
-    finally:
-        emu.emu_set_schedule(8, 8)
 
 
-def emu_any(E, game, root, solver, policy, iters, seed, player):
+def emu_any(E, game, root, solver, policy, iters, seed, player, width=1, dump=0):
     cap = 8 * (iters + 2)
     nodes = np.zeros(cap, dtype=O.NODE_DTYPE)
     n = C.c_uint32()
-    assert E.emu_search(game, C.byref(root), solver, policy, iters, seed, 0, 0, 0.7, player, nodes.ctypes.data, cap,
-                        C.byref(n)) == 0
+    assert E.emu_search(game, C.byref(root), solver, policy, iters, seed, 0, 0, width, dump, 0.7, player,
+                        nodes.ctypes.data, cap, C.byref(n)) == 0
     return nodes[:n.value]
 
 
@@ -170,17 +174,18 @@ def test_mnk_mo_every_node(emu, policy):
             assert (got[f] == want[f]).all(), (p, f)
 
 
-@pytest.mark.parametrize("mode,split", [(1, 0), (2, 6), (3, 10)])
-def test_result_does_not_depend_on_the_pass_plan(emu, mode, split):
-    try:
-        emu.emu_set_schedule_mode(mode, split)
-        s = O.kw_deal(3, 5, 4)
-        want = O.so_search(O.GAME_KW, s, 800, seed=8)
-        got = emu_search(emu, O.GAME_KW, s, 800, 8, 0, 0)
-        for f in FIELDS:
-            assert (got[f] == want[f]).all(), f
-    finally:
-        emu.emu_set_schedule_mode(6, 8)
+@pytest.mark.parametrize("solver,policy", [(O.SOLVER_MO, O.POLICY_UCB1), (O.SOLVER_SO, O.POLICY_EXP3), (O.SOLVER_MO, O.POLICY_EXP3)])
+def test_mo_and_exp3_in_a_warp(emu, solver, policy):
+    s = O.kw_deal(3, 5, 4)
+    fields = FIELDS if policy == O.POLICY_UCB1 else ("parent", "move", "player", "visits", "score", "prob")
+    if solver == O.SOLVER_MO:
+        want = O.mo_search(O.GAME_KW, s, 250, seed=6, pos=0, tree=3, policy=policy)[1]
+    else:
+        want = O.so_search(O.GAME_KW, s, 250, seed=6, pos=0, tree=3, policy=policy)
+    got = emu_any(emu, O.GAME_KW, s, solver, policy, 250, 6, 1, width=8, dump=3)
+    assert len(got) == len(want)
+    for f in fields:
+        assert (got[f] == want[f]).all(), f
 
 
 def emu_shared(E, game, root, iters, width, seed):
