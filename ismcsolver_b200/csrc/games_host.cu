@@ -46,7 +46,7 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     const uint32_t np = num_players < 2 ? 2 : num_players > 7 ? 7 : num_players;
     std::memset(out, 0, sizeof *out);
     out->num_players = (uint8_t)np;
-    uint64_t hands[ISMCTS_KW_MAX_PLAYERS] = {0};
+    uint64_t hands[KwGame::kHandWords] = {0};
     KwGame g;
     g.bind(hands, 1);
     ismcts_kw_state blank;
@@ -59,13 +59,10 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     rng.init(seed, stream, kDealTree, ring, 1);
     rng.begin_iteration(kDealIteration);
     g.start_deal();
-    while (g.chance_pending()) {
-        const KwGame::Mask c = g.chance_set();
-        g.step(c.kth(rng.below(c.count())));
-        if (rng.low()) rng.refill();
-    }
+    while (g.chance_pending()) g.chance_draw(rng.below(g.chance_count()));
     // one of the remaining cards is turned up for trumps and leaves the unknown set (:50-53)
-    uint64_t unknown = g.pool;
+    uint64_t unknown = g.pile_set();
+    rng.align();
     const uint32_t up = kth_bit64(unknown, rng.below(popc64(unknown)));
     unknown &= ~((uint64_t)1 << up);
     g.trump = up / 13u;
@@ -76,7 +73,7 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
 uint64_t ismcts_kw_legal(const ismcts_kw_state* s)
 {
     if (!s) return 0;
-    uint64_t hands[ISMCTS_KW_MAX_PLAYERS];
+    uint64_t hands[KwGame::kHandWords];
     KwGame g;
     g.bind(hands, 1);
     g.load(s);
@@ -87,7 +84,7 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
 {
     if (!s) return ISMCTS_ERR_INVALID;
     if (move >= ISMCTS_KW_CARDS) return ISMCTS_ERR_ILLEGAL_MOVE;
-    uint64_t hands[ISMCTS_KW_MAX_PLAYERS];
+    uint64_t hands[KwGame::kHandWords];
     KwGame g;
     g.bind(hands, 1);
     g.load(s);
@@ -102,14 +99,13 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
     rng.begin_iteration(0, draw_counter ? *draw_counter : 0);
     g.step(move);
     uint64_t unknown = s->unknown;
-    bool dealt = false;
-    while (g.chance_pending()) {
-        const KwGame::Mask c = g.chance_set();
-        g.step(c.kth(rng.below(c.count())));
-        if (rng.low()) rng.refill();
-        dealt = true;
+    if (g.chance_pending()) {
+        // the chance events of a round end (tie-break, deal) start a Philox block, and so does what follows
+        rng.align();
+        while (g.chance_pending()) g.chance_draw(rng.below(g.chance_count()));
+        rng.align();
+        unknown = g.pile_set(); // deal, :138-152: the undealt rest of the deck is unknown to everyone
     }
-    if (dealt) unknown = g.pool; // deal, :138-152: the undealt rest of the deck is unknown to everyone
     if (draw_counter) *draw_counter = rng.consumed();
     // the cards of the trick in progress (m_currentTrick)
     if (play) {

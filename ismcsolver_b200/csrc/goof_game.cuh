@@ -80,6 +80,10 @@ struct GoofGame {
         return Mask{(uint64_t)prizes};
     }
 
+    // a pending chance event is one uniform draw: the j-th member of chance_set()
+    ISMCTS_DEV uint32_t chance_count() const { return chance_set().count(); }
+    ISMCTS_DEV void chance_draw(uint32_t j) { chance_step(chance_set().kth(j)); }
+
     ISMCTS_DEV void chance_step(uint32_t b)
     {
         if (hidden_bid) { move0 = b; hidden_bid = 0; return; }

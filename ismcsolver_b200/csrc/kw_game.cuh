@@ -9,16 +9,21 @@
 // round-end bookkeeping (knock-outs, most tricks, ties, deal sizes) is a
 // handful of word-parallel operations instead of loops over the players.
 //
-// Every random event of the reference — the determinisation shuffle
-// (cloneAndRandomise, knockoutwhist.cpp:56-76), the re-deal shuffle (deal,
-// :138-152), the round-winner tie-break (roundWinner, :198-210) and the
-// uniformly random move of the default policy (utility.h:69-83) — is expressed
-// as ONE kind of micro-step: "remove a uniformly random member from a bit set".
-// A micro-step draws exactly one Philox word.  Chance events that the reference
-// resolves inside doMove become pending micro-steps (mode != kPlay) which are
-// drained before the next decision, in the order the reference draws them
-// (tie-break, then the deal player by player in ascending id).  That is what lets
-// the 32 lanes of a warp, each in its own game and phase, run one loop body.
+// The chance events the reference resolves inside its functions — the
+// determinisation shuffle (cloneAndRandomise, knockoutwhist.cpp:56-76), the
+// re-deal shuffle (deal, :138-152) and the round-winner tie-break (roundWinner,
+// :198-210) — become pending steps (mode != kPlay) that are drained before the
+// next decision, in the order the reference draws (tie-break, then the deal
+// player by player in ascending id), one uniform draw each.  Cards are dealt from
+// a PILE, a byte array in shared memory that starts in ascending card order: a
+// uniformly random card leaves it and the last card of the pile takes its place
+// (the steps of a Fisher-Yates shuffle of which only the dealt cards are kept; a
+// shuffle followed by "take the first k" has the same distribution).  The stream
+// is aligned to a Philox block before and after every sequence of chance events
+// and at the start of the rollout (philox.cuh), so that the lanes of a warp, which
+// go through the phases of an iteration together (lane_search.cuh), generate their
+// blocks in the same steps: chance_phase() and play_phase() below keep the current
+// block in registers.
 #pragma once
 
 #include "devdefs.cuh"
@@ -32,20 +37,22 @@ namespace ismcts {
 // player to move) already set up as a pending deal.  Built once per position.
 struct alignas(16) KwPrepared {
     uint64_t hand_obs;   // the observer's own hand (the only one it can see)
-    uint64_t unseen;     // unknown cards + the other players' hands: the pool to deal back
     uint32_t sizes;      // 4 bits per player: cards to deal back (0 for the observer)
     uint32_t observer;
     uint32_t player, dealer, trump, tricks_left, request_trump;
     uint32_t alive4, tricks, best;
     uint32_t trick_len, lead_suit, win_key, win_player;
-    uint32_t pad[2];
+    uint32_t pile_n;     // unknown cards + the other players' hands: the pile to deal back from
+    uint32_t pad;
+    uint64_t pile[7];    // its cards, one per byte, ascending
 };
-static_assert(sizeof(KwPrepared) == 80, "five 16-byte loads");
+static_assert(sizeof(KwPrepared) == 128, "eight 16-byte loads");
 
 struct KwGame {
     static constexpr uint32_t kGameId = ISMCTS_GAME_KW;
     static constexpr uint32_t kMoveStride = 64;
-    static constexpr uint32_t kHandWords = ISMCTS_KW_MAX_PLAYERS; // 8-byte words of per-thread scratch
+    static constexpr uint32_t kPileWords = 7;                       // 52 cards, one per byte
+    static constexpr uint32_t kHandWords = ISMCTS_KW_MAX_PLAYERS + kPileWords; // 8-byte words of per-thread scratch
     static constexpr uint32_t kMaxPlayers = ISMCTS_KW_MAX_PLAYERS;
     static constexpr uint32_t kMaxLegal = ISMCTS_KW_CARDS;
     static constexpr uint32_t kMaxDepth = 208;  // plies are bounded by 6 + players * 28 (gametest.cpp:166-178)
@@ -60,7 +67,7 @@ struct KwGame {
     static constexpr uint64_t kSuit = 0x1FFF;
     static constexpr uint32_t kOnes = 0x1111111u; // bit 4p for each of the 7 players
 
-    // per-thread hands: hand of player p is hands[p * stride]
+    // per-thread scratch: the hand of player p is hands[p * stride], the pile follows the hands
     uint64_t* hands;
     uint32_t stride;
 
@@ -73,12 +80,27 @@ struct KwGame {
     uint32_t win_key;    // strength of the card currently winning it (card_key)
     uint32_t win_player; // who played that card
     uint32_t mode;       // pending chance event, if any
-    uint64_t pool;       // kDeal: cards not dealt yet; kTie: tied players (bit 4p)
+    uint32_t tied;       // kTie: the players tied on most tricks (bit 4p)
+    uint32_t pile_n;     // kDeal: cards left in the pile
     uint32_t deal_player, deal_left; // kDeal: who is being dealt to and how many more cards
     uint32_t need;       // kDeal: 4 bits per player, cards the players after deal_player still get
 
     ISMCTS_DEV uint64_t hand(uint32_t p) const { return hands[p * stride]; }
     ISMCTS_DEV void set_hand(uint32_t p, uint64_t v) { hands[p * stride] = v; }
+
+    // card i of the pile: byte i % 8 of word i / 8
+    ISMCTS_DEV uint8_t* pile_at(uint32_t i) const
+    {
+        return reinterpret_cast<uint8_t*>(hands + (ISMCTS_KW_MAX_PLAYERS + (i >> 3)) * stride) + (i & 7u);
+    }
+    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) { hands[(ISMCTS_KW_MAX_PLAYERS + i) * stride] = v; }
+    // the cards left in the pile as a set (after a deal: the cards nobody holds)
+    ISMCTS_DEV uint64_t pile_set() const
+    {
+        uint64_t out = 0;
+        for (uint32_t i = 0; i < pile_n; ++i) out |= (uint64_t)1 << *pile_at(i);
+        return out;
+    }
 
     ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; mode = kPlay; }
 
@@ -123,7 +145,7 @@ struct KwGame {
         trick_len = r->trick_len;
         lead_suit = 0; win_key = 0; win_player = 0;
         for (uint32_t i = 0; i < trick_len; ++i) fold_trick(i, r->trick_player[i], r->trick_card[i]);
-        mode = kPlay; pool = 0; deal_player = 0; deal_left = 0; need = 0;
+        mode = kPlay; tied = 0; pile_n = 0; deal_player = 0; deal_left = 0; need = 0;
     }
 
     ISMCTS_DEV void fold_trick(uint32_t index, uint32_t who, uint32_t card)
@@ -145,31 +167,39 @@ struct KwGame {
         // cloneAndRandomise, knockoutwhist.cpp:56-76: what the observer cannot see (the unknown
         // cards and the other players' hands) is pooled and dealt back to the other players,
         // ascending id, keeping their hand sizes
-        p.unseen = r->unknown; p.sizes = 0;
+        uint64_t unseen = r->unknown;
+        p.sizes = 0;
         for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q) {
             if (!((g.alive4 >> (4 * q)) & 1u) || q == g.player) continue;
-            p.unseen |= g.hand(q);
+            unseen |= g.hand(q);
             p.sizes |= popc64(g.hand(q)) << (4 * q);
         }
+        for (uint32_t i = 0; i < kPileWords; ++i) p.pile[i] = 0;
+        p.pile_n = 0;
+        for (unseen &= kFullDeck; unseen; unseen &= unseen - 1) {
+            p.pile[p.pile_n >> 3] |= (uint64_t)ctz64(unseen) << (8 * (p.pile_n & 7u));
+            ++p.pile_n;
+        }
+        p.pad = 0;
         if (!g.legal().any()) g.tricks_left = 0;      // a finished game, however it is recorded
         p.player = g.player; p.dealer = g.dealer; p.trump = g.trump; p.tricks_left = g.tricks_left;
         p.request_trump = g.request_trump; p.alive4 = g.alive4; p.tricks = g.tricks; p.best = g.best;
         p.trick_len = g.trick_len; p.lead_suit = g.lead_suit; p.win_key = g.win_key; p.win_player = g.win_player;
-        p.pad[0] = p.pad[1] = 0;
         *out = p;
     }
 
     // Clone of the root with the determinisation pending (sosolver.h:46).
     ISMCTS_DEV void start(const Prepared* q)
     {
-        const Prepared p = *q;
         for (uint32_t i = 0; i < ISMCTS_KW_MAX_PLAYERS; ++i) set_hand(i, 0);
-        set_hand(p.observer, p.hand_obs);
-        player = p.player; dealer = p.dealer; trump = p.trump; tricks_left = p.tricks_left;
-        request_trump = p.request_trump; alive4 = p.alive4; tricks = p.tricks; best = p.best;
-        trick_len = p.trick_len; lead_suit = p.lead_suit; win_key = p.win_key; win_player = p.win_player;
-        mode = kPlay;
-        begin_deal(p.unseen, p.sizes);
+        for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, q->pile[i]);
+        set_hand(q->observer, q->hand_obs);
+        player = q->player; dealer = q->dealer; trump = q->trump; tricks_left = q->tricks_left;
+        request_trump = q->request_trump; alive4 = q->alive4; tricks = q->tricks; best = q->best;
+        trick_len = q->trick_len; lead_suit = q->lead_suit; win_key = q->win_key; win_player = q->win_player;
+        mode = kPlay; tied = 0;
+        pile_n = q->pile_n;
+        begin_deal(q->sizes);
     }
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
@@ -201,19 +231,15 @@ struct KwGame {
         return Mask{follow ? follow : h};
     }
 
-    // The set a pending chance micro-step draws from.
-    ISMCTS_DEV Mask chance_set() const { return Mask{pool}; }
-
     // getResult * 2, knockoutwhist.cpp:117-120: the first remaining player has won.
     ISMCTS_DEV uint32_t result2(uint32_t who) const { return 4u * who == ctz32(alive4) ? 2u : 0u; }
     ISMCTS_DEV uint32_t outcome() const { return ctz32(alive4) >> 2; }
 
-    // Starts dealing from `from`: `sizes` holds 4 bits per player, the number of
-    // cards each gets, ascending id.
-    ISMCTS_DEV void begin_deal(uint64_t from, uint32_t sizes)
+    // Starts dealing from the pile: `sizes` holds 4 bits per player, the number of cards each
+    // gets, ascending id.
+    ISMCTS_DEV void begin_deal(uint32_t sizes)
     {
         if (sizes == 0) { mode = kPlay; return; }
-        pool = from;
         const uint32_t shift = ctz32(sizes) & ~3u;
         deal_player = shift >> 2;
         deal_left = (sizes >> shift) & 15u;
@@ -222,7 +248,12 @@ struct KwGame {
     }
 
     // deal, knockoutwhist.cpp:138-152: a fresh deck, tricks_left cards to each remaining player.
-    ISMCTS_DEV void start_deal() { begin_deal(kFullDeck, alive4 * tricks_left); }
+    ISMCTS_DEV void start_deal()
+    {
+        for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, 0x0706050403020100ull + i * 0x0808080808080808ull);
+        pile_n = ISMCTS_KW_CARDS;
+        begin_deal(alive4 * tricks_left);
+    }
 
     // finishRound, knockoutwhist.cpp:163-180
     ISMCTS_DEV void finish_round()
@@ -232,7 +263,7 @@ struct KwGame {
             --tricks_left;
             request_trump = 1;
             // roundWinner, :198-210: uniform among the players with most tricks
-            pool = alive4 & ~nonzero4(tricks ^ (best * kOnes));
+            tied = alive4 & ~nonzero4(tricks ^ (best * kOnes));
             mode = kTie;
         } else {
             tricks_left = 0; // over: nobody holds cards, validMoves() is empty
@@ -244,30 +275,50 @@ struct KwGame {
     // (prepare() normalises root records that are finished in some other way).
     ISMCTS_DEV bool terminal() const { return tricks_left == 0; }
 
-    // A pending chance event: `b` is the drawn member of chance_set().
-    ISMCTS_DEV void chance_step(uint32_t b)
+    // A pending chance event is one uniform draw below chance_count().
+    ISMCTS_DEV uint32_t chance_count() const { return mode == kDeal ? pile_n : popc32(tied); }
+
+    // The last card of the pile takes the place of card `j`, which is dealt.
+    ISMCTS_DEV uint32_t take_from_pile(uint32_t j)
     {
-        if (mode == kDeal) {
-            const uint64_t bit = (uint64_t)1 << b;
-            pool &= ~bit;
-            set_hand(deal_player, hand(deal_player) | bit);
-            if (--deal_left == 0) {
-                if (need) {
-                    const uint32_t shift = ctz32(need) & ~3u;
-                    deal_player = shift >> 2;
-                    deal_left = (need >> shift) & 15u;
-                    need &= ~(15u << shift);
-                } else {
-                    mode = kPlay;
-                }
-            }
-            return;
+        uint8_t* at = pile_at(j);
+        const uint32_t card = *at;
+        *at = *pile_at(--pile_n);
+        return card;
+    }
+
+    // After the last card of a hand: the next player to deal to, or the end of the deal.
+    ISMCTS_DEV void next_hand()
+    {
+        if (need) {
+            const uint32_t shift = ctz32(need) & ~3u;
+            deal_player = shift >> 2;
+            deal_left = (need >> shift) & 15u;
+            need &= ~(15u << shift);
+        } else {
+            mode = kPlay;
         }
-        // kTie: the round winner calls trumps (roundWinner, knockoutwhist.cpp:198-210)
-        player = b >> 2;
+    }
+
+    // The tie-break: the j-th of the tied players has won the round and calls trumps
+    // (roundWinner, knockoutwhist.cpp:198-210), then the cards are dealt.
+    ISMCTS_DEV void break_tie(uint32_t j)
+    {
+        player = kth_bit32(tied, j) >> 2;
         dealer = next_alive(dealer);
         tricks = 0; best = 0;
         start_deal();
+    }
+
+    // The pending chance event with draw `j` (uniform below chance_count()).
+    ISMCTS_DEV void chance_draw(uint32_t j)
+    {
+        if (mode == kDeal) {
+            set_hand(deal_player, hand(deal_player) | (uint64_t)1 << take_from_pile(j));
+            if (--deal_left == 0) next_hand();
+        } else {
+            break_tie(j);
+        }
     }
 
     // doMove, knockoutwhist.cpp:95-115 (no chance event pending).
@@ -293,51 +344,60 @@ struct KwGame {
         if (hand(player) == 0) finish_round();
     }
 
-    // One micro-step of either kind.
-    ISMCTS_DEV void step(uint32_t b)
-    {
-        if (mode != kPlay) chance_step(b); else play(b);
-    }
+    // A move of the tree or of a caller (no chance event pending).
+    ISMCTS_DEV void step(uint32_t b) { play(b); }
 
-    // ---- phases of the lock-step loop (lane_search.cuh, run_lockstep): the same transitions as
-    // chance_step() and play(), drawn in the same order from the same stream, as tight loops over
-    // ONE kind of step with the state of that kind in registers.
+    // ---- phases of the lock-step loop (lane_search.cuh): the same transitions as chance_draw() and
+    // play() with the same draws, as tight loops over ONE kind of step.  Every lane that takes
+    // part makes one draw per step from an aligned stream, so draw s of the phase is half s % 2 of
+    // word (s / 2) % 4 of block s / 8 for all of them: the block is generated in registers by all
+    // lanes in the same steps and no ring is involved.
     static constexpr bool kPhased = true;
 
-    // Every pending chance event of the warp: the tie-breaks (at most one per lane, they start
-    // a deal), then the deals card by card.  The hand being dealt is collected in registers
-    // and stored when it is complete.  `active`: the lane takes part (it may still have nothing
-    // pending).
+    // The four words of a block, handed out in order.
+    struct BlockWords {
+        uint32_t b[4];
+        ISMCTS_DEV uint32_t next()
+        {
+            const uint32_t x = b[0];
+            b[0] = b[1]; b[1] = b[2]; b[2] = b[3];
+            return x;
+        }
+    };
+
+    // Every pending chance event of the warp: the tie-break (it starts a deal), then the deal
+    // card by card.  The hand being dealt is collected in registers and stored when it is
+    // complete.  `active`: the lane takes part in the search (it may have nothing pending).
     template <class Rng>
     ISMCTS_DEV void chance_phase(Rng& rng, bool active)
     {
-        if (warp_any(active && mode == kTie)) {
-            if (active && mode == kTie) chance_step(kth_bit32((uint32_t)pool, rng.below(popc32((uint32_t)pool))));
-        }
-        uint64_t from = pool, hand_acc = 0;
-        uint32_t left = popc64(from);
-        for (uint32_t s = 0; warp_any(active && mode == kDeal); ++s) {
-            if ((s & 3u) == 0u && active && rng.low()) rng.refill();
-            if (active && mode == kDeal) {
-                const uint64_t bit = (uint64_t)1 << kth_bit64(from, rng.below_waiting(left));
-                --left;
-                from &= ~bit;
-                hand_acc |= bit;
-                if (--deal_left == 0) {
-                    set_hand(deal_player, hand(deal_player) | hand_acc);
-                    hand_acc = 0;
-                    if (need) {
-                        const uint32_t shift = ctz32(need) & ~3u;
-                        deal_player = shift >> 2;
-                        deal_left = (need >> shift) & 15u;
-                        need &= ~(15u << shift);
-                    } else {
-                        mode = kPlay;
-                        pool = from;
+        const bool mine = active && mode != kPlay;
+        if (!warp_any(mine)) return;
+        const uint32_t first_block = mine ? rng.phase_begin() : 0u;
+        BlockWords words;
+        uint32_t w = 0, draws = 0;
+        uint64_t hand_acc = 0;
+        for (uint32_t s = 0; warp_any(active && mode != kPlay); ++s) {
+            if ((s & 7u) == 0u) rng.block(first_block + (s >> 3), words.b);
+            if ((s & 1u) == 0u) w = words.next();
+            if (active && mode != kPlay) {
+                const uint64_t product = (uint64_t)w * chance_count();
+                const uint32_t j = (uint32_t)(product >> 32);
+                w = (uint32_t)product;
+                ++draws;
+                if (mode == kDeal) {
+                    hand_acc |= (uint64_t)1 << take_from_pile(j);
+                    if (--deal_left == 0) {
+                        set_hand(deal_player, hand(deal_player) | hand_acc);
+                        hand_acc = 0;
+                        next_hand();
                     }
+                } else {
+                    break_tie(j);
                 }
             }
         }
+        if (mine) { rng.phase_end(first_block, draws); rng.align(); }
     }
 
     // Rollout moves (simulate, solverbase.h:36-43) for the lanes with `rolling` until their
@@ -345,21 +405,34 @@ struct KwGame {
     template <class Rng>
     ISMCTS_DEV void play_phase(Rng& rng, bool rolling, uint32_t& plies)
     {
-        // the round winner calls trumps: one of the four suits
-        if (warp_any(rolling && mode == kPlay && tricks_left != 0 && request_trump)) {
-            if (rolling && mode == kPlay && tricks_left != 0 && request_trump) { ++plies; play(13u * rng.below(4)); }
-        }
+        const bool mine = rolling && mode == kPlay && tricks_left != 0;
+        if (!warp_any(mine)) return;
+        const uint32_t first_block = mine ? rng.phase_begin() : 0u;   // the rollout and every round start a block
+        BlockWords words;
+        uint32_t w = 0, draws = 0;
         // the hand of the player to move (lanes that do not take part may hold no game at all)
-        uint64_t h = rolling && mode == kPlay && tricks_left != 0 ? hand(player) : 0;
+        uint64_t h = mine && !request_trump ? hand(player) : 0;
         for (uint32_t s = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++s) {
-            if ((s & 3u) == 0u && rolling && rng.low()) rng.refill();
+            if ((s & 7u) == 0u) rng.block(first_block + (s >> 3), words.b);
+            if ((s & 1u) == 0u) w = words.next();
             if (rolling && mode == kPlay && tricks_left != 0) {
+                ++plies;
+                ++draws;
+                if (request_trump) {
+                    // the round winner calls trumps: one of the four suits
+                    const uint64_t product = (uint64_t)w * 4u;
+                    w = (uint32_t)product;
+                    play(13u * (uint32_t)(product >> 32));
+                    h = hand(player);
+                    continue;
+                }
                 // validMoves, knockoutwhist.cpp:122-136: follow suit if possible (with one card
                 // in hand both cases give the same set)
                 const uint64_t follow = h & (kSuit << (13u * lead_suit));
                 const uint64_t set = trick_len != 0 && follow != 0 ? follow : h;
-                const uint32_t b = kth_bit64(set, rng.below_waiting(popc64(set)));
-                ++plies;
+                const uint64_t product = (uint64_t)w * popc64(set);
+                w = (uint32_t)product;
+                const uint32_t b = kth_bit64(set, (uint32_t)(product >> 32));
                 // doMove, :95-115
                 set_hand(player, h & ~((uint64_t)1 << b));
                 fold_trick(trick_len, player, b);
@@ -376,6 +449,7 @@ struct KwGame {
                 if (h == 0) finish_round();
             }
         }
+        if (mine) rng.phase_end(first_block, draws);
     }
 };
 

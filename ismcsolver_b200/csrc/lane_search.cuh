@@ -358,10 +358,7 @@ struct Lane {
             } else if (warp_any(wants_chance())) {
                 do {
                     tick_rng(tick);
-                    if (wants_chance()) {
-                        const Mask set = g.chance_set();
-                        g.chance_step(set.kth(rng.below(set.count())));
-                    }
+                    if (wants_chance()) g.chance_draw(rng.below(g.chance_count()));
                 } while (warp_any(wants_chance()));
             }
             if (kTree && warp_any(wants_descent())) {

@@ -46,6 +46,8 @@ struct MnkGame {
     ISMCTS_DEV void start(const Prepared* p) { load(p); }
     ISMCTS_DEV Mask chance_set() const { return Mask::none(); }
     ISMCTS_DEV void chance_step(uint32_t) {}
+    ISMCTS_DEV uint32_t chance_count() const { return 0; }
+    ISMCTS_DEV void chance_draw(uint32_t) {}
     ISMCTS_DEV bool terminal() const { return res2 != -1; }     // validMoves() is empty, mnkgame.cpp:61-64
     ISMCTS_DEV void play(uint32_t cell) { step(cell); }
 

@@ -108,6 +108,10 @@ struct PhantomGame : MnkGame {
     ISMCTS_DEV bool chance_pending() const { return replay_left != 0; }
     ISMCTS_DEV Mask chance_set() const { return Mask{{pool_word(0), pool_word(1), pool_word(2), pool_word(3)}}; }
 
+    // a pending chance event is one uniform draw: the j-th member of chance_set()
+    ISMCTS_DEV uint32_t chance_count() const { return chance_set().count(); }
+    ISMCTS_DEV void chance_draw(uint32_t j) { chance_step(chance_set().kth(j)); }
+
     // randomReplay, phantommnkgame.cpp:57-81: one hidden stone of the opponent.
     ISMCTS_DEV void chance_step(uint32_t cell)
     {

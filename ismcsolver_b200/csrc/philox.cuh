@@ -6,9 +6,14 @@
 //                 key = seed)[d % 4],
 // (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11), so any
 // random choice can be recomputed from its coordinates alone and the result of a
-// search does not depend on how trees map to threads, warps or GPUs.  Every
-// random choice of the engine is "uniform integer below n" = high word of
-// word * n, and consumes exactly one word.
+// search does not depend on how trees map to threads, warps or GPUs.  A random
+// choice is "uniform integer below n" = the high half of word * n; the low half
+// is the word of the next choice, so a word serves TWO consecutive choices (the
+// pair deviates from uniform by less than n1 * n2 / 2^32 < 1e-6).  align() moves
+// on to the next block of four words: Knockout Whist aligns around every sequence
+// of chance events and at the start of the rollout, which makes the lanes of a
+// warp generate their blocks in the same steps (kw_game.cuh).  The oracle
+// (oracle/oracle.c: rng_below, rng_align) states the same protocol sequentially.
 #pragma once
 
 #include "devdefs.cuh"
@@ -32,69 +37,94 @@ ISMCTS_DEV void philox4x32_10(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3
     out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
 }
 
-// The stream of one lane.  Generated words wait in a small ring in shared memory
-// (one 4-byte column per thread, 8 rows; word d of the iteration sits in row
-// d % 8): the search loop refills all lanes of a warp in the same steps, so the
-// ten Philox rounds are executed with all lanes active although the lanes
-// consume their words at different rates.
+// The stream of one lane.  Words generated ahead wait in a small ring in shared memory (one
+// 4-byte column per thread, 8 rows; word d of the iteration sits in row d % 8).  The phase
+// loops of Knockout Whist do not use the ring: they keep the current block in registers
+// (phase_begin / block / phase_end).
 struct LaneRng {
     static constexpr uint32_t kRingWords = 8;
+    static constexpr uint32_t kDrawsPerWord = 2;
     uint32_t k0, k1;      // key = seed
     uint32_t c1, c2, c3;  // iteration, tree, position
-    uint32_t next_block;  // next block (d / 4) to generate
+    uint32_t next_block;  // next block (d / 4) to generate into the ring
     uint32_t d;           // next word to hand out; words [d, 4 * next_block) wait in the ring
+    uint32_t w, left;     // the word being used up and the draws it still serves
     uint32_t* ring;       // ring[(d % 8) * stride]
     uint32_t stride;
 
     ISMCTS_DEV void init(uint64_t seed, uint32_t pos, uint32_t tree, uint32_t* ring_base, uint32_t ring_stride)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        c1 = 0; c2 = tree; c3 = pos; next_block = 0; d = 0;
+        c1 = 0; c2 = tree; c3 = pos; next_block = 0; d = 0; w = 0; left = 0;
         ring = ring_base; stride = ring_stride;
     }
+
+    // Block `index` of the current iteration.
+    ISMCTS_DEV void block(uint32_t index, uint32_t out[4]) const { philox4x32_10(index, c1, c2, c3, k0, k1, out); }
 
     // Generates the next block of four words into its half of the ring.
     ISMCTS_DEV void refill()
     {
-        uint32_t w[4];
-        philox4x32_10(next_block, c1, c2, c3, k0, k1, w);
+        uint32_t b[4];
+        block(next_block, b);
         uint32_t* half = ring + (next_block & 1u) * 4u * stride;
         ++next_block;
 #pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) half[i * stride] = w[i];
+        for (uint32_t i = 0; i < 4; ++i) half[i * stride] = b[i];
     }
 
-    // Starts the stream of `iteration` at word 0 (or at word `at` for the host helpers).
+    // Starts the stream of `iteration` at word 0 (or at word `at` for the host helpers); nothing
+    // is generated until a word is asked for.
     ISMCTS_DEV void begin_iteration(uint32_t iteration, uint32_t at = 0)
     {
-        c1 = iteration; next_block = at >> 2; d = at;
-        refill();
+        c1 = iteration; d = at; left = 0;
+        next_block = at >> 2;
+        if (at & 3u) refill();
     }
 
     ISMCTS_DEV uint32_t waiting() const { return 4u * next_block - d; }
     ISMCTS_DEV bool low() const { return waiting() <= 4u; }   // room for one more block
-    ISMCTS_DEV uint32_t consumed() const { return d; }         // words handed out
+    ISMCTS_DEV uint32_t consumed() const { return d; }         // words handed out (or skipped by align)
 
-    // Next word when one is known to wait: the loops refill every lane that is low() at least
-    // every fourth step and draw at most one word per step.
-    ISMCTS_DEV uint32_t word_waiting()
-    {
-        const uint32_t w = ring[(d & (kRingWords - 1)) * stride];
-        ++d;
-        return w;
-    }
-
-    // Next 32-bit word of the stream; generates the block it needs when nothing waits (a lane
-    // that draws several words in one step: an EXP3 descent draws one per level).
+    // The next whole word (EXP3 samples with all 32 bits); drops what is left of the current one.
     ISMCTS_DEV uint32_t word()
     {
+        left = 0;
         if (waiting() == 0) refill();
-        return word_waiting();
+        const uint32_t x = ring[(d & (kRingWords - 1)) * stride];
+        ++d;
+        return x;
     }
 
-    // Uniform integer in [0, n) — always consumes exactly one word.
-    ISMCTS_DEV uint32_t below(uint32_t n) { return mulhi32(word(), n); }
-    ISMCTS_DEV uint32_t below_waiting(uint32_t n) { return mulhi32(word_waiting(), n); }
+    // Uniform integer in [0, n).
+    ISMCTS_DEV uint32_t below(uint32_t n)
+    {
+        if (left == 0) { w = word(); left = kDrawsPerWord; }
+        const uint64_t p = (uint64_t)w * n;
+        w = (uint32_t)p;
+        --left;
+        return (uint32_t)(p >> 32);
+    }
+
+    // On to the start of the next block (a no-op at the start of a block with nothing used).
+    ISMCTS_DEV void align()
+    {
+        left = 0;
+        d = (d + 3u) & ~3u;
+    }
+
+    // A phase that generates its blocks in registers: aligns and returns the index of its first
+    // block; `draws` draws later (two per word, four words per block) phase_end() moves the
+    // stream past the words they used.  The ring is empty afterwards and the words up to the
+    // next block boundary are NOT in it: the next use of the stream must be an align() — which is
+    // what follows every phase of Knockout Whist — or the end of the iteration.
+    ISMCTS_DEV uint32_t phase_begin() { align(); return d >> 2; }
+    ISMCTS_DEV void phase_end(uint32_t first_block, uint32_t draws)
+    {
+        d = 4u * first_block + ((draws + 1u) >> 1);
+        next_block = (d + 3u) >> 2;
+        left = 0;
+    }
 };
 
 } // namespace ismcts

@@ -46,21 +46,48 @@ uint32_t orc_draw_word(uint64_t seed, uint32_t pos, uint32_t tree, uint32_t iter
     return out[d & 3];
 }
 
-/* A random stream position: every random choice of one iteration is word d,
- * d = 0, 1, 2, ... of the stream (seed; pos, tree, iteration). */
+/* A random stream position.  The words of one iteration are d = 0, 1, 2, ... of the stream
+ * (seed; pos, tree, iteration).  A word serves TWO consecutive draws: "uniform integer below
+ * n" is the high half of word * n and the low half is the word of the second draw (the
+ * deviation from uniform of the pair is below n1 * n2 / 2^32 < 1e-6).  rng_align() moves on to
+ * the start of the next Philox block of four words: Knockout Whist aligns the stream around
+ * every sequence of chance events and at the start of the rollout, so that all playouts of a
+ * position consume their words in the same rhythm (on the GPU: the lanes of a warp generate
+ * their blocks in the same steps). */
 typedef struct rng {
     uint64_t seed;
     uint32_t pos, tree, iteration, d;
     orc_counters* cnt;
+    uint32_t w, left;      /* the word being used up and the draws it still serves */
 } rng;
 
-/* Uniform integer in [0, n): the high word of word * n.  Always consumes one word. */
+enum { RNG_DRAWS_PER_WORD = 2 };
+
+/* The next whole word (EXP3 samples with all 32 bits); drops what is left of the current one. */
+static uint32_t rng_word(rng* r)
+{
+    r->left = 0;
+    if (r->cnt) r->cnt->draws++;
+    return orc_draw_word(r->seed, r->pos, r->tree, r->iteration, r->d++);
+}
+
+/* Uniform integer in [0, n). */
 static uint32_t rng_below(rng* r, uint32_t n)
 {
-    const uint32_t w = orc_draw_word(r->seed, r->pos, r->tree, r->iteration, r->d++);
-    if (r->cnt) r->cnt->draws++;
-    return (uint32_t)(((uint64_t)w * n) >> 32);
+    if (r->left == 0) { r->w = rng_word(r); r->left = RNG_DRAWS_PER_WORD; }
+    const uint64_t p = (uint64_t)r->w * n;
+    r->w = (uint32_t)p;
+    r->left--;
+    return (uint32_t)(p >> 32);
 }
+
+static void rng_align(rng* r)
+{
+    r->left = 0;
+    r->d = (r->d + 3u) & ~3u;
+}
+
+static void rng_restart(rng* r) { r->d = 0; r->left = 0; }
 
 /* ========================================================== Knockout Whist */
 
@@ -138,19 +165,42 @@ static int okw_alive_count(const okw* g)
     return k;
 }
 
-/* deal, knockoutwhist.cpp:138-152.  The reference shuffles all 52 cards and
- * hands tricks_left to each remaining player in order; drawing the same cards
- * one by one without replacement gives the same distribution. */
+/* A pile of cards to deal from: a uniformly random card leaves it by taking the place of...
+ * rather, by the LAST card of the pile taking its place (one step of a Fisher-Yates shuffle
+ * that only keeps the dealt prefix).  The pile starts in ascending card order. */
+typedef struct okw_pile { unsigned char card[52]; int n; } okw_pile;
+
+static void pile_from_set(okw_pile* d, const unsigned char* set)
+{
+    d->n = 0;
+    for (int c = 0; c < 52; ++c) if (set[c]) d->card[d->n++] = (unsigned char)c;
+}
+
+static int pile_draw(okw_pile* d, rng* r)
+{
+    const int j = (int)rng_below(r, (uint32_t)d->n);
+    if (r->cnt) r->cnt->chance_picks++;
+    const int c = d->card[j];
+    d->card[j] = d->card[--d->n];
+    return c;
+}
+
+/* deal, knockoutwhist.cpp:138-152.  The reference shuffles all 52 cards and hands tricks_left
+ * to each remaining player in order; drawing the same cards one by one without replacement
+ * gives the same distribution. */
 static void okw_deal(okw* g, rng* r)
 {
-    unsigned char deck[52];
-    memset(deck, 1, sizeof deck);
+    unsigned char all[52];
+    memset(all, 1, sizeof all);
+    okw_pile pile;
+    pile_from_set(&pile, all);
     for (int p = 0; p < g->np; ++p) {
         if (!g->alive[p]) continue;
         for (int j = 0; j < g->tricks_left; ++j)
-            g->hand[p][set_draw(deck, 52, r)] = 1;
+            g->hand[p][pile_draw(&pile, r)] = 1;
     }
-    memcpy(g->unknown, deck, sizeof deck);
+    memset(g->unknown, 0, sizeof g->unknown);
+    for (int i = 0; i < pile.n; ++i) g->unknown[pile.card[i]] = 1;
 }
 
 /* KnockoutWhist::KnockoutWhist, knockoutwhist.cpp:36-54. */
@@ -163,6 +213,7 @@ static void okw_new(okw* g, int players, rng* r)
     for (int p = 0; p < g->np; ++p) g->alive[p] = 1;
     okw_deal(g, r);
     /* one of the remaining cards is turned up for trumps and leaves the unknown set (:50-53) */
+    rng_align(r);
     g->trump = set_draw(g->unknown, 52, r) / 13;
 }
 
@@ -209,10 +260,12 @@ static void okw_finish_round(okw* g, rng* r)
         for (int p = 0; p < g->np; ++p) if (g->alive[p] && g->tricks[p] > best) best = g->tricks[p];
         unsigned char tied[7] = {0};
         for (int p = 0; p < g->np; ++p) tied[p] = (unsigned char)(g->alive[p] && g->tricks[p] == best);
+        rng_align(r);                  /* the chance events of a round end start a Philox block ... */
         g->player = set_draw(tied, 7, r);
         g->dealer = okw_next(g, g->dealer);
         for (int p = 0; p < g->np; ++p) g->tricks[p] = 0;
         okw_deal(g, r);
+        rng_align(r);                  /* ... and the next decision starts one */
     } else {
         g->tricks_left = 0; /* game over; the reference's final deal() hands out 0 cards */
     }
@@ -264,10 +317,14 @@ static void okw_determinise(okw* g, int observer, rng* r)
         if (!g->alive[p] || p == observer) continue;
         for (int c = 0; c < 52; ++c) if (g->hand[p][c]) { pool[c] = 1; size[p]++; g->hand[p][c] = 0; }
     }
+    okw_pile pile;
+    pile_from_set(&pile, pool);
+    rng_align(r);
     for (int p = 0; p < g->np; ++p) {
         if (!g->alive[p] || p == observer) continue;
-        for (int j = 0; j < size[p]; ++j) g->hand[p][set_draw(pool, 52, r)] = 1;
+        for (int j = 0; j < size[p]; ++j) g->hand[p][pile_draw(&pile, r)] = 1;
     }
+    rng_align(r);
 }
 
 /* ==================================================================== m,n,k */
@@ -620,7 +677,7 @@ static uint32_t og_stride(uint32_t kind) { return kind == ISMCTS_GAME_MNK || kin
 
 static rng generator_rng(uint64_t seed, uint32_t stream, uint32_t tree, uint32_t iteration, uint32_t d)
 {
-    rng r = { seed, stream, tree, iteration, d, NULL };
+    rng r = { seed, stream, tree, iteration, d, NULL, 0, 0 };
     return r;
 }
 
@@ -798,6 +855,7 @@ static uint32_t og_rollout(ogame* g, rng* r)
     uint16_t mv[256];
     uint32_t plies = 0;
     int n;
+    if (g->kind == ISMCTS_GAME_KW) rng_align(r);   /* Knockout Whist: the rollout starts a Philox block */
     while ((n = og_legal(g, mv)) > 0) {
         og_apply(g, mv[rng_below(r, (uint32_t)n)], r);
         ++plies;
@@ -810,7 +868,7 @@ uint32_t orc_playout(uint32_t game, const void* root, uint64_t seed, uint32_t po
 {
     ogame g;
     if (og_load(&g, game, root)) return 0xFFFFFFFFu;
-    rng r = { seed, pos, tree, iteration, 0, NULL };
+    rng r = { seed, pos, tree, iteration, 0, NULL, 0, 0 };
     og_determinise(&g, og_player(&g), &r);
     const uint32_t plies = og_rollout(&g, &r);
     uint32_t winner;
@@ -952,8 +1010,7 @@ static uint32_t otree_select(otree* t, uint32_t node, const uint16_t* legal, int
     orc_exp3_probabilities(scores, visits, K, probs);
     for (uint32_t i = 0; i < K; ++i) t->n[cand[i]].prob = probs[i];
     /* sample: x uniform in [0,1) from one word; first i with x < cumulative p */
-    const uint32_t w = orc_draw_word(r->seed, r->pos, r->tree, r->iteration, r->d++);
-    if (r->cnt) r->cnt->draws++;
+    const uint32_t w = rng_word(r);
     const double x = ISMCTS_DMUL((double)w, 1.0 / 4294967296.0);
     double cum = 0.0;
     for (uint32_t i = 0; i < K; ++i) {
@@ -999,7 +1056,7 @@ static void so_iteration(otree* t, const ogame* root, uint32_t policy, double ex
 {
     ogame g = *root;
     uint16_t legal[256], untried[256];
-    r->d = 0;
+    rng_restart(r);
     og_determinise(&g, og_player(root), r);
     uint32_t node = 0;
     for (;;) {
@@ -1029,7 +1086,7 @@ int orc_so_search(uint32_t game, const void* root, uint32_t policy, double explo
     if (og_load(&g, game, root)) return ISMCTS_ERR_INVALID;
     otree t;
     otree_init(&t);
-    rng r = { seed, pos, tree, 0, 0, counters };
+    rng r = { seed, pos, tree, 0, 0, counters, 0, 0 };
     for (uint64_t it = 0; it < iterations; ++it) {
         r.iteration = (uint32_t)it;
         so_iteration(&t, &g, policy, exploration, &r);
@@ -1068,7 +1125,7 @@ static void mo_iteration(motrees* m, const ogame* root, uint32_t policy, double 
     ogame g = *root;
     uint16_t legal[256], untried[256];
     uint32_t cur[8] = {0};
-    r->d = 0;
+    rng_restart(r);
     og_determinise(&g, og_player(root), r);
     for (;;) {
         const int n = og_legal(&g, legal);
@@ -1108,7 +1165,7 @@ int orc_mo_search(uint32_t game, const void* root, uint32_t policy, double explo
     if (og_load(&g, game, root)) return ISMCTS_ERR_INVALID;
     motrees m;
     mo_init(&m, &g);
-    rng r = { seed, pos, tree, 0, 0, counters };
+    rng r = { seed, pos, tree, 0, 0, counters, 0, 0 };
     for (uint64_t it = 0; it < iterations; ++it) {
         r.iteration = (uint32_t)it;
         mo_iteration(&m, &g, policy, exploration, &r);
@@ -1162,7 +1219,7 @@ int orc_root_parallel(uint32_t game, uint32_t solver, const void* root, uint32_t
     for (uint32_t j = 0; j < trees; ++j) {
         const uint32_t tg = tree_base + j;
         const uint64_t n_it = orc_tree_iterations(iterations, trees_total, tg);
-        rng r = { seed, pos, tg, 0, 0, counters };
+        rng r = { seed, pos, tg, 0, 0, counters, 0, 0 };
         if (solver == ISMCTS_SOLVER_SO) {
             otree t;
             otree_init(&t);
