@@ -15,9 +15,12 @@
 #if defined(__CUDACC__)
 #define ISMCTS_DEV __host__ __device__ __forceinline__
 #define ISMCTS_HDI __host__ __device__ __forceinline__
+// a real call: keeps the registers of rarely executed code out of the hot loops (lane_search.cuh)
+#define ISMCTS_DEV_CALL __host__ __device__ __noinline__
 #else
 #define ISMCTS_DEV inline
 #define ISMCTS_HDI inline
+#define ISMCTS_DEV_CALL inline
 #endif
 
 #include "../../include/ismcts_detmath.h"

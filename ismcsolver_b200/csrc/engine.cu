@@ -310,6 +310,7 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
         switch (ctx->min_blocks) {
         case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         }

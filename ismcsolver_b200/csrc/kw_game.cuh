@@ -354,14 +354,27 @@ struct KwGame {
     // lanes in the same steps and no ring is involved.
     static constexpr bool kPhased = true;
 
-    // The four words of a block, handed out in order.
+    // A block of the stream in registers.  A turn of a phase loop is two steps (the two draws of
+    // one word); every fourth turn generates the next block.
     struct BlockWords {
-        uint32_t b[4];
-        ISMCTS_DEV uint32_t next()
+        uint32_t w, b1, b2, b3;   // the word being used up, the words not started yet
+        template <class Rng>
+        ISMCTS_DEV void turn(const Rng& rng, uint32_t first_block, uint32_t t)
         {
-            const uint32_t x = b[0];
-            b[0] = b[1]; b[1] = b[2]; b[2] = b[3];
-            return x;
+            if ((t & 3u) == 0u) {
+                uint32_t b[4];
+                rng.block(first_block + (t >> 2), b);
+                w = b[0]; b1 = b[1]; b2 = b[2]; b3 = b[3];
+            } else {
+                w = b1; b1 = b2; b2 = b3;
+            }
+        }
+        // uniform integer below n from the word in use
+        ISMCTS_DEV uint32_t below(uint32_t n)
+        {
+            const uint64_t product = (uint64_t)w * n;
+            w = (uint32_t)product;
+            return (uint32_t)(product >> 32);
         }
     };
 
@@ -375,29 +388,59 @@ struct KwGame {
         if (!warp_any(mine)) return;
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;
         BlockWords words;
-        uint32_t w = 0, draws = 0;
+        uint32_t draws = 0;
         uint64_t hand_acc = 0;
-        for (uint32_t s = 0; warp_any(active && mode != kPlay); ++s) {
-            if ((s & 7u) == 0u) rng.block(first_block + (s >> 3), words.b);
-            if ((s & 1u) == 0u) w = words.next();
-            if (active && mode != kPlay) {
-                const uint64_t product = (uint64_t)w * chance_count();
-                const uint32_t j = (uint32_t)(product >> 32);
-                w = (uint32_t)product;
-                ++draws;
-                if (mode == kDeal) {
-                    hand_acc |= (uint64_t)1 << take_from_pile(j);
-                    if (--deal_left == 0) {
-                        set_hand(deal_player, hand(deal_player) | hand_acc);
-                        hand_acc = 0;
-                        next_hand();
+        for (uint32_t t = 0; warp_any(active && mode != kPlay); ++t) {
+            words.turn(rng, first_block, t);
+#pragma unroll
+            for (uint32_t half = 0; half < 2; ++half) {
+                if (active && mode != kPlay) {
+                    const uint32_t j = words.below(chance_count());
+                    ++draws;
+                    if (mode == kDeal) {
+                        hand_acc |= (uint64_t)1 << take_from_pile(j);
+                        if (--deal_left == 0) {
+                            set_hand(deal_player, hand(deal_player) | hand_acc);
+                            hand_acc = 0;
+                            next_hand();
+                        }
+                    } else {
+                        break_tie(j);
                     }
-                } else {
-                    break_tie(j);
                 }
             }
         }
         if (mine) { rng.phase_end(first_block, draws); rng.align(); }
+    }
+
+    // One rollout move with the hand `h` of the player to move; leaves the hand of the next player
+    // to move in `h`.
+    ISMCTS_DEV void rollout_step(BlockWords& words, uint64_t& h)
+    {
+        if (request_trump) {
+            // the round winner calls trumps: one of the four suits
+            play(13u * words.below(4));
+        } else {
+            // validMoves, knockoutwhist.cpp:122-136: follow suit if possible (with one card in
+            // hand both cases give the same set)
+            const uint64_t follow = h & (kSuit << (13u * lead_suit));
+            const uint64_t set = trick_len != 0 && follow != 0 ? follow : h;
+            const uint32_t b = kth_bit64(set, words.below(popc64(set)));
+            // doMove, :95-115
+            set_hand(player, h & ~((uint64_t)1 << b));
+            fold_trick(trick_len, player, b);
+            ++trick_len;
+            player = next_alive(player);
+            if (trick_len == popc32(alive4)) {            // finishTrick, :155-161
+                tricks += 1u << (4 * win_player);
+                const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
+                best = taken > best ? taken : best;
+                trick_len = 0;
+                player = win_player;
+            }
+        }
+        h = hand(player);
+        if (h == 0) finish_round();
     }
 
     // Rollout moves (simulate, solverbase.h:36-43) for the lanes with `rolling` until their
@@ -409,46 +452,20 @@ struct KwGame {
         if (!warp_any(mine)) return;
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;   // the rollout and every round start a block
         BlockWords words;
-        uint32_t w = 0, draws = 0;
+        uint32_t draws = 0;
         // the hand of the player to move (lanes that do not take part may hold no game at all)
-        uint64_t h = mine && !request_trump ? hand(player) : 0;
-        for (uint32_t s = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++s) {
-            if ((s & 7u) == 0u) rng.block(first_block + (s >> 3), words.b);
-            if ((s & 1u) == 0u) w = words.next();
-            if (rolling && mode == kPlay && tricks_left != 0) {
-                ++plies;
-                ++draws;
-                if (request_trump) {
-                    // the round winner calls trumps: one of the four suits
-                    const uint64_t product = (uint64_t)w * 4u;
-                    w = (uint32_t)product;
-                    play(13u * (uint32_t)(product >> 32));
-                    h = hand(player);
-                    continue;
+        uint64_t h = mine ? hand(player) : 0;
+        for (uint32_t t = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++t) {
+            words.turn(rng, first_block, t);
+#pragma unroll
+            for (uint32_t half = 0; half < 2; ++half) {
+                if (rolling && mode == kPlay && tricks_left != 0) {
+                    ++draws;
+                    rollout_step(words, h);
                 }
-                // validMoves, knockoutwhist.cpp:122-136: follow suit if possible (with one card
-                // in hand both cases give the same set)
-                const uint64_t follow = h & (kSuit << (13u * lead_suit));
-                const uint64_t set = trick_len != 0 && follow != 0 ? follow : h;
-                const uint64_t product = (uint64_t)w * popc64(set);
-                w = (uint32_t)product;
-                const uint32_t b = kth_bit64(set, (uint32_t)(product >> 32));
-                // doMove, :95-115
-                set_hand(player, h & ~((uint64_t)1 << b));
-                fold_trick(trick_len, player, b);
-                ++trick_len;
-                player = next_alive(player);
-                if (trick_len == popc32(alive4)) {            // finishTrick, :155-161
-                    tricks += 1u << (4 * win_player);
-                    const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
-                    best = taken > best ? taken : best;
-                    trick_len = 0;
-                    player = win_player;
-                }
-                h = hand(player);
-                if (h == 0) finish_round();
             }
         }
+        plies += draws;
         if (mine) rng.phase_end(first_block, draws);
     }
 };

@@ -156,7 +156,7 @@ struct Lane {
     // The game is over (validMoves() empty): backPropagate, solverbase.h:45-51 /
     // mosolver.h:97-101 — every node from the cursor up to but excluding the root.
     // Then the next iteration.
-    ISMCTS_DEV void finish_iteration(uint32_t gtid)
+    ISMCTS_DEV_CALL void finish_iteration(uint32_t gtid)
     {
         if (kTree) {
             if (kShared) {
@@ -253,7 +253,7 @@ struct Lane {
     // descent resumes).  MO: the tree of the player to move decides, then the
     // cursor of EVERY tree moves to the child for that move, which is created where
     // it does not exist yet (findOrAddChild, node.h:50-56).
-    ISMCTS_DEV void descend()
+    ISMCTS_DEV_CALL void descend()
     {
         for (;;) {
             const Mask legal = g.legal();
@@ -294,7 +294,7 @@ struct Lane {
     }
 
     // select + expand on a tree shared with other lanes (tree parallelisation).
-    ISMCTS_DEV void descend_shared()
+    ISMCTS_DEV_CALL void descend_shared()
     {
         if constexpr (kShared) {
             for (;;) {
@@ -337,47 +337,57 @@ struct Lane {
     }
 
     // ---- the lock-step loop (see the head of this file)
-    ISMCTS_DEV bool wants_chance() const { return phase != kDone && g.chance_pending(); }
+    //
+    // The tree operations (descend, finish_iteration) are real calls: the lane object lives in local
+    // memory and the registers those operations need (64-bit node fields, the double-precision
+    // bandit values) do not count against the loops that run most of the time.  Those loops —
+    // chance events and rollout moves — work on copies of the game and of the stream, which
+    // are registers, between two tree operations.
     ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !g.chance_pending() && !g.terminal(); }
-    ISMCTS_DEV bool wants_move() const { return phase == kRollout && !g.chance_pending() && !g.terminal(); }
-
-    // Refills the Philox rings of the lanes that have room, every fourth step of the warp: lanes that
-    // take part in a phase consume one word per step, so they refill in the same steps.
-    ISMCTS_DEV void tick_rng(uint32_t& tick)
-    {
-        if ((tick++ & 3u) == 0u && phase != kDone && rng.low()) rng.refill();
-    }
 
     ISMCTS_DEV void run(uint32_t gtid)
     {
-        uint32_t tick = 0;
         for (;;) {
             if (!warp_any(phase != kDone)) break;
-            if constexpr (game_is_phased<Game>(0)) {
-                g.chance_phase(rng, phase != kDone);
-            } else if (warp_any(wants_chance())) {
-                do {
-                    tick_rng(tick);
-                    if (wants_chance()) g.chance_draw(rng.below(g.chance_count()));
-                } while (warp_any(wants_chance()));
+            {
+                Game hot = g;
+                LaneRng stream = rng;
+                const uint32_t ph = phase;
+                uint32_t moves = 0;
+                for (;;) {
+                    // every pending chance event of the warp
+                    if constexpr (game_is_phased<Game>(0)) {
+                        hot.chance_phase(stream, ph != kDone);
+                    } else {
+                        for (uint32_t s = 0; warp_any(ph != kDone && hot.chance_pending()); ++s) {
+                            if ((s & 3u) == 0u && ph != kDone && stream.low()) stream.refill();
+                            if (ph != kDone && hot.chance_pending()) hot.chance_draw(stream.below(hot.chance_count()));
+                        }
+                    }
+                    // the tree decides next, for some lane
+                    if (kTree && warp_any(ph == kSelect && !hot.chance_pending() && !hot.terminal())) break;
+                    // every game is over
+                    if (!warp_any(ph == kRollout && !hot.chance_pending() && !hot.terminal())) break;
+                    // rollout moves (simulate, solverbase.h:36-43) until a chance event or the end of the game
+                    if constexpr (game_is_phased<Game>(0)) {
+                        hot.play_phase(stream, ph == kRollout, moves);
+                    } else {
+                        for (uint32_t s = 0; warp_any(ph == kRollout && !hot.chance_pending() && !hot.terminal()); ++s) {
+                            if ((s & 3u) == 0u && ph == kRollout && stream.low()) stream.refill();
+                            if (ph == kRollout && !hot.chance_pending() && !hot.terminal()) {
+                                const Mask set = hot.legal();
+                                ++moves;
+                                hot.play(set.kth(stream.below(set.count())));
+                            }
+                        }
+                    }
+                }
+                g = hot;
+                rng = stream;
+                plies += moves;
             }
             if (kTree && warp_any(wants_descent())) {
                 if (wants_descent()) { if (kShared) descend_shared(); else descend(); }
-                continue;
-            }
-            if (warp_any(wants_move())) {
-                if constexpr (game_is_phased<Game>(0)) {
-                    g.play_phase(rng, phase == kRollout, plies);
-                } else {
-                    do {
-                        tick_rng(tick);
-                        if (wants_move()) {
-                            const Mask set = g.legal();
-                            ++plies;
-                            g.play(set.kth(rng.below(set.count())));
-                        }
-                    } while (warp_any(wants_move()));
-                }
                 continue;
             }
             // every lane still at work has reached the end of its game
