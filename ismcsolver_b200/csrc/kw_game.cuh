@@ -103,6 +103,8 @@ struct KwGame {
     }
 
     ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; mode = kPlay; }
+    // the same columns again (a copy of the game whose pointers the compiler can follow)
+    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; }
 
     // bit p -> bit 4p
     ISMCTS_DEV static uint32_t spread4(uint32_t bits)
@@ -428,7 +430,11 @@ struct KwGame {
             const uint32_t b = kth_bit64(set, words.below(popc64(set)));
             // doMove, :95-115
             set_hand(player, h & ~((uint64_t)1 << b));
-            fold_trick(trick_len, player, b);
+            // trickWinner as in fold_trick(), with the suit by a multiplication (exact below 64)
+            const uint32_t suit = (b * 79u) >> 10, rank = b - 13u * suit;
+            if (trick_len == 0) lead_suit = suit;
+            const uint32_t key = rank + (suit == trump ? 32u : suit == lead_suit ? 16u : 0u);
+            if (trick_len == 0 || key > win_key) { win_key = key; win_player = player; }
             ++trick_len;
             player = next_alive(player);
             if (trick_len == popc32(alive4)) {            // finishTrick, :155-161

@@ -345,13 +345,18 @@ struct Lane {
     // are registers, between two tree operations.
     ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !g.chance_pending() && !g.terminal(); }
 
-    ISMCTS_DEV void run(uint32_t gtid)
+    // `scratch`, `ring`: the per-thread columns the game and the stream are bound to, handed in again so
+    // that the copies the loops work on address them as shared memory (the lane object itself lives in
+    // local memory, where a pointer is just 64 bits).
+    ISMCTS_DEV void run(uint32_t gtid, uint64_t* scratch, uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride)
     {
         for (;;) {
             if (!warp_any(phase != kDone)) break;
             {
                 Game hot = g;
                 LaneRng stream = rng;
+                hot.rebind(scratch, scratch_stride);
+                stream.ring = ring; stream.stride = ring_stride;
                 const uint32_t ph = phase;
                 uint32_t moves = 0;
                 for (;;) {
@@ -437,7 +442,7 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
         }
         if (lane.budget_left()) lane.start_iteration();
     }
-    lane.run(gtid);
+    lane.run(gtid, scratch, scratch_stride, ring, ring_stride);
     if (!valid) return;
     if (kShared) atomic_add_u64(P.iters_done + tree_index, lane.done);
     else P.iters_done[tree_index] = lane.done;
@@ -502,7 +507,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
         lane.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
         lane.start_iteration();
     }
-    lane.run(gtid);
+    lane.run(gtid, scratch, scratch_stride, ring, ring_stride);
 }
 
 } // namespace ismcts

@@ -30,6 +30,8 @@ struct MnkGame {
     int32_t res2;     // 2 * m_result from player 0's view, -1 while running
 
     ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { stones = scratch; stride = scratch_stride; }
+    // the same columns again (a copy of the game whose pointers the compiler can follow)
+    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride) { stones = scratch; stride = scratch_stride; }
 
     ISMCTS_DEV void load(const Root* r)
     {
