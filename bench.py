@@ -35,9 +35,10 @@ ITERATIONS_PER_DECISION = 1_000_000
 DEAL_SEED = 0x1535C75B200           # printed with every line (config.deal_seed)
 # algorithmic node traffic of one KW4 iteration (select 1.28 KB + expand 232 B + backprop 80 B)
 ALGO_BYTES_PER_ITERATION = 1600.0
-# ncu (profiles/r01_final_ncu_raw.txt): warp-instructions executed and DRAM bytes per iteration of the search kernel
-NCU_WARP_INST_PER_ITERATION = 145685200119.0 / 64e6
-NCU_DRAM_BYTES_PER_ITERATION = (76.196156e9 + 27.458430e9) / 64e6
+# ncu (profiles/r01_ls_d_ncu_raw.txt): warp-instructions executed and DRAM bytes per iteration of the search kernel
+NCU_PROFILE = "profiles/r01_ls_d_ncu_raw.txt"
+NCU_WARP_INST_PER_ITERATION = 50190451505.0 / 64e6
+NCU_DRAM_BYTES_PER_ITERATION = (87.994779e9 + 36.264068e9) / 64e6
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
@@ -291,7 +292,7 @@ def b200_arm(args):
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": NCU_DRAM_BYTES_PER_ITERATION * per_launch_iters,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel and workload "
-                                  "(profiles/r01_final_ncu_raw.txt), bytes per launch",
+                                  f"({NCU_PROFILE}), bytes per launch",
                 "algorithmic_bytes_per_launch": per_launch_iters * ALGO_BYTES_PER_ITERATION,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "note": "the path is bound by SM instruction issue, not HBM (see DESIGN.md); "
@@ -304,7 +305,7 @@ def b200_arm(args):
                 "frac": per_launch_iters / (search_ms * 1e-3) * NCU_WARP_INST_PER_ITERATION / (148 * 4 * sm_max * 1e6),
                 "warp_inst_per_iteration": NCU_WARP_INST_PER_ITERATION,
                 "note": "the binding roofline: 148 SMs x 4 schedulers x SM clock; instructions per iteration from ncu "
-                        "smsp__inst_executed.sum (profiles/r01_final_ncu_raw.txt)",
+                        f"smsp__inst_executed.sum ({NCU_PROFILE})",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

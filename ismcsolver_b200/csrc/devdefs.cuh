@@ -46,6 +46,7 @@ ISMCTS_DEV bool warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value) { return atomicCAS(p, expect, value); }
 ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { atomicOr((unsigned long long*)p, (unsigned long long)v); }
+ISMCTS_DEV void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
 ISMCTS_DEV void fence_device() { __threadfence(); }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return __ldcg(p); }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
@@ -77,6 +78,7 @@ ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value)
 }
 ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t old = *p; *p += v; return old; }
 ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { *p |= v; }
+ISMCTS_DEV void atomic_add_f64(double* p, double v) { *p = ISMCTS_DADD(*p, v); }
 ISMCTS_DEV void fence_device() {}
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return *p; }

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace ismcts {
@@ -62,10 +63,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
 template <class Slot>
-__global__ void init_shared_roots_kernel(SearchParams P)
+__global__ void init_shared_roots_kernel(SearchParams P, uint32_t n_roots)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n_positions * P.trees) init_shared_root<Slot>(P, i);
+    if (i < P.n_positions * P.trees) init_shared_root<Slot>(P, i, n_roots);
 }
 
 // Root statistics of every tree -> per-position sums (one thread per tree), after the search.
@@ -261,8 +262,6 @@ static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
         if ((d->flags & 0xFCu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
         if ((d->flags >> ISMCTS_FLAG_LANES_SHIFT) == 0) return fail(ctx, ISMCTS_ERR_INVALID, "shared tree: lanes must be > 0");
-        if (d->solver != ISMCTS_SOLVER_SO || d->policy != ISMCTS_POLICY_UCB1)
-            return fail(ctx, ISMCTS_ERR_INVALID, "shared trees (tree parallelisation) are available for SO-ISMCTS with UCB1");
     } else if ((d->flags & ~ISMCTS_FLAG_KW_MAX4) != 0) {
         return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
     }
@@ -330,9 +329,20 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
     const uint32_t tables = P.n_positions * P.trees, tgrid = (tables + 127) / 128;
     const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
-        init_shared_roots_kernel<SlotUcb<Mask>><<<tgrid, 128, 0, ctx->stream>>>(P);
-        search_kernel<Game, SlotUcb<Mask>, kSO, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
-        collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
+        // tree parallelisation: the lanes of a group share the tree (SO) or the trees of all players (MO)
+        auto run = [&](auto slot_tag, auto kind_tag) {
+            using Slot = typename decltype(slot_tag)::Game;
+            constexpr uint32_t kKind = decltype(kind_tag)::value;
+            init_shared_roots_kernel<Slot><<<tgrid, 128, 0, ctx->stream>>>(P, kKind == kMO ? Game::kMaxPlayers : 1u);
+            search_kernel<Game, Slot, kKind, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
+            collect_roots_kernel<Game, Slot, kKind><<<tgrid, 128, 0, ctx->stream>>>(P);
+        };
+        using So = std::integral_constant<uint32_t, kSO>;
+        using Mo = std::integral_constant<uint32_t, kMO>;
+        if (so && ucb) run(GameTag<SlotUcb<Mask>>{}, So{});
+        else if (so) run(GameTag<SlotExp<Mask>>{}, So{});
+        else if (ucb) run(GameTag<SlotUcb<Mask>>{}, Mo{});
+        else run(GameTag<SlotExp<Mask>>{}, Mo{});
         ctx->launches += 3;
     } else {
         if (so && ucb) {
@@ -376,7 +386,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     uint32_t log2cap;
     if (d->iterations > 0) {
         max_it = d->iterations / d->trees_total + 1;
-        log2cap = std::max<uint32_t>(4, ceil_log2(2 * (per_lane * (max_it + 1) + (shared ? width : 0))));
+        log2cap = std::max<uint32_t>(4, ceil_log2(2 * (per_lane * (max_it + 1) + (shared ? (uint64_t)width * per_lane : 0))));
         if (log2cap > kMaxSlotsLog2) return fail(ctx, ISMCTS_ERR_CAPACITY, "too many iterations per tree for the node pool");
     } else {
         // time mode: the iteration count is unknown; give every lane an equal share of the free memory

@@ -82,7 +82,8 @@ enum LaneKind : uint32_t { kPlayout = 0, kSO = 1, kMO = 2 };
 // work on ONE tree: nodes are reserved with compare-and-swap, statistics are updated with
 // reductions, and every node a descent passes through is counted as visited at once (virtual
 // loss: the visit is in, the reward follows at backpropagation), which steers the other
-// lanes away from the path while its playout is still running.  SO + UCB1 only.
+// lanes away from the path while its playout is still running.  MO-ISMCTS shares the trees of all
+// players the same way; EXP3 updates its scores with floating-point atomics.
 template <class Game, class SlotType, uint32_t kKind, bool kShared = false>
 struct Lane {
     using Mask = typename Game::Mask;
@@ -129,7 +130,7 @@ struct Lane {
     ISMCTS_DEV bool budget_left() const
     {
         if (kTree && !kShared && tree.count + kTrees > P.max_nodes) return false;
-        if (kShared && load_u32_cg(node_counter) + P.lanes_per_tree > P.max_nodes) return false;
+        if (kShared && load_u32_cg(node_counter) + P.lanes_per_tree * kTrees > P.max_nodes) return false;
         return P.iterations > 0 || !kTree ? done < quota : global_timer_ns() < deadline;
     }
 
@@ -159,11 +160,21 @@ struct Lane {
     ISMCTS_DEV_CALL void finish_iteration(uint32_t gtid)
     {
         if (kTree) {
-            if (kShared) {
+            if (kShared && !kMulti && !kExp3) {
                 // the visits were counted on the way down (virtual loss); now the rewards
                 for (uint32_t i = 0; i < depth; ++i)
                     red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[path[i] & 0xFFFFFFu]),
                                 (uint64_t)g.result2(path[i] >> 24) << 32);
+            } else if (kShared) {
+                // the same along the parent links of every tree
+                for (uint32_t t = 0; t < kTrees; ++t) {
+                    uint32_t n = node[t];
+                    while (n >= tree.roots) {
+                        const Slot s = load_slot(&tree.slots[n]);
+                        add_reward_shared(&tree.slots[n], g.result2(s.player), slot_prob(s));
+                        n = slot_parent_of(s.key);
+                    }
+                }
             } else if (!kMulti && !kExp3) {
                 for (uint32_t i = 0; i < depth; ++i) update_node(path[i] & 0xFFFFFFu, path[i] >> 24, 1.0);
             } else {
@@ -183,6 +194,14 @@ struct Lane {
         ++done;
         if (budget_left()) start_iteration();
         else phase = kDone;
+    }
+
+    // updateData on a shared node whose visit is already counted (ucb1.h:53-56, exp3.h:45-48).
+    template <class S>
+    ISMCTS_DEV static void add_reward_shared(S* s, uint32_t r2, double prob)
+    {
+        if constexpr (!S::kExp3) red_add_u64(reinterpret_cast<uint64_t*>(s), (uint64_t)r2 << 32);
+        else atomic_add_f64(&s->score, ISMCTS_DDIV(ISMCTS_DMUL((double)r2, 0.5), prob > 0.0 ? prob : 1.0)); // (a node another lane is still filling in)
     }
 
     template <class S> ISMCTS_DEV static double slot_prob(const S& s) { if constexpr (S::kExp3) return s.prob; else return 1.0; }
@@ -293,7 +312,45 @@ struct Lane {
         }
     }
 
-    // select + expand on a tree shared with other lanes (tree parallelisation).
+    // A visit of `slot` counted now (virtual loss): the reward follows at backpropagation.
+    ISMCTS_DEV void count_visit(uint32_t slot)
+    {
+        if constexpr (!kExp3) red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[slot]), 1u);
+        else atomic_add_u32(&tree.slots[slot].visits, 1u);
+    }
+
+    // UCB1 on a node whose children other lanes update (selectChild as in select_child()).
+    template <class S>
+    ISMCTS_DEV uint32_t select_child_shared(uint32_t parent, const Mask& legal, uint32_t& chosen_move, uint32_t& chosen_player)
+    {
+        if constexpr (!S::kExp3) {
+            double best_u = -1.0;
+            uint32_t best_created = 0xFFFFFFFFu, best = 0;
+            for (Mask rest = legal; rest.any();) {
+                const uint32_t m = rest.pop_lowest();
+                S c;
+                const uint32_t ci = tree.find(parent, m, c);
+                atomic_add_u32(&tree.slots[ci].avail, 1u);                 // markAvailable, ucb1.h:71-72
+                const uint32_t avail = c.avail + 1u < P.ln_count ? c.avail + 1u : P.ln_count - 1u;
+                const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[avail], P.exploration);
+                if (u > best_u || (u == best_u && c.created < best_created)) {
+                    best_u = u; best_created = c.created; best = ci; chosen_move = m; chosen_player = c.player;
+                }
+            }
+            return best;
+        } else {
+            // EXP3 reads the scores and visits the other lanes are updating and stores its probabilities,
+            // as the reference does with its atomics (exp3.h:42-48,84)
+            S chosen;
+            const uint32_t ci = select_child(parent, legal, chosen, chosen_move);
+            chosen_player = chosen.player;
+            return ci;
+        }
+    }
+
+    // select + expand on trees shared with other lanes (tree parallelisation): SO-ISMCTS on one tree,
+    // MO-ISMCTS on the trees of all players (the children of the other players' trees are found or
+    // created for every move, findOrAddChild, node.h:50-56).
     ISMCTS_DEV_CALL void descend_shared()
     {
         if constexpr (kShared) {
@@ -301,34 +358,29 @@ struct Lane {
                 const Mask legal = g.legal();
                 if (!legal.any()) return;
                 const uint32_t who = g.current_player();
-                const Mask kids = Mask::load_shared(&tree.slots[node[0]].child_mask); // other lanes add children
+                const uint32_t a = kMulti ? who : 0;                  // the deciding tree
+                const Mask kids = Mask::load_shared(&tree.slots[node[a]].child_mask); // other lanes add children
                 const Mask untried = legal.minus(kids);
-                uint32_t move, next, stored = 0;
                 const bool expand = untried.any();
-                if (expand) {
-                    move = untried.kth(rng.below(untried.count()));
-                    next = tree.find_or_insert_shared(node[0], move, who, node_counter);
-                    // count the visit before the child becomes visible: a published child has visits >= 1
-                    red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[next]), 1u);
-                    fence_device();
-                    Mask::set_shared(&tree.slots[node[0]].child_mask, move);
-                } else {
-                    double best_u = -1.0;
-                    uint32_t best_created = 0xFFFFFFFFu;
-                    move = 0; next = 0;
-                    for (Mask rest = legal; rest.any();) {
-                        const uint32_t m = rest.pop_lowest();
-                        Slot c;
-                        const uint32_t ci = tree.find(node[0], m, c);
-                        atomic_add_u32(&tree.slots[ci].avail, 1u);                 // markAvailable, ucb1.h:71-72
-                        const uint32_t avail = c.avail + 1u < P.ln_count ? c.avail + 1u : P.ln_count - 1u;
-                        const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[avail], P.exploration);
-                        if (u > best_u || (u == best_u && c.created < best_created)) { best_u = u; best_created = c.created; next = ci; move = m; stored = c.player; }
+                uint32_t move = 0, chosen = 0, stored = who;
+                if (expand) move = untried.kth(rng.below(untried.count()));
+                else chosen = select_child_shared<Slot>(node[a], legal, move, stored);
+                for (uint32_t t = 0; t < kTrees; ++t) {
+                    if (kMulti && !((tree_players >> t) & 1u)) continue;
+                    uint32_t next;
+                    if (t == a && !expand) {
+                        next = chosen;
+                        count_visit(next);
+                    } else {
+                        next = tree.find_or_insert_shared(node[t], move, who, node_counter);
+                        // count the visit before the child becomes visible: a published child has visits >= 1
+                        count_visit(next);
+                        fence_device();
+                        Mask::set_shared(&tree.slots[node[t]].child_mask, move);
                     }
-                    red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[next]), 1u);  // virtual loss
+                    node[t] = next;
                 }
-                node[0] = next;
-                path[depth++] = next | ((expand ? who : stored) << 24);
+                if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : stored) << 24);
                 g.step(move);
                 if (expand) { phase = kRollout; return; }
                 if (g.chance_pending()) return;
@@ -448,14 +500,14 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
     else P.iters_done[tree_index] = lane.done;
 }
 
-// Shared trees: the root node and the node counter of tree `index`, before the search starts.
+// Shared trees: the root node(s) and the node counter of tree `index`, before the search starts.
 template <class Slot>
-ISMCTS_DEV void init_shared_root(const SearchParams& P, uint32_t index)
+ISMCTS_DEV void init_shared_root(const SearchParams& P, uint32_t index, uint32_t n_roots = 1)
 {
     TreePool<Slot> tree;
-    tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)index << P.log2cap), P.log2cap, 1);
+    tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)index << P.log2cap), P.log2cap, n_roots);
     tree.init_roots();
-    P.node_counters[index] = 1;
+    P.node_counters[index] = n_roots;
 }
 
 // Root children of tree `index` -> per-position sums (RootParallel::compileVisitCounts,

@@ -135,7 +135,8 @@ struct TreePool {
             if (i >= roots) {
                 const uint32_t old = atomic_cas_u32(&slots[i].key, 0u, key);
                 if (old == 0u) {
-                    slots[i].avail = 1;                       // ucb1.h:51
+                    if constexpr (!Slot::kExp3) slots[i].avail = 1;   // ucb1.h:51
+                    else slots[i].prob = 1.0;                          // exp3.h:42
                     slots[i].player = player;
                     slots[i].created = atomic_add_u32(counter, 1u);
                     return i;

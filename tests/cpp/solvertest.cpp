@@ -3,7 +3,7 @@
 // Restates the assertions of the reference's test/solvertest.cpp (:64-138) — constructors and
 // getters, setters, "operator() returns a valid move" by iteration count and by time, and the
 // P1DrawOrLose position that every solver must answer with move 2 from 16 iterations — for
-// {SOSolver, MOSolver} x {CudaRootParallel, CudaTreeParallel}, plus the game checks of
+// {SOSolver, MOSolver} x {CudaRootParallel, CudaTreeParallel} (x EXP3 where the reference's tests use it), plus the game checks of
 // test/gametest.cpp that concern the host game classes (:92-106,120-130,184-206).
 //
 //   solvertest            all checks; needs a CUDA device
@@ -313,6 +313,7 @@ int main(int argc, char **argv)
     testConstruction<SOSolver<Card, CudaTreeParallel>>();
     testConstruction<MOSolver<Card, CudaRootParallel>>();
     testConstruction<MOSolver<int, CudaRootParallel, EXP3>>();
+    testConstruction<MOSolver<Card, CudaTreeParallel>>();
     testHostOnly();
     if (hostOnly) {
         // without a device every search throws
@@ -328,8 +329,13 @@ int main(int argc, char **argv)
         testKnockoutWhist<SOSolver<Card, CudaTreeParallel>>();
         testKnockoutWhist<MOSolver<Card, CudaRootParallel>>();
         testKnockoutWhist<MOSolver<Card, CudaRootParallel, EXP3>>();
+        testKnockoutWhist<MOSolver<Card, CudaTreeParallel>>();
+        testKnockoutWhist<SOSolver<Card, CudaTreeParallel, EXP3>>();
+        testKnockoutWhist<MOSolver<Card, CudaTreeParallel, EXP3>>();
         testGoofspiel<SOSolver<Card, CudaRootParallel>>();
         testGoofspiel<MOSolver<Card, CudaRootParallel>>();
+        testGoofspiel<SOSolver<Card, CudaTreeParallel>>();
+        testGoofspiel<MOSolver<Card, CudaTreeParallel>>();
         {
             // the phantom game through both solvers: a valid move by count and by time
             PhantomMnkGame game {3, 3, 3, 5};
@@ -347,9 +353,11 @@ int main(int argc, char **argv)
         testP1DrawOrLose<SOSolver<int, CudaRootParallel>>();
         testP1DrawOrLose<SOSolver<int, CudaTreeParallel>>();
         testP1DrawOrLose<MOSolver<int, CudaRootParallel>>();
+        testP1DrawOrLose<MOSolver<int, CudaTreeParallel>>();
         testTrees<SOSolver<int, CudaRootParallel>>();
         testTrees<SOSolver<int, CudaTreeParallel>>();
         testTrees<MOSolver<int, CudaRootParallel>>();
+        testTrees<MOSolver<int, CudaTreeParallel>>();
         {
             // currentTrees(): the device pool as host nodes (sosolver.h:38-41)
             P1DrawOrLose game;

@@ -217,15 +217,16 @@ int search_game(const void* root, uint32_t solver, uint32_t policy, uint64_t ite
     return search_t<Game, SlotExp<Mask>, kMO>(root, iterations, seed, pos, tree, width, dump, exploration, player, nodes, capacity, count);
 }
 
-// Tree parallelisation on the host: the `width` lanes of one warp share ONE tree (on the GPU the
-// interleaving of the lanes is whatever the hardware does; here it is the fibers' fixed one).
-template <class Game>
-int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint64_t seed, ismcts_node_rec* nodes,
-                    uint32_t capacity, uint32_t* count, uint64_t* done_out)
+// Tree parallelisation on the host: the `width` lanes of one warp share ONE tree (MO-ISMCTS: the
+// trees of all players); on the GPU the interleaving of the lanes is whatever the hardware does, here
+// it is the fibers' fixed one.  Writes the tree of `player` (SO: the tree).
+template <class Game, class Slot, uint32_t kKind>
+int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint64_t seed, uint32_t player,
+                    ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* done_out)
 {
-    using Slot = SlotUcb<typename Game::Mask>;
+    constexpr uint32_t n_roots = kKind == kMO ? Game::kMaxPlayers : 1;
     uint32_t log2cap = 4;
-    while (((uint64_t)1 << log2cap) < 2 * (iterations + 2 + width)) ++log2cap;
+    while (((uint64_t)1 << log2cap) < 2 * n_roots * (iterations + 2 + width)) ++log2cap;
     std::vector<Slot> table((size_t)1 << log2cap);
     std::memset((void*)table.data(), 0, table.size() * sizeof(Slot));
     const std::vector<double> ln = ln_table(iterations + 300);
@@ -241,26 +242,45 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
     P.visits = v.data(); P.score2 = s2.data(); P.avail = a.data(); P.iters_done = it.data();
     P.lanes_per_tree = width; P.node_counters = &counter;
-    init_shared_root<Slot>(P, 0);
+    init_shared_root<Slot>(P, 0, n_roots);
     WarpScratch<Game> ws(width);
     FiberWarp warp(width);
     warp.run([&](uint32_t lane) {
-        lane_tree_search<Game, Slot, kSO, true>(P, lane, true, ws.scratch.data() + lane, width, ws.ring.data() + lane, width,
-                                                ws.path.data() + (size_t)lane * Game::kMaxDepth);
+        lane_tree_search<Game, Slot, kKind, true>(P, lane, true, ws.scratch.data() + lane, width, ws.ring.data() + lane, width,
+                                                  ws.path.data() + (size_t)lane * Game::kMaxDepth);
     });
     *done_out = it[0];
-    return dump_table(table.data(), table.size(), 1, 0, nodes, capacity, count);
+    return dump_table(table.data(), table.size(), n_roots, kKind == kMO ? player : 0, nodes, capacity, count);
+}
+
+template <class Game>
+int shared_search_game(const void* root, uint32_t solver, uint32_t policy, uint64_t iterations, uint32_t width, uint64_t seed,
+                       uint32_t player, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* done)
+{
+    using Mask = typename Game::Mask;
+    if (solver == ISMCTS_SOLVER_SO && policy == ISMCTS_POLICY_UCB1)
+        return shared_search_t<Game, SlotUcb<Mask>, kSO>(root, iterations, width, seed, player, nodes, capacity, count, done);
+    if (solver == ISMCTS_SOLVER_SO)
+        return shared_search_t<Game, SlotExp<Mask>, kSO>(root, iterations, width, seed, player, nodes, capacity, count, done);
+    if (policy == ISMCTS_POLICY_UCB1)
+        return shared_search_t<Game, SlotUcb<Mask>, kMO>(root, iterations, width, seed, player, nodes, capacity, count, done);
+    return shared_search_t<Game, SlotExp<Mask>, kMO>(root, iterations, width, seed, player, nodes, capacity, count, done);
 }
 
 } // namespace
 
 extern "C" {
 
-int emu_shared_search(uint32_t game, const void* root, uint64_t iterations, uint32_t width, uint64_t seed,
-                      ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* done)
+int emu_shared_search(uint32_t game, const void* root, uint32_t solver, uint32_t policy, uint64_t iterations, uint32_t width,
+                      uint64_t seed, uint32_t player, ismcts_node_rec* nodes, uint32_t capacity, uint32_t* count, uint64_t* done)
 {
-    if (game == ISMCTS_GAME_KW) return shared_search_t<KwGame>(root, iterations, width, seed, nodes, capacity, count, done);
-    return shared_search_t<MnkGame>(root, iterations, width, seed, nodes, capacity, count, done);
+    if (game == ISMCTS_GAME_KW)
+        return shared_search_game<KwGame>(root, solver, policy, iterations, width, seed, player, nodes, capacity, count, done);
+    if (game == ISMCTS_GAME_GOOF)
+        return shared_search_game<GoofGame>(root, solver, policy, iterations, width, seed, player, nodes, capacity, count, done);
+    if (game == ISMCTS_GAME_PHANTOM)
+        return shared_search_game<PhantomGame>(root, solver, policy, iterations, width, seed, player, nodes, capacity, count, done);
+    return shared_search_game<MnkGame>(root, solver, policy, iterations, width, seed, player, nodes, capacity, count, done);
 }
 
 uint32_t emu_playout(uint32_t game, const void* root, uint64_t seed, uint32_t pos, uint32_t iteration)

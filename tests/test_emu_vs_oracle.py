@@ -21,8 +21,8 @@ def emu():
     E = C.CDLL(os.path.join(EMU_DIR, "libemu.so"))
     E.emu_playout.restype = C.c_uint32
     E.emu_playout.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32]
-    E.emu_shared_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32,
-                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    E.emu_shared_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64,
+                                    C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     E.emu_search.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32,
                              C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_void_p, C.c_uint32,
                              C.POINTER(C.c_uint32)]
@@ -188,15 +188,15 @@ def test_mo_and_exp3_in_a_warp(emu, solver, policy):
         assert (got[f] == want[f]).all(), f
 
 
-def emu_shared(E, game, root, iters, width, seed):
-    nodes = np.zeros(iters + width + 2, dtype=O.NODE_DTYPE)
+def emu_shared(E, game, root, iters, width, seed, solver=O.SOLVER_SO, policy=O.POLICY_UCB1, player=0):
+    nodes = np.zeros(8 * (iters + width + 2), dtype=O.NODE_DTYPE)
     n, done = C.c_uint32(), C.c_uint64()
-    assert E.emu_shared_search(game, C.byref(root), iters, width, seed, nodes.ctypes.data, len(nodes), C.byref(n),
-                               C.byref(done)) == 0
+    assert E.emu_shared_search(game, C.byref(root), solver, policy, iters, width, seed, player, nodes.ctypes.data,
+                               len(nodes), C.byref(n), C.byref(done)) == 0
     return nodes[:n.value], done.value
 
 
-def check_tree_invariants(nodes, iterations):
+def check_tree_invariants(nodes, iterations, ucb=True):
     """What any correct tree-parallel search satisfies, whatever the interleaving of its lanes."""
     top = nodes[1:][nodes[1:]["parent"] == 0]
     assert int(top["visits"].sum()) == iterations            # every iteration passes through one root child
@@ -205,7 +205,11 @@ def check_tree_invariants(nodes, iterations):
     for r in nodes[1:]:
         kids[r["parent"]] += r["visits"]
     assert (kids[1:] <= nodes[1:]["visits"]).all()          # a node is visited at least as often as its children
-    assert (nodes[1:]["score2"] <= 2 * nodes[1:]["visits"]).all() and (nodes[1:]["visits"] >= 1).all()
+    assert (nodes[1:]["visits"] >= 1).all()
+    if ucb:
+        assert (nodes[1:]["score2"] <= 2 * nodes[1:]["visits"]).all()
+    else:
+        assert (nodes[1:]["score"] >= 0).all() and ((nodes[1:]["prob"] > 0) & (nodes[1:]["prob"] <= 1)).all()
     keys = set(zip(nodes[1:]["parent"].tolist(), nodes[1:]["move"].tolist()))
     assert len(keys) == len(nodes) - 1                       # no duplicated child
 
@@ -226,6 +230,32 @@ def test_shared_tree_invariants(emu, width):
         nodes, done = emu_shared(emu, game, s, 3000, width, 11)
         assert done == 3000
         check_tree_invariants(nodes, 3000)
+
+
+@pytest.mark.parametrize("solver,policy", [(O.SOLVER_MO, O.POLICY_UCB1), (O.SOLVER_SO, O.POLICY_EXP3), (O.SOLVER_MO, O.POLICY_EXP3)])
+def test_shared_trees_mo_and_exp3_one_lane_is_the_sequential_search(emu, solver, policy):
+    """MO-ISMCTS and EXP3 on shared trees: with one lane in flight the trees equal the oracle's."""
+    s = O.kw_deal(5, 5, 4)
+    fields = FIELDS if policy == O.POLICY_UCB1 else ("parent", "move", "player", "visits", "score", "prob")
+    for p in ((0, 2) if solver == O.SOLVER_MO else (0,)):
+        if solver == O.SOLVER_MO:
+            want = O.mo_search(O.GAME_KW, s, 500, seed=9, policy=policy)[p]
+        else:
+            want = O.so_search(O.GAME_KW, s, 500, seed=9, policy=policy)
+        got, done = emu_shared(emu, O.GAME_KW, s, 500, 1, 9, solver, policy, p)
+        assert done == 500 and len(got) == len(want)
+        for f in fields:
+            assert (got[f] == want[f]).all(), (p, f)
+
+
+@pytest.mark.parametrize("solver,policy", [(O.SOLVER_MO, O.POLICY_UCB1), (O.SOLVER_SO, O.POLICY_EXP3), (O.SOLVER_MO, O.POLICY_EXP3)])
+@pytest.mark.parametrize("width", [5, 32])
+def test_shared_trees_mo_and_exp3_invariants(emu, solver, policy, width):
+    for game, s in ((O.GAME_KW, O.kw_deal(5, 6, 4)), (O.GAME_MNK, O.mnk_init(4, 4, 3))):
+        for p in ((0, 1) if solver == O.SOLVER_MO else (0,)):
+            nodes, done = emu_shared(emu, game, s, 1500, width, 11, solver, policy, p)
+            assert done == 1500
+            check_tree_invariants(nodes, 1500, ucb=policy == O.POLICY_UCB1)
 
 
 def _goof_positions(count, seed=0):

@@ -287,13 +287,58 @@ def test_shared_tree_mnk_p1_draw_or_lose(engine):
     assert int(res["best_move"][0]) == 2 and int(res["visits"][0].sum()) == 20000
 
 
-def test_shared_tree_rejects_unsupported_combinations(engine):
+def test_shared_tree_rejects_zero_lanes(engine):
     s = capi.kw_deal(1, 1, 4)
     with pytest.raises(capi.EngineError):
-        engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=100, policy=capi.POLICY_EXP3,
-                                       flags=_shared_flags(32)), capi.pack_states([s]))
-    with pytest.raises(capi.EngineError):
         engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=100, flags=SHARED), capi.pack_states([s]))
+
+
+@pytest.mark.parametrize("solver,policy", [(capi.SOLVER_MO, capi.POLICY_UCB1), (capi.SOLVER_SO, capi.POLICY_EXP3),
+                                           (capi.SOLVER_MO, capi.POLICY_EXP3)])
+def test_shared_trees_mo_and_exp3_one_lane_is_bit_exact(engine, solver, policy):
+    """MO-ISMCTS (the trees of all players shared) and EXP3 on shared trees: one lane in flight is the
+    sequential search, every node."""
+    s = capi.kw_deal(5, 5, 4)
+    fields = FIELDS if policy == capi.POLICY_UCB1 else ("parent", "move", "player", "visits", "score", "prob")
+    desc = engine.make_desc(capi.GAME_KW, 1, 1, iterations=800, seed=9, solver=solver, policy=policy,
+                            flags=_shared_flags(1))
+    res = engine.search(desc, capi.pack_states([s]))
+    assert int(res["iterations_done"][0, 0]) == 800
+    for p in ((0, 1, 3) if solver == capi.SOLVER_MO else (0,)):
+        got = engine.dump_tree(0, 1000, player=p)
+        if solver == capi.SOLVER_MO:
+            want = O.mo_search(O.GAME_KW, _okw(s), 800, seed=9, policy=policy)[p]
+        else:
+            want = O.so_search(O.GAME_KW, _okw(s), 800, seed=9, policy=policy)
+        assert len(got) == len(want)
+        for f in fields:
+            assert (got[f] == want[f]).all(), (p, f)
+
+
+@pytest.mark.parametrize("solver,policy", [(capi.SOLVER_MO, capi.POLICY_UCB1), (capi.SOLVER_SO, capi.POLICY_EXP3),
+                                           (capi.SOLVER_MO, capi.POLICY_EXP3)])
+@pytest.mark.parametrize("lanes", [64, 4096])
+def test_shared_trees_mo_and_exp3_many_lanes(engine, solver, policy, lanes):
+    """Many lanes on the shared trees: every tree stays consistent, every iteration is accounted for and the
+    decision on the reference's decisive opening deal is the sequential one."""
+    iterations = 40000
+    s = O.KwState.from_hex(GOLDEN_OPENING)
+    desc = engine.make_desc(capi.GAME_KW, 1, 1, iterations=iterations, seed=4, solver=solver, policy=policy,
+                            flags=_shared_flags(lanes))
+    res = engine.search(desc, np.frombuffer(bytes(s), dtype=np.uint8))
+    assert int(res["iterations_done"].sum()) == iterations
+    assert int(res["visits"][0].sum()) == iterations
+    for p in ((0, 2) if solver == capi.SOLVER_MO else (0,)):
+        nodes = engine.dump_tree(0, 4 * iterations + 8, player=p)
+        top = nodes[1:][nodes[1:]["parent"] == 0]
+        assert int(top["visits"].sum()) == iterations
+        kids = np.zeros(len(nodes), dtype=np.int64)
+        for r in nodes[1:]:
+            kids[r["parent"]] += r["visits"]
+        assert (kids[1:] <= nodes[1:]["visits"]).all() and (nodes[1:]["visits"] >= 1).all()
+        assert len(set(zip(nodes[1:]["parent"].tolist(), nodes[1:]["move"].tolist()))) == len(nodes) - 1
+    if policy == capi.POLICY_UCB1:
+        assert int(res["best_move"][0]) == 37
 
 
 # ------------------------------------------------------------------ Goofspiel (simultaneous moves, EXP3)
