@@ -211,6 +211,7 @@ struct Lane {
     template <class S>
     ISMCTS_DEV uint32_t select_child(uint32_t parent, const Mask& legal, S& chosen, uint32_t& chosen_move)
     {
+        for (Mask rest = legal; rest.any();) tree.prefetch(parent, rest.pop_lowest());
         if constexpr (!S::kExp3) {
             uint32_t best = 0;
             double best_u = -1.0;
@@ -324,6 +325,7 @@ struct Lane {
     ISMCTS_DEV uint32_t select_child_shared(uint32_t parent, const Mask& legal, uint32_t& chosen_move, uint32_t& chosen_player)
     {
         if constexpr (!S::kExp3) {
+            for (Mask rest = legal; rest.any();) tree.prefetch(parent, rest.pop_lowest());
             double best_u = -1.0;
             uint32_t best_created = 0xFFFFFFFFu, best = 0;
             for (Mask rest = legal; rest.any();) {

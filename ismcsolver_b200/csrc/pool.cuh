@@ -122,6 +122,10 @@ struct TreePool {
         }
     }
 
+    // Starts loading the home slot of the child of `parent` for `move`: a descent looks its children up
+    // one after the other, and without this their DRAM latencies add up.
+    ISMCTS_DEV void prefetch(uint32_t parent, uint32_t move) const { prefetch_l2(&slots[home(slot_make_key(parent, move))]); }
+
     // Shared tree (tree parallelisation): the child of `parent` for `move`, created if no lane has
     // created it yet (Node::addChild under the node mutex, node.h:44-48,121-126, without the
     // mutex).  A slot is reserved by a compare-and-swap on its key; the winner fills in the
