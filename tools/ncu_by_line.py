@@ -24,6 +24,7 @@ ap.add_argument("--per", type=float, default=1.0)
 ap.add_argument("--lib", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                                "ismcsolver_b200", "libismcts_b200.so"))
 ap.add_argument("--top", type=int, default=50)
+ap.add_argument("--metric", default="Instructions Executed", help="column of the SASS page to sum (e.g. stall_long_sb, '# Samples')")
 a = ap.parse_args()
 
 # 1. address -> (innermost line, site line) from nvdisasm -gi of the kernel's cubin
@@ -60,7 +61,7 @@ src = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--pri
 rows = list(csv.reader(io.StringIO(src)))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
-ia, ie, it = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
+ia, ie, it = hdr.index("Address"), hdr.index(a.metric), hdr.index("Thread Instructions Executed")
 base = None
 by = collections.Counter()
 thr = collections.Counter()
