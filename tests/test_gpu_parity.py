@@ -127,6 +127,44 @@ def test_tree_sharding_is_invariant(engine):
         assert (acc[k] == whole[k]).all()
 
 
+def test_full_size_decision_properties(engine):
+    """BASELINE.json configs[1] at its full size (1M iterations per decision over 2368 trees): what does not
+    depend on the size — every iteration is accounted for, passes through exactly one legal root child,
+    scores never exceed visits, two half-launches with the tree range split (as two GPUs would) give the
+    sums of the whole launch, and the same launch twice gives the same numbers."""
+    n_pos, trees, iterations = 4, 2368, 1_000_000
+    states = [capi.kw_deal(0x1535C75B200, i, 4) for i in range(n_pos)]
+    roots = capi.pack_states(states)
+    whole = engine.search(engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=0xB200), roots)
+    assert int(whole["iterations_done"].sum()) == n_pos * iterations
+    per_tree = whole["iterations_done"]
+    assert int(per_tree.max()) - int(per_tree.min()) <= 1          # execution.h:42-52: an even split
+    for i, s in enumerate(states):
+        legal = capi.kw_legal_mask(s)
+        assert int(whole["visits"][i].sum()) == iterations
+        for m in range(64):
+            if not legal >> m & 1:
+                assert whole["visits"][i][m] == 0
+        assert (whole["score2"][i] <= 2 * whole["visits"][i]).all()
+        assert legal >> int(whole["best_move"][i]) & 1
+    halves = {k: np.zeros_like(whole[k]) for k in ("visits", "score2", "avail")}
+    for base in (0, trees // 2):
+        part = engine.search(engine.make_desc(capi.GAME_KW, n_pos, trees // 2, iterations=iterations, seed=0xB200,
+                                              trees_total=trees, tree_base=base), roots)
+        for k in halves:
+            halves[k] += part[k]
+    again = engine.search(engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=0xB200), roots)
+    for k in halves:
+        assert (again[k] == whole[k]).all() and (halves[k] == whole[k]).all(), k
+    # one tree of the full-size launch against the oracle, every node
+    it0 = int(per_tree[0, 5])
+    nodes = O.so_search(O.GAME_KW, _okw(states[0]), it0, seed=0xB200, pos=0, tree=5)
+    got = engine.dump_tree(5, it0 + 2)
+    assert len(got) == len(nodes)
+    for f in FIELDS:
+        assert (got[f] == nodes[f]).all(), f
+
+
 def test_p1_draw_or_lose(engine):
     """solvertest.cpp:45-60,131-138: from P1DrawOrLose every solver must play move 2 with 16 iterations."""
     s = capi.mnk_init(3, 3, 3)
