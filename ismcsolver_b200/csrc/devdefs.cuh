@@ -31,6 +31,7 @@ namespace ismcts {
 ISMCTS_DEV uint32_t popc32(uint32_t x) { return (uint32_t)__popc(x); }
 ISMCTS_DEV uint32_t popc64(uint64_t x) { return (uint32_t)__popcll(x); }
 ISMCTS_DEV uint32_t ctz32(uint32_t x) { return (uint32_t)(__ffs((int)x) - 1); }
+ISMCTS_DEV uint32_t clz32(uint32_t x) { return (uint32_t)__clz((int)x); }
 ISMCTS_DEV uint32_t ctz64(uint64_t x) { return (uint32_t)(__ffsll((long long)x) - 1); }
 ISMCTS_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 ISMCTS_DEV uint64_t global_timer_ns()
@@ -61,6 +62,7 @@ ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v)
 ISMCTS_DEV uint32_t popc32(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
 ISMCTS_DEV uint32_t popc64(uint64_t x) { return (uint32_t)__builtin_popcountll(x); }
 ISMCTS_DEV uint32_t ctz32(uint32_t x) { return (uint32_t)__builtin_ctz(x); }
+ISMCTS_DEV uint32_t clz32(uint32_t x) { return x ? (uint32_t)__builtin_clz(x) : 32u; }
 ISMCTS_DEV uint32_t ctz64(uint64_t x) { return (uint32_t)__builtin_ctzll(x); }
 ISMCTS_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 ISMCTS_DEV uint64_t global_timer_ns()

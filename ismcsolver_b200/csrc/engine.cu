@@ -53,12 +53,13 @@ template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams P)
 {
     extern __shared__ uint64_t smem[];
-    uint64_t* scratch = smem + threadIdx.x;
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
+    Game::init_block(threadIdx.x, blockDim.x);
+    __syncthreads();
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
-    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, scratch, kBlock, ring, kBlock, path);
+    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, smem, kBlock, threadIdx.x, ring, kBlock, path);
 }
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
@@ -81,10 +82,11 @@ template <class Game>
 __global__ void __launch_bounds__(kBlock) playout_kernel(SearchParams P, uint32_t per_position)
 {
     extern __shared__ uint64_t smem[];
-    uint64_t* scratch = smem + threadIdx.x;
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
+    Game::init_block(threadIdx.x, blockDim.x);
+    __syncthreads();
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    lane_playout<Game>(P, gtid, gtid < P.n_positions * per_position, per_position, scratch, kBlock, ring, kBlock);
+    lane_playout<Game>(P, gtid, gtid < P.n_positions * per_position, per_position, smem, kBlock, threadIdx.x, ring, kBlock);
 }
 
 } // namespace ismcts
@@ -527,8 +529,14 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     if (d->game == ISMCTS_GAME_KW) {
         // positions with at most four players use the denser shared-memory layout of the jobs kernel
         bool max4 = true;
-        for (uint32_t p = 0; p < d->n_positions; ++p)
-            max4 = max4 && ((const ismcts_kw_state*)((const uint8_t*)roots + p * state))->num_players <= 4;
+        for (uint32_t p = 0; p < d->n_positions; ++p) {
+            const ismcts_kw_state* rec = (const ismcts_kw_state*)((const uint8_t*)roots + p * state);
+            max4 = max4 && rec->num_players <= 4;
+            // a hand has seven places (the game never deals more than seven cards)
+            for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q)
+                if (__builtin_popcountll(rec->hands[q]) > 7)
+                    return fail(ctx, ISMCTS_ERR_INVALID, "Knockout Whist: a hand holds more than seven cards");
+        }
         if (max4) desc.flags |= ISMCTS_FLAG_KW_MAX4; else desc.flags &= ~ISMCTS_FLAG_KW_MAX4;
     }
     rc = ismcts_search_device(ctx, &desc, ctx->roots, dv, ds, da, di);

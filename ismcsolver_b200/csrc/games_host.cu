@@ -22,9 +22,9 @@ namespace {
 constexpr uint32_t kDealTree = 0xFFFFFFFFu, kDealIteration = 0xFFFFFFFFu;
 constexpr uint32_t kApplyTree = 0xFFFFFFFEu;
 
-void kw_store(const KwGame& g, const uint64_t* hands, uint64_t unknown, ismcts_kw_state* s)
+void kw_store(const KwGame& g, uint64_t unknown, ismcts_kw_state* s)
 {
-    for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) s->hands[p] = hands[p];
+    for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) s->hands[p] = g.hand_ids(p);
     s->unknown = unknown;
     s->player = (uint8_t)g.player; s->dealer = (uint8_t)g.dealer; s->trump = (uint8_t)g.trump;
     s->tricks_left = (uint8_t)g.tricks_left; s->request_trump = (uint8_t)g.request_trump;
@@ -48,7 +48,7 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     out->num_players = (uint8_t)np;
     uint64_t hands[KwGame::kHandWords] = {0};
     KwGame g;
-    g.bind(hands, 1);
+    g.bind(hands, 1, 0);
     ismcts_kw_state blank;
     std::memset(&blank, 0, sizeof blank);
     blank.num_players = (uint8_t)np; blank.alive_mask = (uint8_t)((1u << np) - 1u);
@@ -66,7 +66,7 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     const uint32_t up = kth_bit64(unknown, rng.below(popc64(unknown)));
     unknown &= ~((uint64_t)1 << up);
     g.trump = up / 13u;
-    kw_store(g, hands, unknown, out);
+    kw_store(g, unknown, out);
     return ISMCTS_OK;
 }
 
@@ -75,7 +75,7 @@ uint64_t ismcts_kw_legal(const ismcts_kw_state* s)
     if (!s) return 0;
     uint64_t hands[KwGame::kHandWords];
     KwGame g;
-    g.bind(hands, 1);
+    g.bind(hands, 1, 0);
     g.load(s);
     return g.legal().w;
 }
@@ -86,12 +86,12 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
     if (move >= ISMCTS_KW_CARDS) return ISMCTS_ERR_ILLEGAL_MOVE;
     uint64_t hands[KwGame::kHandWords];
     KwGame g;
-    g.bind(hands, 1);
+    g.bind(hands, 1, 0);
     g.load(s);
     // doMove accepts any card while trumps are requested (knockoutwhist.cpp:97-102); otherwise
     // the card must be in the mover's hand or std::out_of_range is thrown (:105-109)
     const bool play = !g.request_trump;
-    if (play && !((hands[g.player] >> move) & 1u)) return ISMCTS_ERR_ILLEGAL_MOVE;
+    if (play && !((g.hand_ids(g.player) >> move) & 1u)) return ISMCTS_ERR_ILLEGAL_MOVE;
     const uint32_t mover = g.player;
     uint32_t ring[LaneRng::kRingWords];
     LaneRng rng;
@@ -117,7 +117,7 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
             s->trick_card[g.trick_len - 1] = (uint8_t)move;
         }
     }
-    kw_store(g, hands, unknown, s);
+    kw_store(g, unknown, s);
     return ISMCTS_OK;
 }
 
@@ -149,7 +149,7 @@ int ismcts_phantom_apply(ismcts_phantom_state* s, uint32_t move)
     if (!s) return ISMCTS_ERR_INVALID;
     uint64_t scratch[PhantomGame::kHandWords];
     PhantomGame g;
-    g.bind(scratch, 1);
+    g.bind(scratch, 1, 0);
     g.load(s);
     // phantommnkgame.cpp:85-88: the move must be one the player still believes possible
     if (move >= (uint32_t)s->m * s->n || !g.legal().test(move)) return ISMCTS_ERR_ILLEGAL_MOVE;
@@ -244,7 +244,7 @@ void ismcts_mnk_legal(const ismcts_mnk_state* s, uint64_t legal[4])
 {
     uint64_t stones[8];
     MnkGame g;
-    g.bind(stones, 1);
+    g.bind(stones, 1, 0);
     g.load(s);
     const MnkGame::Mask l = g.legal();
     for (int i = 0; i < 4; ++i) legal[i] = l.w[i];
@@ -255,7 +255,7 @@ int ismcts_mnk_apply(ismcts_mnk_state* s, uint32_t move)
     if (!s) return ISMCTS_ERR_INVALID;
     uint64_t stones[8];
     MnkGame g;
-    g.bind(stones, 1);
+    g.bind(stones, 1, 0);
     g.load(s);
     // mnkgame.cpp:41-43: the move must be one of the remaining cells
     if (move >= (uint32_t)s->m * s->n || g.occupied_by(0, move) || g.occupied_by(1, move)) return ISMCTS_ERR_ILLEGAL_MOVE;

@@ -40,8 +40,9 @@ struct GoofGame {
     uint32_t hidden_bid;    // observer 1: player 0's bid is still to be drawn
     uint32_t current_prize, move0, move1, score0, score1, player, draw_prize;
 
-    ISMCTS_DEV void bind(uint64_t*, uint32_t) { hidden_bid = 0; next_prize = 0; player = 2; draw_prize = 1; prizes = 0; }
-    ISMCTS_DEV void rebind(uint64_t*, uint32_t) {}
+    ISMCTS_DEV void bind(uint64_t*, uint32_t, uint32_t) { hidden_bid = 0; next_prize = 0; player = 2; draw_prize = 1; prizes = 0; }
+    ISMCTS_DEV void rebind(uint64_t*, uint32_t, uint32_t) {}
+    ISMCTS_DEV static void init_block(uint32_t, uint32_t) {}   // no per-block tables
 
     ISMCTS_DEV static uint32_t value(uint32_t rank) { return rank == 12u ? 1u : rank + 2u; } // goofspiel.cpp:17-36
 

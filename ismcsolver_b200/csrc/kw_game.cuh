@@ -2,12 +2,22 @@
 //
 // Device mirror of ISMCTS::Game<Card> for the reference's KnockoutWhist
 // (test/common/knockoutwhist.{h,cpp}; rules restated in SURVEY.md appendix B).
-// One GPU thread owns one game.  Card sets are 64-bit masks (bit id =
-// rank + 13*suit, card.h:38-41); the seven hands live in shared memory, one
-// 8-byte column per thread, everything else in registers.  Sets of players and
-// the trick counts are kept as one 4-bit field per player, so that the
-// round-end bookkeeping (knock-outs, most tricks, ties, deal sizes) is a
+// One GPU thread owns one game.  Everything but the cards lives in registers;
+// sets of players and the trick counts are one 4-bit field per player, so that
+// the round-end bookkeeping (knock-outs, most tricks, ties, deal sizes) is a
 // handful of word-parallel operations instead of loops over the players.
+//
+// Cards.  Moves of the tree and of the C ABI are card ids rank + 13 * suit
+// (card.h:38-41); inside the game a card is the code (suit << 4) | rank.  A HAND
+// is seven places (the game never deals more than seven cards): `list` holds the
+// code put on each place (one byte per place), `held` has bit 8 * suit + place
+// set while the card on that place has not been played.  A card is put on the
+// first place after the last card still held, a played card leaves its place
+// empty.  With this layout the cards that follow suit are one shift and mask of
+// `held`, "the j-th legal card" is a look-up in a 128-entry table of bit
+// positions, and playing a card clears one bit — the default policy (simulate,
+// solverbase.h:36-43) never searches a 64-bit set.  The hands live in shared
+// memory, one column per thread.
 //
 // The chance events the reference resolves inside its functions — the
 // determinisation shuffle (cloneAndRandomise, knockoutwhist.cpp:56-76), the
@@ -18,12 +28,14 @@
 // a PILE, a byte array in shared memory that starts in ascending card order: a
 // uniformly random card leaves it and the last card of the pile takes its place
 // (the steps of a Fisher-Yates shuffle of which only the dealt cards are kept; a
-// shuffle followed by "take the first k" has the same distribution).  The stream
-// is aligned to a Philox block before and after every sequence of chance events
-// and at the start of the rollout (philox.cuh), so that the lanes of a warp, which
-// go through the phases of an iteration together (lane_search.cuh), generate their
-// blocks in the same steps: chance_phase() and play_phase() below keep the current
-// block in registers.
+// shuffle followed by "take the first k" has the same distribution).  The default
+// policy plays the j-th legal card in place order (any fixed order is uniform).
+// The stream is aligned to a Philox block before and after every sequence of
+// chance events and at the start of the rollout (philox.cuh), so that the lanes of
+// a warp, which go through the phases of an iteration together (lane_search.cuh),
+// generate their blocks in the same steps: chance_phase() and play_phase() below
+// keep the current block in registers.  oracle/oracle.c states all of this
+// sequentially (hand_append, okw_rollout_move, pile_draw, rng_align).
 #pragma once
 
 #include "devdefs.cuh"
@@ -36,23 +48,27 @@ namespace ismcts {
 // registers want it, with the determinisation (cloneAndRandomise for the root's
 // player to move) already set up as a pending deal.  Built once per position.
 struct alignas(16) KwPrepared {
-    uint64_t hand_obs;   // the observer's own hand (the only one it can see)
+    uint64_t list_obs;   // the observer's own hand (the only one it can see): the places ...
+    uint32_t held_obs;   // ... and which of them hold a card
     uint32_t sizes;      // 4 bits per player: cards to deal back (0 for the observer)
     uint32_t observer;
     uint32_t player, dealer, trump, tricks_left, request_trump;
     uint32_t alive4, tricks, best;
     uint32_t trick_len, lead_suit, win_key, win_player;
     uint32_t pile_n;     // unknown cards + the other players' hands: the pile to deal back from
-    uint32_t pad;
-    uint64_t pile[7];    // its cards, one per byte, ascending
+    uint64_t pile[7];    // its cards (codes), one per byte, ascending
 };
 static_assert(sizeof(KwPrepared) == 128, "eight 16-byte loads");
 
 struct KwGame {
     static constexpr uint32_t kGameId = ISMCTS_GAME_KW;
     static constexpr uint32_t kMoveStride = 64;
+    static constexpr uint32_t kPlaces = 7;                          // cards a hand can hold
     static constexpr uint32_t kPileWords = 7;                       // 52 cards, one per byte
-    static constexpr uint32_t kHandWords = ISMCTS_KW_MAX_PLAYERS + kPileWords; // 8-byte words of per-thread scratch
+    // 8-byte words of per-thread scratch: one list per player, the pile, `held` of the players (4 bytes each)
+    static constexpr uint32_t kPileRow = ISMCTS_KW_MAX_PLAYERS;
+    static constexpr uint32_t kHeldRow = kPileRow + kPileWords;
+    static constexpr uint32_t kHandWords = kHeldRow + (ISMCTS_KW_MAX_PLAYERS + 1) / 2;
     static constexpr uint32_t kMaxPlayers = ISMCTS_KW_MAX_PLAYERS;
     static constexpr uint32_t kMaxLegal = ISMCTS_KW_CARDS;
     static constexpr uint32_t kMaxDepth = 208;  // plies are bounded by 6 + players * 28 (gametest.cpp:166-178)
@@ -64,11 +80,12 @@ struct KwGame {
 
     static constexpr uint64_t kFullDeck = (uint64_t(1) << 52) - 1;
     static constexpr uint64_t kTrumpChoices = uint64_t(1) | (uint64_t(1) << 13) | (uint64_t(1) << 26) | (uint64_t(1) << 39);
-    static constexpr uint64_t kSuit = 0x1FFF;
     static constexpr uint32_t kOnes = 0x1111111u; // bit 4p for each of the 7 players
 
-    // per-thread scratch: the hand of player p is hands[p * stride], the pile follows the hands
+    // per-thread scratch: 8-byte word w is hands[w * stride]; `held` of player p is held[p * stride]
+    // (rows of 4-byte words behind the 8-byte rows)
     uint64_t* hands;
+    uint32_t* held;
     uint32_t stride;
 
     uint32_t player, dealer, trump, tricks_left, request_trump;
@@ -84,27 +101,120 @@ struct KwGame {
     uint32_t pile_n;     // kDeal: cards left in the pile
     uint32_t deal_player, deal_left; // kDeal: who is being dealt to and how many more cards
     uint32_t need;       // kDeal: 4 bits per player, cards the players after deal_player still get
+    uint32_t deal_place; // kDeal: the place the next card of deal_player goes to
+    uint32_t deal_held;  // kDeal: `held` of deal_player while it is being dealt, stored when it is complete
 
-    ISMCTS_DEV uint64_t hand(uint32_t p) const { return hands[p * stride]; }
-    ISMCTS_DEV void set_hand(uint32_t p, uint64_t v) { hands[p * stride] = v; }
+    // ---- cards and hands
+
+    ISMCTS_DEV static uint32_t code_of_id(uint32_t id)
+    {
+        const uint32_t suit = (id * 79u) >> 10;   // id / 13, exact below 64
+        return (suit << 4) | (id - 13u * suit);
+    }
+    ISMCTS_DEV static uint32_t id_of_code(uint32_t code) { return (code >> 4) * 13u + (code & 15u); }
+    // the places that hold a card, whatever its suit
+    ISMCTS_DEV static uint32_t occupied(uint32_t held)
+    {
+        held |= held >> 16;
+        held |= held >> 8;
+        return held & 0x7Fu;
+    }
+    // one past the last place that holds a card
+    ISMCTS_DEV static uint32_t top_place(uint32_t held) { return 32u - clz32(occupied(held)); }
+    ISMCTS_DEV static uint32_t code_at(uint64_t list, uint32_t place) { return (uint32_t)(list >> (8u * place)) & 0xFFu; }
+
+    ISMCTS_DEV uint64_t list_of(uint32_t p) const { return hands[p * stride]; }
+    ISMCTS_DEV void set_list(uint32_t p, uint64_t v) { hands[p * stride] = v; }
+    ISMCTS_DEV uint32_t held_of(uint32_t p) const { return held[p * stride]; }
+    ISMCTS_DEV void set_held(uint32_t p, uint32_t v) { held[p * stride] = v; }
+
+    // a hand as a set of card ids (the C ABI, the tree)
+    ISMCTS_DEV static uint64_t ids_of(uint64_t list, uint32_t places)
+    {
+        uint64_t out = 0;
+        for (; places; places &= places - 1) out |= (uint64_t)1 << id_of_code(code_at(list, ctz32(places)));
+        return out;
+    }
+    ISMCTS_DEV uint64_t hand_ids(uint32_t p) const { return ids_of(list_of(p), occupied(held_of(p))); }
+    // ... and the other way round: ascending ids on the places 0, 1, ... (a hand holds at most seven cards)
+    ISMCTS_DEV void set_hand_ids(uint32_t p, uint64_t ids)
+    {
+        uint64_t list = 0;
+        uint32_t held = 0, place = 0;
+        for (ids &= kFullDeck; ids && place < kPlaces; ids &= ids - 1, ++place) {
+            const uint32_t code = code_of_id(ctz64(ids));
+            list |= (uint64_t)code << (8u * place);
+            held |= 1u << (8u * (code >> 4) + place);
+        }
+        set_list(p, list);
+        set_held(p, held);
+    }
 
     // card i of the pile: byte i % 8 of word i / 8
     ISMCTS_DEV uint8_t* pile_at(uint32_t i) const
     {
-        return reinterpret_cast<uint8_t*>(hands + (ISMCTS_KW_MAX_PLAYERS + (i >> 3)) * stride) + (i & 7u);
+        return reinterpret_cast<uint8_t*>(hands + (kPileRow + (i >> 3)) * stride) + (i & 7u);
     }
-    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) { hands[(ISMCTS_KW_MAX_PLAYERS + i) * stride] = v; }
-    // the cards left in the pile as a set (after a deal: the cards nobody holds)
+    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) { hands[(kPileRow + i) * stride] = v; }
+    // the cards left in the pile as a set of ids (after a deal: the cards nobody holds)
     ISMCTS_DEV uint64_t pile_set() const
     {
         uint64_t out = 0;
-        for (uint32_t i = 0; i < pile_n; ++i) out |= (uint64_t)1 << *pile_at(i);
+        for (uint32_t i = 0; i < pile_n; ++i) out |= (uint64_t)1 << id_of_code(*pile_at(i));
         return out;
     }
+    // word i of the full deck in ascending order (codes)
+    ISMCTS_DEV static constexpr uint64_t deck_word(uint32_t i)
+    {
+        uint64_t w = 0;
+        for (uint32_t b = 0; b < 8; ++b) {
+            const uint32_t id = 8u * i + b;
+            if (id < ISMCTS_KW_CARDS) w |= (uint64_t)(((id / 13u) << 4) | (id % 13u)) << (8u * b);
+        }
+        return w;
+    }
 
-    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; mode = kPlay; }
+    // The place of the j-th set bit of a 7-bit set, 3 bits per j: the table behind "the j-th legal
+    // card".  In shared memory on the device (filled by init_block at the start of a kernel).
+    ISMCTS_DEV static uint32_t place_table_entry(uint32_t set)
+    {
+        uint32_t entry = 0, j = 0;
+        for (uint32_t place = 0; place < kPlaces; ++place)
+            if ((set >> place) & 1u) entry |= place << (3u * j++);
+        return entry;
+    }
+    ISMCTS_DEV static uint32_t* place_table()
+    {
+#if defined(__CUDA_ARCH__)
+        __shared__ uint32_t table[128];
+        return table;
+#else
+        static uint32_t table[128];
+        static bool ready = false;
+        if (!ready) { for (uint32_t s = 0; s < 128; ++s) table[s] = place_table_entry(s); ready = true; }
+        return table;
+#endif
+    }
+    // Called by every thread of a block before any game runs (followed by a block barrier).
+    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t* table = place_table();
+        for (uint32_t s = thread; s < 128; s += threads) table[s] = place_table_entry(s);
+#else
+        (void)thread; (void)threads;
+#endif
+    }
+
+    // `scratch`: the block's scratch, rows of `scratch_stride` 8-byte words; this game owns column `column`
+    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column) { rebind(scratch, scratch_stride, column); mode = kPlay; }
     // the same columns again (a copy of the game whose pointers the compiler can follow)
-    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride) { hands = scratch; stride = scratch_stride; }
+    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column)
+    {
+        hands = scratch + column;
+        held = reinterpret_cast<uint32_t*>(scratch + kHeldRow * scratch_stride) + column;
+        stride = scratch_stride;
+    }
 
     // bit p -> bit 4p
     ISMCTS_DEV static uint32_t spread4(uint32_t bits)
@@ -125,16 +235,18 @@ struct KwGame {
     // winning one if it has the same suit and a higher rank, or another suit that
     // is trumps.  With (trumps 2, suit led 1, other 0) * 16 + rank that is
     // "strictly larger key" (the first card of a trick is of the suit led).
-    ISMCTS_DEV uint32_t card_key(uint32_t card, uint32_t lead) const
+    ISMCTS_DEV void fold_trick(uint32_t index, uint32_t who, uint32_t code)
     {
-        const uint32_t suit = card / 13u, rank = card - 13u * suit;
-        return rank + (suit == trump ? 32u : suit == lead ? 16u : 0u);
+        const uint32_t suit = code >> 4, rank = code & 15u;
+        if (index == 0) lead_suit = suit;
+        const uint32_t key = rank + (suit == trump ? 32u : suit == lead_suit ? 16u : 0u);
+        if (index == 0 || key > win_key) { win_key = key; win_player = who; }
     }
 
     // Loads a root position (knockoutwhist.h:36-48 as POD).
     ISMCTS_DEV void load(const Root* r)
     {
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) set_hand(p, r->hands[p]);
+        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) set_hand_ids(p, r->hands[p]);
         player = r->player; dealer = r->dealer; trump = r->trump;
         tricks_left = r->tricks_left; request_trump = r->request_trump;
         alive4 = spread4(r->alive_mask);
@@ -146,26 +258,21 @@ struct KwGame {
         }
         trick_len = r->trick_len;
         lead_suit = 0; win_key = 0; win_player = 0;
-        for (uint32_t i = 0; i < trick_len; ++i) fold_trick(i, r->trick_player[i], r->trick_card[i]);
+        for (uint32_t i = 0; i < trick_len; ++i) fold_trick(i, r->trick_player[i], code_of_id(r->trick_card[i]));
         mode = kPlay; tied = 0; pile_n = 0; deal_player = 0; deal_left = 0; need = 0;
-    }
-
-    ISMCTS_DEV void fold_trick(uint32_t index, uint32_t who, uint32_t card)
-    {
-        if (index == 0) lead_suit = card / 13u;
-        const uint32_t key = card_key(card, lead_suit);
-        if (index == 0 || key > win_key) { win_key = key; win_player = who; }
+        deal_place = 0; deal_held = 0;
     }
 
     // The start of an iteration for `observer` = the root's player to move.
     ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t* scratch)
     {
         KwGame g;
-        g.bind(scratch, 1);
+        g.bind(scratch, 1, 0);
         g.load(r);
         Prepared p;
         p.observer = g.player;
-        p.hand_obs = g.hand(g.player);
+        p.list_obs = g.list_of(g.player);
+        p.held_obs = g.held_of(g.player);
         // cloneAndRandomise, knockoutwhist.cpp:56-76: what the observer cannot see (the unknown
         // cards and the other players' hands) is pooled and dealt back to the other players,
         // ascending id, keeping their hand sizes
@@ -173,16 +280,16 @@ struct KwGame {
         p.sizes = 0;
         for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q) {
             if (!((g.alive4 >> (4 * q)) & 1u) || q == g.player) continue;
-            unseen |= g.hand(q);
-            p.sizes |= popc64(g.hand(q)) << (4 * q);
+            const uint64_t ids = g.hand_ids(q);
+            unseen |= ids;
+            p.sizes |= popc64(ids) << (4 * q);
         }
         for (uint32_t i = 0; i < kPileWords; ++i) p.pile[i] = 0;
         p.pile_n = 0;
         for (unseen &= kFullDeck; unseen; unseen &= unseen - 1) {
-            p.pile[p.pile_n >> 3] |= (uint64_t)ctz64(unseen) << (8 * (p.pile_n & 7u));
+            p.pile[p.pile_n >> 3] |= (uint64_t)code_of_id(ctz64(unseen)) << (8 * (p.pile_n & 7u));
             ++p.pile_n;
         }
-        p.pad = 0;
         if (!g.legal().any()) g.tricks_left = 0;      // a finished game, however it is recorded
         p.player = g.player; p.dealer = g.dealer; p.trump = g.trump; p.tricks_left = g.tricks_left;
         p.request_trump = g.request_trump; p.alive4 = g.alive4; p.tricks = g.tricks; p.best = g.best;
@@ -193,9 +300,10 @@ struct KwGame {
     // Clone of the root with the determinisation pending (sosolver.h:46).
     ISMCTS_DEV void start(const Prepared* q)
     {
-        for (uint32_t i = 0; i < ISMCTS_KW_MAX_PLAYERS; ++i) set_hand(i, 0);
+        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) set_held(p, 0);      // nobody holds a card ...
         for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, q->pile[i]);
-        set_hand(q->observer, q->hand_obs);
+        set_list(q->observer, q->list_obs);                                        // ... but the observer
+        set_held(q->observer, q->held_obs);
         player = q->player; dealer = q->dealer; trump = q->trump; tricks_left = q->tricks_left;
         request_trump = q->request_trump; alive4 = q->alive4; tricks = q->tricks; best = q->best;
         trick_len = q->trick_len; lead_suit = q->lead_suit; win_key = q->win_key; win_player = q->win_player;
@@ -222,37 +330,74 @@ struct KwGame {
         return ctz32(above ? above : alive4) >> 2;
     }
 
-    // validMoves, knockoutwhist.cpp:122-136 (empty <=> the game is over).  Only
+    // The places of the legal cards of a hand: those that follow suit if there are any, else all.
+    ISMCTS_DEV uint32_t legal_places(uint32_t held) const
+    {
+        const uint32_t follow = (held >> (8u * lead_suit)) & 0x7Fu;
+        return trick_len != 0 && follow != 0 ? follow : occupied(held);
+    }
+
+    // validMoves, knockoutwhist.cpp:122-136, as card ids (empty <=> the game is over).  Only
     // meaningful while no chance event is pending.
     ISMCTS_DEV Mask legal() const
     {
         if (request_trump) return Mask{kTrumpChoices};
-        const uint64_t h = hand(player);
-        if (trick_len == 0 || popc64(h) < 2) return Mask{h};
-        const uint64_t follow = h & (kSuit << (13u * lead_suit));
-        return Mask{follow ? follow : h};
+        return Mask{ids_of(list_of(player), legal_places(held_of(player)))};
     }
 
     // getResult * 2, knockoutwhist.cpp:117-120: the first remaining player has won.
     ISMCTS_DEV uint32_t result2(uint32_t who) const { return 4u * who == ctz32(alive4) ? 2u : 0u; }
     ISMCTS_DEV uint32_t outcome() const { return ctz32(alive4) >> 2; }
 
+    // ---- chance events
+
+    // The hand the next cards go to: what deal_player holds stays, the first free place is the one
+    // after the last card held.  The cards go straight to their places in shared memory (a played
+    // card stays on its place, only `held` says whether a place counts), `held` is stored when the
+    // hand is complete.
+    ISMCTS_DEV void open_hand()
+    {
+        deal_held = held_of(deal_player);
+        deal_place = top_place(deal_held);
+    }
+    ISMCTS_DEV void close_hand() { set_held(deal_player, deal_held); }
+    ISMCTS_DEV void deal_card(uint32_t code)
+    {
+        if (deal_place < kPlaces) {
+            reinterpret_cast<uint8_t*>(hands + deal_player * stride)[deal_place] = (uint8_t)code;
+            deal_held |= 1u << (8u * (code >> 4) + deal_place);
+            ++deal_place;
+        }
+    }
+
     // Starts dealing from the pile: `sizes` holds 4 bits per player, the number of cards each
     // gets, ascending id.
     ISMCTS_DEV void begin_deal(uint32_t sizes)
     {
-        if (sizes == 0) { mode = kPlay; return; }
-        const uint32_t shift = ctz32(sizes) & ~3u;
-        deal_player = shift >> 2;
-        deal_left = (sizes >> shift) & 15u;
-        need = sizes & ~(15u << shift);
-        mode = kDeal;
+        need = sizes;
+        next_hand();
+    }
+
+    // The next player to deal to, or the end of the deal.
+    ISMCTS_DEV void next_hand()
+    {
+        if (need) {
+            const uint32_t shift = ctz32(need) & ~3u;
+            deal_player = shift >> 2;
+            deal_left = (need >> shift) & 15u;
+            need &= ~(15u << shift);
+            mode = kDeal;
+            open_hand();
+        } else {
+            mode = kPlay;
+        }
     }
 
     // deal, knockoutwhist.cpp:138-152: a fresh deck, tricks_left cards to each remaining player.
     ISMCTS_DEV void start_deal()
     {
-        for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, 0x0706050403020100ull + i * 0x0808080808080808ull);
+#pragma unroll
+        for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, deck_word(i));
         pile_n = ISMCTS_KW_CARDS;
         begin_deal(alive4 * tricks_left);
     }
@@ -284,22 +429,9 @@ struct KwGame {
     ISMCTS_DEV uint32_t take_from_pile(uint32_t j)
     {
         uint8_t* at = pile_at(j);
-        const uint32_t card = *at;
+        const uint32_t code = *at;
         *at = *pile_at(--pile_n);
-        return card;
-    }
-
-    // After the last card of a hand: the next player to deal to, or the end of the deal.
-    ISMCTS_DEV void next_hand()
-    {
-        if (need) {
-            const uint32_t shift = ctz32(need) & ~3u;
-            deal_player = shift >> 2;
-            deal_left = (need >> shift) & 15u;
-            need &= ~(15u << shift);
-        } else {
-            mode = kPlay;
-        }
+        return code;
     }
 
     // The tie-break: the j-th of the tied players has won the round and calls trumps
@@ -316,38 +448,56 @@ struct KwGame {
     ISMCTS_DEV void chance_draw(uint32_t j)
     {
         if (mode == kDeal) {
-            set_hand(deal_player, hand(deal_player) | (uint64_t)1 << take_from_pile(j));
-            if (--deal_left == 0) next_hand();
+            deal_card(take_from_pile(j));
+            if (--deal_left == 0) { close_hand(); next_hand(); }
         } else {
             break_tie(j);
         }
     }
 
-    // doMove, knockoutwhist.cpp:95-115 (no chance event pending).
-    ISMCTS_DEV void play(uint32_t b)
+    // ---- moves
+
+    // The card on `place` of the hand (`list`, `held`) of the player to move is played:
+    // doMove, knockoutwhist.cpp:95-115.  Leaves the hand of the next player to move in (`list`, `held`).
+    ISMCTS_DEV void play_place(uint32_t place, uint64_t& list, uint32_t& held)
     {
-        if (request_trump) {
-            trump = b / 13u;
-            request_trump = 0;
-            player = next_alive(dealer);
-            return;
-        }
-        set_hand(player, hand(player) & ~((uint64_t)1 << b));
-        fold_trick(trick_len, player, b);
+        const uint32_t code = code_at(list, place);
+        set_held(player, held & ~(1u << (8u * (code >> 4) + place)));
+        fold_trick(trick_len, player, code);
         ++trick_len;
         player = next_alive(player);
-        if (trick_len == popc32(alive4)) { // finishTrick, :155-161
+        if (trick_len == popc32(alive4)) {                // finishTrick, :155-161
             tricks += 1u << (4 * win_player);
             const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
             best = taken > best ? taken : best;
             trick_len = 0;
             player = win_player;
         }
-        if (hand(player) == 0) finish_round();
+        list = list_of(player);
+        held = held_of(player);
+        if (held == 0) finish_round();
     }
 
-    // A move of the tree or of a caller (no chance event pending).
-    ISMCTS_DEV void step(uint32_t b) { play(b); }
+    // doMove for a card id (a move of the tree or of a caller; no chance event pending).
+    ISMCTS_DEV void play(uint32_t id)
+    {
+        if (request_trump) {
+            trump = id / 13u;
+            request_trump = 0;
+            player = next_alive(dealer);
+            return;
+        }
+        uint64_t list = list_of(player);
+        uint32_t held = held_of(player);
+        const uint32_t code = code_of_id(id);
+        uint32_t place = 0;
+        for (uint32_t rest = (held >> (8u * (code >> 4))) & 0x7Fu; rest; rest &= rest - 1) {
+            place = ctz32(rest);
+            if (code_at(list, place) == code) break;
+        }
+        play_place(place, list, held);
+    }
+    ISMCTS_DEV void step(uint32_t id) { play(id); }
 
     // ---- phases of the lock-step loop (lane_search.cuh): the same transitions as chance_draw() and
     // play() with the same draws, as tight loops over ONE kind of step.  Every lane that takes
@@ -381,8 +531,7 @@ struct KwGame {
     };
 
     // Every pending chance event of the warp: the tie-break (it starts a deal), then the deal
-    // card by card.  The hand being dealt is collected in registers and stored when it is
-    // complete.  `active`: the lane takes part in the search (it may have nothing pending).
+    // card by card.  `active`: the lane takes part in the search (it may have nothing pending).
     template <class Rng>
     ISMCTS_DEV void chance_phase(Rng& rng, bool active)
     {
@@ -391,83 +540,55 @@ struct KwGame {
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;
         BlockWords words;
         uint32_t draws = 0;
-        uint64_t hand_acc = 0;
         for (uint32_t t = 0; warp_any(active && mode != kPlay); ++t) {
             words.turn(rng, first_block, t);
 #pragma unroll
             for (uint32_t half = 0; half < 2; ++half) {
                 if (active && mode != kPlay) {
-                    const uint32_t j = words.below(chance_count());
                     ++draws;
-                    if (mode == kDeal) {
-                        hand_acc |= (uint64_t)1 << take_from_pile(j);
-                        if (--deal_left == 0) {
-                            set_hand(deal_player, hand(deal_player) | hand_acc);
-                            hand_acc = 0;
-                            next_hand();
-                        }
-                    } else {
-                        break_tie(j);
-                    }
+                    chance_draw(words.below(chance_count()));
                 }
             }
         }
         if (mine) { rng.phase_end(first_block, draws); rng.align(); }
     }
 
-    // One rollout move with the hand `h` of the player to move; leaves the hand of the next player
-    // to move in `h`.
-    ISMCTS_DEV void rollout_step(BlockWords& words, uint64_t& h)
+    // One move of the default policy (simulate, solverbase.h:36-43) from the hand (`list`, `held`)
+    // of the player to move: uniform over validMoves(), knockoutwhist.cpp:122-136.
+    ISMCTS_DEV void rollout_step(BlockWords& words, const uint32_t* table, uint64_t& list, uint32_t& held)
     {
         if (request_trump) {
-            // the round winner calls trumps: one of the four suits
-            play(13u * words.below(4));
+            play(13u * words.below(4));                   // the round winner calls trumps: one of the four suits
+            list = list_of(player);
+            held = held_of(player);
         } else {
-            // validMoves, knockoutwhist.cpp:122-136: follow suit if possible (with one card in
-            // hand both cases give the same set)
-            const uint64_t follow = h & (kSuit << (13u * lead_suit));
-            const uint64_t set = trick_len != 0 && follow != 0 ? follow : h;
-            const uint32_t b = kth_bit64(set, words.below(popc64(set)));
-            // doMove, :95-115
-            set_hand(player, h & ~((uint64_t)1 << b));
-            // trickWinner as in fold_trick(), with the suit by a multiplication (exact below 64)
-            const uint32_t suit = (b * 79u) >> 10, rank = b - 13u * suit;
-            if (trick_len == 0) lead_suit = suit;
-            const uint32_t key = rank + (suit == trump ? 32u : suit == lead_suit ? 16u : 0u);
-            if (trick_len == 0 || key > win_key) { win_key = key; win_player = player; }
-            ++trick_len;
-            player = next_alive(player);
-            if (trick_len == popc32(alive4)) {            // finishTrick, :155-161
-                tricks += 1u << (4 * win_player);
-                const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
-                best = taken > best ? taken : best;
-                trick_len = 0;
-                player = win_player;
-            }
+            const uint32_t places = legal_places(held);
+            const uint32_t j = words.below(popc32(places));
+            play_place((table[places] >> (3u * j)) & 7u, list, held);
         }
-        h = hand(player);
-        if (h == 0) finish_round();
     }
 
-    // Rollout moves (simulate, solverbase.h:36-43) for the lanes with `rolling` until their
-    // round ends (a chance event becomes pending) or their game does.  `plies` counts the moves.
+    // Rollout moves for the lanes with `rolling` until their round ends (a chance event becomes
+    // pending) or their game does.  `plies` counts the moves.
     template <class Rng>
     ISMCTS_DEV void play_phase(Rng& rng, bool rolling, uint32_t& plies)
     {
         const bool mine = rolling && mode == kPlay && tricks_left != 0;
         if (!warp_any(mine)) return;
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;   // the rollout and every round start a block
+        const uint32_t* table = place_table();
         BlockWords words;
         uint32_t draws = 0;
         // the hand of the player to move (lanes that do not take part may hold no game at all)
-        uint64_t h = mine ? hand(player) : 0;
+        uint64_t list = mine ? list_of(player) : 0;
+        uint32_t held = mine ? held_of(player) : 0;
         for (uint32_t t = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++t) {
             words.turn(rng, first_block, t);
 #pragma unroll
             for (uint32_t half = 0; half < 2; ++half) {
                 if (rolling && mode == kPlay && tricks_left != 0) {
                     ++draws;
-                    rollout_step(words, h);
+                    rollout_step(words, table, list, held);
                 }
             }
         }

@@ -399,17 +399,17 @@ struct Lane {
     // are registers, between two tree operations.
     ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !g.chance_pending() && !g.terminal(); }
 
-    // `scratch`, `ring`: the per-thread columns the game and the stream are bound to, handed in again so
+    // `scratch` + `column`, `ring`: the columns the game and the stream are bound to, handed in again so
     // that the copies the loops work on address them as shared memory (the lane object itself lives in
     // local memory, where a pointer is just 64 bits).
-    ISMCTS_DEV void run(uint32_t gtid, uint64_t* scratch, uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride)
+    ISMCTS_DEV void run(uint32_t gtid, uint64_t* scratch, uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride)
     {
         for (;;) {
             if (!warp_any(phase != kDone)) break;
             {
                 Game hot = g;
                 LaneRng stream = rng;
-                hot.rebind(scratch, scratch_stride);
+                hot.rebind(scratch, scratch_stride, column);
                 stream.ring = ring; stream.stride = ring_stride;
                 const uint32_t ph = phase;
                 uint32_t moves = 0;
@@ -461,13 +461,13 @@ struct Lane {
 // statistics of the root children are collected afterwards by collect_roots.
 template <class Game, class Slot, uint32_t kKind, bool kShared>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
-                                 uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
+                                 uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
     using Mask = typename Game::Mask;
     using L = Lane<Game, Slot, kKind, kShared>;
     L lane(P);
     lane.path = path;
-    lane.g.bind(scratch, scratch_stride);
+    lane.g.bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
     lane.iteration_stride = 1; lane.node_counter = nullptr;
     lane.root_children = Mask::none();
@@ -496,7 +496,7 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
         }
         if (lane.budget_left()) lane.start_iteration();
     }
-    lane.run(gtid, scratch, scratch_stride, ring, ring_stride);
+    lane.run(gtid, scratch, scratch_stride, column, ring, ring_stride);
     if (!valid) return;
     if (kShared) atomic_add_u64(P.iters_done + tree_index, lane.done);
     else P.iters_done[tree_index] = lane.done;
@@ -545,12 +545,12 @@ ISMCTS_DEV void collect_roots(const SearchParams& P, uint32_t index)
 // Determinise + rollout only: playout `gtid % per_position` of position `gtid / per_position`.
 template <class Game>
 ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, uint32_t per_position, uint64_t* scratch,
-                             uint32_t scratch_stride, uint32_t* ring, uint32_t ring_stride)
+                             uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride)
 {
     using Mask = typename Game::Mask;
     Lane<Game, SlotUcb<Mask>, kPlayout> lane(P);
     lane.path = nullptr;
-    lane.g.bind(scratch, scratch_stride);
+    lane.g.bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
     lane.iteration_stride = 1; lane.node_counter = nullptr;
     lane.root_children = Mask::none();
@@ -561,7 +561,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
         lane.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
         lane.start_iteration();
     }
-    lane.run(gtid, scratch, scratch_stride, ring, ring_stride);
+    lane.run(gtid, scratch, scratch_stride, column, ring, ring_stride);
 }
 
 } // namespace ismcts

@@ -29,9 +29,11 @@ struct MnkGame {
     uint32_t m, n, k, player;
     int32_t res2;     // 2 * m_result from player 0's view, -1 while running
 
-    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { stones = scratch; stride = scratch_stride; }
+    // `scratch`: the block's scratch, rows of `scratch_stride` 8-byte words; this game owns column `column`
+    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column) { stones = scratch + column; stride = scratch_stride; }
+    ISMCTS_DEV static void init_block(uint32_t, uint32_t) {}   // no per-block tables
     // the same columns again (a copy of the game whose pointers the compiler can follow)
-    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride) { stones = scratch; stride = scratch_stride; }
+    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column) { stones = scratch + column; stride = scratch_stride; }
 
     ISMCTS_DEV void load(const Root* r)
     {

@@ -43,7 +43,7 @@ struct PhantomGame : MnkGame {
     ISMCTS_DEV uint64_t& avail_word(uint32_t p, uint32_t i) const { return stones[(8 + p * 4 + i) * stride]; }
     ISMCTS_DEV uint64_t& pool_word(uint32_t i) const { return stones[(16 + i) * stride]; }
 
-    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride) { MnkGame::bind(scratch, scratch_stride); replay_left = 0; over = 1; }
+    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column) { MnkGame::bind(scratch, scratch_stride, column); replay_left = 0; over = 1; }
 
     ISMCTS_DEV Mask avail_of(uint32_t p) const { return Mask{{avail_word(p, 0), avail_word(p, 1), avail_word(p, 2), avail_word(p, 3)}}; }
 

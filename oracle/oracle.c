@@ -94,10 +94,35 @@ static void rng_restart(rng* r) { r->d = 0; r->left = 0; }
 typedef struct okw {
     int np, player, dealer, trump, tricks_left, request_trump;
     int alive[7], tricks[7];
-    unsigned char hand[7][52];
+    unsigned char hand[7][52];          /* the hands as sets ... */
+    unsigned char hcard[7][7], hlive[7][7]; /* ... and as the seven places of a hand: the card put there, and whether it is still held */
     unsigned char unknown[52];
     int trick_n, trick_player[7], trick_card[7];
 } okw;
+
+/* The places of a hand.  A hand holds at most seven cards (the game never deals more); a card is
+ * put on the first place after the last card still held, a played card leaves its place empty.
+ * The default policy picks "the j-th legal card in place order", which costs the kernels a table
+ * look-up instead of a search through a 64-bit set; any fixed order gives the same distribution
+ * as the reference's RandomElement (utility.h:69-83). */
+static void hand_clear(okw* g, int p)
+{
+    memset(g->hand[p], 0, sizeof g->hand[p]);
+    memset(g->hlive[p], 0, sizeof g->hlive[p]);
+}
+static void hand_append(okw* g, int p, int card)
+{
+    int k = 0;
+    for (int i = 0; i < 7; ++i) if (g->hlive[p][i]) k = i + 1;
+    if (k >= 7) return;
+    g->hcard[p][k] = (unsigned char)card; g->hlive[p][k] = 1; g->hand[p][card] = 1;
+}
+static void hand_remove(okw* g, int p, int card)
+{
+    for (int i = 0; i < 7; ++i)
+        if (g->hlive[p][i] && g->hcard[p][i] == card) { g->hlive[p][i] = 0; break; }
+    g->hand[p][card] = 0;
+}
 
 static void okw_from_pod(okw* g, const ismcts_kw_state* s)
 {
@@ -107,7 +132,7 @@ static void okw_from_pod(okw* g, const ismcts_kw_state* s)
     for (int p = 0; p < 7; ++p) {
         g->alive[p] = (s->alive_mask >> p) & 1;
         g->tricks[p] = s->tricks_taken[p];
-        for (int c = 0; c < 52; ++c) g->hand[p][c] = (unsigned char)((s->hands[p] >> c) & 1);
+        for (int c = 0; c < 52; ++c) if ((s->hands[p] >> c) & 1) hand_append(g, p, c);   /* ascending */
     }
     for (int c = 0; c < 52; ++c) g->unknown[c] = (unsigned char)((s->unknown >> c) & 1);
     g->trick_n = s->trick_len;
@@ -197,7 +222,7 @@ static void okw_deal(okw* g, rng* r)
     for (int p = 0; p < g->np; ++p) {
         if (!g->alive[p]) continue;
         for (int j = 0; j < g->tricks_left; ++j)
-            g->hand[p][pile_draw(&pile, r)] = 1;
+            hand_append(g, p, pile_draw(&pile, r));
     }
     memset(g->unknown, 0, sizeof g->unknown);
     for (int i = 0; i < pile.n; ++i) g->unknown[pile.card[i]] = 1;
@@ -234,6 +259,21 @@ static int okw_legal(const okw* g, uint16_t* moves)
     }
     for (int c = 0; c < 52; ++c) if (hand[c]) moves[n++] = (uint16_t)c;
     return n;
+}
+
+/* The move of the default policy (simulate, solverbase.h:36-43): uniform over validMoves(), taken as
+ * the j-th legal card in place order (the round winner's call of trumps: the j-th suit). */
+static int okw_rollout_move(const okw* g, rng* r)
+{
+    if (g->request_trump) return 13 * (int)rng_below(r, 4);
+    const int p = g->player;
+    int place[7], n = 0;
+    if (g->trick_n > 0) {
+        const int lead = g->trick_card[0] / 13;
+        for (int i = 0; i < 7; ++i) if (g->hlive[p][i] && g->hcard[p][i] / 13 == lead) place[n++] = i;
+    }
+    if (n == 0) for (int i = 0; i < 7; ++i) if (g->hlive[p][i]) place[n++] = i;
+    return g->hcard[p][place[rng_below(r, (uint32_t)n)]];
 }
 
 /* trickWinner, knockoutwhist.cpp:182-196. */
@@ -286,7 +326,7 @@ static int okw_apply(okw* g, int move, rng* r)
     g->trick_player[g->trick_n] = g->player;
     g->trick_card[g->trick_n] = move;
     g->trick_n++;
-    g->hand[g->player][move] = 0;
+    hand_remove(g, g->player, move);
     g->player = okw_next(g, g->player);
     if (g->trick_n == okw_alive_count(g)) { /* finishTrick, :155-161 */
         const int w = okw_trick_winner(g);
@@ -315,14 +355,15 @@ static void okw_determinise(okw* g, int observer, rng* r)
     int size[7] = {0};
     for (int p = 0; p < g->np; ++p) {
         if (!g->alive[p] || p == observer) continue;
-        for (int c = 0; c < 52; ++c) if (g->hand[p][c]) { pool[c] = 1; size[p]++; g->hand[p][c] = 0; }
+        for (int c = 0; c < 52; ++c) if (g->hand[p][c]) { pool[c] = 1; size[p]++; }
+        hand_clear(g, p);
     }
     okw_pile pile;
     pile_from_set(&pile, pool);
     rng_align(r);
     for (int p = 0; p < g->np; ++p) {
         if (!g->alive[p] || p == observer) continue;
-        for (int j = 0; j < size[p]; ++j) g->hand[p][pile_draw(&pile, r)] = 1;
+        for (int j = 0; j < size[p]; ++j) hand_append(g, p, pile_draw(&pile, r));
     }
     rng_align(r);
 }
@@ -857,7 +898,7 @@ static uint32_t og_rollout(ogame* g, rng* r)
     int n;
     if (g->kind == ISMCTS_GAME_KW) rng_align(r);   /* Knockout Whist: the rollout starts a Philox block */
     while ((n = og_legal(g, mv)) > 0) {
-        og_apply(g, mv[rng_below(r, (uint32_t)n)], r);
+        og_apply(g, g->kind == ISMCTS_GAME_KW ? okw_rollout_move(&g->u.kw, r) : mv[rng_below(r, (uint32_t)n)], r);
         ++plies;
     }
     return plies;

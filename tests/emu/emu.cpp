@@ -161,7 +161,7 @@ uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_t itera
     WarpScratch<Game> ws(1);
     // thread `iteration` of a launch with per_position > iteration plays playout `iteration` of record 0
     FiberWarp warp(1);
-    warp.run([&](uint32_t) { lane_playout<Game>(P, iteration, true, 0x7FFFFFFFu, ws.scratch.data(), 1, ws.ring.data(), 1); });
+    warp.run([&](uint32_t) { lane_playout<Game>(P, iteration, true, 0x7FFFFFFFu, ws.scratch.data(), 1, 0, ws.ring.data(), 1); });
     return out;
 }
 
@@ -195,7 +195,7 @@ int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos,
     WarpScratch<Game> ws(width);
     FiberWarp warp(width);
     warp.run([&](uint32_t lane) {
-        lane_tree_search<Game, Slot, kKind, false>(P, lane, true, ws.scratch.data() + lane, width, ws.ring.data() + lane, width,
+        lane_tree_search<Game, Slot, kKind, false>(P, lane, true, ws.scratch.data(), width, lane, ws.ring.data() + lane, width,
                                                    ws.path.data() + (size_t)lane * Game::kMaxDepth);
     });
     for (uint32_t i = 0; i < width; ++i) if (it[i] != iterations) return 6;
@@ -246,7 +246,7 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     WarpScratch<Game> ws(width);
     FiberWarp warp(width);
     warp.run([&](uint32_t lane) {
-        lane_tree_search<Game, Slot, kKind, true>(P, lane, true, ws.scratch.data() + lane, width, ws.ring.data() + lane, width,
+        lane_tree_search<Game, Slot, kKind, true>(P, lane, true, ws.scratch.data(), width, lane, ws.ring.data() + lane, width,
                                                   ws.path.data() + (size_t)lane * Game::kMaxDepth);
     });
     *done_out = it[0];
