@@ -348,7 +348,13 @@ static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_d
         ctx->launches += 3;
     } else {
         if (so && ucb) {
-            launch_search_variant<Game, SlotUcb<Mask>, kSO, Game::kGameId == ISMCTS_GAME_KW>(ctx, P, grid);
+            if constexpr (Game::kGameId == ISMCTS_GAME_KW) {
+                // positions with at most four players: the same prepared roots, less scratch per lane
+                if (d->flags & ISMCTS_FLAG_KW_MAX4) launch_search_variant<KwGame4, SlotUcb<Mask>, kSO, true>(ctx, P, grid);
+                else launch_search_variant<Game, SlotUcb<Mask>, kSO, true>(ctx, P, grid);
+            } else {
+                launch_search_variant<Game, SlotUcb<Mask>, kSO, false>(ctx, P, grid);
+            }
             collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
         } else if (so) {
             launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);

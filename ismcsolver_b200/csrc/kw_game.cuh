@@ -60,15 +60,18 @@ struct alignas(16) KwPrepared {
 };
 static_assert(sizeof(KwPrepared) == 128, "eight 16-byte loads");
 
-struct KwGame {
+// kSeats: the highest player id + 1 the scratch has room for (7; 4 for positions whose records say so:
+// less shared memory per block leaves more of it to L1).
+template <uint32_t kSeats>
+struct KwGameT {
     static constexpr uint32_t kGameId = ISMCTS_GAME_KW;
     static constexpr uint32_t kMoveStride = 64;
     static constexpr uint32_t kPlaces = 7;                          // cards a hand can hold
     static constexpr uint32_t kPileWords = 7;                       // 52 cards, one per byte
     // 8-byte words of per-thread scratch: one list per player, the pile, `held` of the players (4 bytes each)
-    static constexpr uint32_t kPileRow = ISMCTS_KW_MAX_PLAYERS;
+    static constexpr uint32_t kPileRow = kSeats;
     static constexpr uint32_t kHeldRow = kPileRow + kPileWords;
-    static constexpr uint32_t kHandWords = kHeldRow + (ISMCTS_KW_MAX_PLAYERS + 1) / 2;
+    static constexpr uint32_t kHandWords = kHeldRow + (kSeats + 1) / 2;
     static constexpr uint32_t kMaxPlayers = ISMCTS_KW_MAX_PLAYERS;
     static constexpr uint32_t kMaxLegal = ISMCTS_KW_CARDS;
     static constexpr uint32_t kMaxDepth = 208;  // plies are bounded by 6 + players * 28 (gametest.cpp:166-178)
@@ -246,7 +249,7 @@ struct KwGame {
     // Loads a root position (knockoutwhist.h:36-48 as POD).
     ISMCTS_DEV void load(const Root* r)
     {
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) set_hand_ids(p, r->hands[p]);
+        for (uint32_t p = 0; p < kSeats; ++p) set_hand_ids(p, r->hands[p]);
         player = r->player; dealer = r->dealer; trump = r->trump;
         tricks_left = r->tricks_left; request_trump = r->request_trump;
         alive4 = spread4(r->alive_mask);
@@ -266,7 +269,7 @@ struct KwGame {
     // The start of an iteration for `observer` = the root's player to move.
     ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t* scratch)
     {
-        KwGame g;
+        KwGameT g;
         g.bind(scratch, 1, 0);
         g.load(r);
         Prepared p;
@@ -278,7 +281,7 @@ struct KwGame {
         // ascending id, keeping their hand sizes
         uint64_t unseen = r->unknown;
         p.sizes = 0;
-        for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q) {
+        for (uint32_t q = 0; q < kSeats; ++q) {
             if (!((g.alive4 >> (4 * q)) & 1u) || q == g.player) continue;
             const uint64_t ids = g.hand_ids(q);
             unseen |= ids;
@@ -300,7 +303,7 @@ struct KwGame {
     // Clone of the root with the determinisation pending (sosolver.h:46).
     ISMCTS_DEV void start(const Prepared* q)
     {
-        for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) set_held(p, 0);      // nobody holds a card ...
+        for (uint32_t p = 0; p < kSeats; ++p) set_held(p, 0);                     // nobody holds a card ...
         for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, q->pile[i]);
         set_list(q->observer, q->list_obs);                                        // ... but the observer
         set_held(q->observer, q->held_obs);
@@ -596,5 +599,8 @@ struct KwGame {
         if (mine) rng.phase_end(first_block, draws);
     }
 };
+
+using KwGame = KwGameT<ISMCTS_KW_MAX_PLAYERS>;
+using KwGame4 = KwGameT<4>;   // positions with at most four players (ISMCTS_FLAG_KW_MAX4)
 
 } // namespace ismcts
