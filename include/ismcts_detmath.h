@@ -46,7 +46,8 @@
 ISMCTS_HD double ismcts_ucb_value(uint32_t score2, uint32_t visits, double ln_avail, double exploration)
 {
     const double v = (double)visits;
-    const double x = ISMCTS_DDIV(ISMCTS_DMUL((double)score2, 0.5), v);
+    /* 0 / v is exactly 0: many nodes have no win yet, and a zero numerator takes the slow path of the GPU's division */
+    const double x = score2 ? ISMCTS_DDIV(ISMCTS_DMUL((double)score2, 0.5), v) : 0.0;
     const double e = ISMCTS_DMUL(exploration, ISMCTS_DSQRT(ISMCTS_DDIV(ln_avail, v)));
     return ISMCTS_DADD(x, e);
 }

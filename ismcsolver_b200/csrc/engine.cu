@@ -50,8 +50,12 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
 template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams P)
+__global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams params)
 {
+    // the tree operations are real calls that reach the parameters through a pointer: one copy per block
+    // in shared memory instead of one per thread in local memory
+    __shared__ SearchParams P;
+    if (threadIdx.x == 0) P = params;
     extern __shared__ uint64_t smem[];
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
     Game::init_block(threadIdx.x, blockDim.x);
