@@ -216,13 +216,17 @@ struct Lane {
             uint32_t best = 0;
             double best_u = -1.0;
             chosen.created = 0xFFFFFFFFu;
+            // copies: what is read through `this` or P would be read again after every store to a node
+            const TreePool<S> pool = tree;
+            const double* const ln = P.ln_table;
+            const double exploration = P.exploration;
             for (Mask rest = legal; rest.any();) {
                 const uint32_t move = rest.pop_lowest();
                 S c;
-                const uint32_t ci = tree.find(parent, move, c);
+                const uint32_t ci = pool.find(parent, move, c);
                 c.avail += 1;
-                tree.slots[ci].avail = c.avail;
-                const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[c.avail], P.exploration);
+                pool.slots[ci].avail = c.avail;
+                const double u = ismcts_ucb_value(c.score2, c.visits, ln[c.avail], exploration);
                 if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
             }
             return best;
