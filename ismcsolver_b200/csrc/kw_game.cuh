@@ -462,22 +462,39 @@ struct KwGameT {
 
     // The card on `place` of the hand (`list`, `held`) of the player to move is played:
     // doMove, knockoutwhist.cpp:95-115.  Leaves the hand of the next player to move in (`list`, `held`).
+    // (The state is read before the first store and written after the last load: when the game lives in
+    // memory — a tree operation — the compiler must assume that a store to a hand changes it.)
     ISMCTS_DEV void play_place(uint32_t place, uint64_t& list, uint32_t& held)
     {
+        uint64_t* const lists = hands;
+        uint32_t* const helds = this->held;
+        const uint32_t pitch = stride, alive = alive4, trumps = trump;
+        uint32_t who = player, len = trick_len, lead = lead_suit, key_won = win_key, who_won = win_player;
+        uint32_t taken_all = tricks, most = best;
+
         const uint32_t code = code_at(list, place);
-        set_held(player, held & ~(1u << (8u * (code >> 4) + place)));
-        fold_trick(trick_len, player, code);
-        ++trick_len;
-        player = next_alive(player);
-        if (trick_len == popc32(alive4)) {                // finishTrick, :155-161
-            tricks += 1u << (4 * win_player);
-            const uint32_t taken = (tricks >> (4 * win_player)) & 15u;
-            best = taken > best ? taken : best;
-            trick_len = 0;
-            player = win_player;
+        const uint32_t suit = code >> 4, rank = code & 15u;
+        helds[who * pitch] = held & ~(1u << (8u * suit + place));
+        // trickWinner, :182-196, as in fold_trick()
+        if (len == 0) lead = suit;
+        const uint32_t key = rank + (suit == trumps ? 32u : suit == lead ? 16u : 0u);
+        if (len == 0 || key > key_won) { key_won = key; who_won = who; }
+        ++len;
+        {   // nextPlayer, :83-88
+            const uint32_t above = alive & ~((2u << (4 * who)) - 1u);
+            who = ctz32(above ? above : alive) >> 2;
         }
-        list = list_of(player);
-        held = held_of(player);
+        if (len == popc32(alive)) {                       // finishTrick, :155-161
+            taken_all += 1u << (4 * who_won);
+            const uint32_t taken = (taken_all >> (4 * who_won)) & 15u;
+            most = taken > most ? taken : most;
+            len = 0;
+            who = who_won;
+        }
+        list = lists[who * pitch];
+        held = helds[who * pitch];
+        player = who; trick_len = len; lead_suit = lead; win_key = key_won; win_player = who_won;
+        tricks = taken_all; best = most;
         if (held == 0) finish_round();
     }
 

@@ -114,6 +114,16 @@ struct Lane {
 
     ISMCTS_DEV explicit Lane(const SearchParams& p) : P(p) {}
 
+    // A draw of a tree operation (the loops of the phases draw for themselves).
+    ISMCTS_DEV uint32_t draw_below(uint32_t n)
+    {
+        if constexpr (game_is_phased<Game>(0)) return rng.below_direct(n); else return rng.below(n);
+    }
+    ISMCTS_DEV uint32_t draw_word()
+    {
+        if constexpr (game_is_phased<Game>(0)) return rng.word_direct(); else return rng.word();
+    }
+
     ISMCTS_DEV void start_iteration()
     {
         rng.begin_iteration(first_iteration + done * iteration_stride);
@@ -255,7 +265,7 @@ struct Lane {
                 sum = ISMCTS_DADD(sum, val[i]);
             }
             const double rest_mass = ISMCTS_DSUB(1.0, ISMCTS_DMUL((double)K, e_t));
-            const double x = ISMCTS_DMUL((double)rng.word(), 1.0 / 4294967296.0);
+            const double x = ISMCTS_DMUL((double)draw_word(), 1.0 / 4294967296.0);
             double cum = 0.0;
             uint32_t pick = K - 1;
             bool picked = false;
@@ -289,7 +299,7 @@ struct Lane {
             uint32_t move = 0, chosen_slot = 0;
             Slot chosen;
             chosen.child_mask = Mask::none();
-            if (expand) move = untried.kth(rng.below(untried.count()));   // expand, sosolver.h:63-71
+            if (expand) move = untried.kth(draw_below(untried.count()));  // expand, sosolver.h:63-71
             else chosen_slot = select_child(node[a], legal, chosen, move);
             for (uint32_t t = 0; t < kTrees; ++t) {
                 if (kMulti && !((tree_players >> t) & 1u)) continue;
@@ -369,7 +379,7 @@ struct Lane {
                 const Mask untried = legal.minus(kids);
                 const bool expand = untried.any();
                 uint32_t move = 0, chosen = 0, stored = who;
-                if (expand) move = untried.kth(rng.below(untried.count()));
+                if (expand) move = untried.kth(draw_below(untried.count()));
                 else chosen = select_child_shared<Slot>(node[a], legal, move, stored);
                 for (uint32_t t = 0; t < kTrees; ++t) {
                     if (kMulti && !((tree_players >> t) & 1u)) continue;

@@ -106,6 +106,28 @@ struct LaneRng {
         return (uint32_t)(p >> 32);
     }
 
+    // The same two draws without the ring: the block of word d is generated in registers.  For the
+    // streams of games whose loops keep their blocks in registers anyway (Knockout Whist: the only draws
+    // left are the few of the tree operations) — a stream uses either these or the ring functions.
+    ISMCTS_DEV uint32_t word_direct()
+    {
+        uint32_t b[4];
+        block(d >> 2, b);
+        const uint32_t i = d & 3u;
+        ++d;
+        next_block = (d + 3u) >> 2;   // (the ring stays empty)
+        left = 0;
+        return i == 0 ? b[0] : i == 1 ? b[1] : i == 2 ? b[2] : b[3];
+    }
+    ISMCTS_DEV uint32_t below_direct(uint32_t n)
+    {
+        if (left == 0) { w = word_direct(); left = kDrawsPerWord; }
+        const uint64_t p = (uint64_t)w * n;
+        w = (uint32_t)p;
+        --left;
+        return (uint32_t)(p >> 32);
+    }
+
     // On to the start of the next block (a no-op at the start of a block with nothing used).
     ISMCTS_DEV void align()
     {
