@@ -410,10 +410,10 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
         max_it = (((uint64_t)1 << (log2cap - 1)) - 1) / per_lane;
     }
     const size_t pool_need = ((size_t)tables << log2cap) * slot;
-    {
+    if (pool_need > ctx->pool_bytes) {                    // (asking the driver costs milliseconds: only when the pool grows)
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-        if (pool_need > ctx->pool_bytes && pool_need > free_b + ctx->pool_bytes)
+        if (pool_need > free_b + ctx->pool_bytes)
             return fail(ctx, ISMCTS_ERR_CAPACITY, "node pool does not fit device memory: need " + std::to_string(pool_need) + " bytes");
     }
     rc = ensure(ctx, ctx->pool, ctx->pool_bytes, pool_need);
