@@ -34,7 +34,8 @@ constexpr int kBlock = 128;
 template <class Game>
 constexpr size_t block_smem()
 {
-    return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + LaneRng::kRingWords * sizeof(uint32_t));
+    // (a game whose loops keep their Philox blocks in registers needs no ring: more of the SM's memory stays L1)
+    return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + (game_is_phased<Game>(0) ? 0 : LaneRng::kRingWords) * sizeof(uint32_t));
 }
 
 // Root records -> the register image every iteration starts from (one thread per position).
