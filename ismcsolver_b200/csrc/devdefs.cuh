@@ -91,6 +91,30 @@ ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 #endif
 
+// ---- the scratch of games that find it themselves (Knockout Whist, kw_game.cuh)
+//
+// Such a game holds no pointer to its scratch: it is the column of the thread in the block's dynamic shared
+// memory, found from the thread index alone.  Host builds (the C ABI's game helpers, tests/emu) install the
+// scratch of the "block" and the index of the thread that is running before they call game code.
+constexpr uint32_t kWarpLanes = 32;
+constexpr uint32_t kBlockLanes = 128;      // threads per block of every kernel that runs games (engine.cu: kBlock)
+inline thread_local uint64_t* g_host_block_scratch = nullptr;
+inline thread_local uint32_t g_host_block_lane = 0;
+#if defined(__CUDA_ARCH__)
+ISMCTS_DEV uint64_t* block_scratch()
+{
+    extern __shared__ uint64_t ismcts_dynamic_smem[];
+    return ismcts_dynamic_smem;
+}
+ISMCTS_DEV uint32_t block_lane() { return threadIdx.x; }
+ISMCTS_DEV void warp_sync() { __syncwarp(); }
+#else
+ISMCTS_DEV uint64_t* block_scratch() { return g_host_block_scratch; }
+ISMCTS_DEV uint32_t block_lane() { return g_host_block_lane; }
+// (tests/emu: a vote is the only point where its fibers switch, so a warp_sync() must be one)
+ISMCTS_DEV void warp_sync() { (void)warp_any(false); }
+#endif
+
 // Index of the k-th (0-based) set bit of w; k < popc(w).
 ISMCTS_DEV uint32_t kth_bit32(uint32_t w, uint32_t k)
 {

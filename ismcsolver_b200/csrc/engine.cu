@@ -32,25 +32,26 @@ constexpr int kBlock = 128;
 // 8-byte column per thread) followed by the per-thread Philox rings (one 4-byte
 // column per thread): column layouts are bank-conflict free.
 template <class Game>
-constexpr size_t block_smem()
+__host__ __device__ constexpr size_t block_smem()
 {
     // (a game whose loops keep their Philox blocks in registers needs no ring: more of the SM's memory stays L1)
     return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + (game_is_phased<Game>(0) ? 0 : LaneRng::kRingWords) * sizeof(uint32_t));
 }
 
 // Root records -> the register image every iteration starts from (one thread per position).
+// (Games that find their scratch themselves — Knockout Whist — use the block's dynamic shared memory.)
 template <class Game>
 __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::Prepared* prepared, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t scratch[Game::kHandWords];
+    uint64_t scratch[game_home_in_scratch<Game>(0) ? 1 : Game::kHandWords];
     Game::prepare(roots + i, prepared + i, scratch);
 }
 
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
-template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
+template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks, bool kLaneSm = false>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams params)
 {
     // the tree operations are real calls that reach the parameters through a pointer: one copy per block
@@ -64,7 +65,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
-    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, smem, kBlock, threadIdx.x, ring, kBlock, path);
+    // kLaneSm: the lane objects live in shared memory behind the scratch (their fields are what the tree
+    // operations work on; on the stack they are local memory, most of which misses L1)
+    using L = Lane<Game, Slot, kKind, kShared>;
+    constexpr size_t kScratchBytes = block_smem<Game>();
+    constexpr uint32_t kLaneBytes = lane_stride<L>();
+    void* lane_mem = kLaneSm ? reinterpret_cast<unsigned char*>(smem) + kScratchBytes + (size_t)threadIdx.x * kLaneBytes : nullptr;
+    lane_tree_search<Game, Slot, kKind, kShared, kLaneSm>(P, gtid, gtid < lanes, smem, kBlock, threadIdx.x, ring, kBlock, path, lane_mem);
 }
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
@@ -301,7 +308,8 @@ static int launch_prepare(ismcts_ctx* ctx, const void* d_roots, uint32_t n)
 {
     int rc = ensure(ctx, ctx->prepared, ctx->prepared_bytes, (size_t)n * sizeof(typename Game::Prepared));
     if (rc) return rc;
-    prepare_kernel<Game><<<(n + 127) / 128, 128, 0, ctx->stream>>>((const typename Game::Root*)d_roots,
+    const size_t smem = game_home_in_scratch<Game>(0) ? (size_t)128 * Game::kHandWords * sizeof(uint64_t) : 0;
+    prepare_kernel<Game><<<(n + 127) / 128, 128, smem, ctx->stream>>>((const typename Game::Root*)d_roots,
                                                                   (typename Game::Prepared*)ctx->prepared, n);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
@@ -314,11 +322,25 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
     const size_t smem = block_smem<Game>();
     if constexpr (kTuned) {
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
+        if (std::getenv("ISMCTS_LANE_SHARED")) {
+            // experiment: lane objects in shared memory
+            const size_t smem_l = smem + (size_t)kBlock * lane_stride<Lane<Game, Slot, kKind, false>>();
+            auto go = [&](auto kernel) {
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+                kernel<<<grid, kBlock, smem_l, ctx->stream>>>(P);
+            };
+            switch (ctx->min_blocks) {
+            case 4: go(search_kernel<Game, Slot, kKind, false, 4, true>); return;
+            case 5: go(search_kernel<Game, Slot, kKind, false, 5, true>); return;
+            default: go(search_kernel<Game, Slot, kKind, false, 6, true>); return;
+            }
+        }
         switch (ctx->min_blocks) {
         case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        default:
+            search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         }
     } else {
         search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);

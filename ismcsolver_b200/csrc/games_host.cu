@@ -22,6 +22,15 @@ namespace {
 constexpr uint32_t kDealTree = 0xFFFFFFFFu, kDealIteration = 0xFFFFFFFFu;
 constexpr uint32_t kApplyTree = 0xFFFFFFFEu;
 
+// The scratch of ONE host-side Knockout Whist game (the game code finds it through devdefs.cuh: block_scratch).
+struct KwHostScratch {
+    uint64_t words[(size_t)KwGame::kHandWords * kBlockLanes];
+    KwHostScratch() { std::memset(words, 0, sizeof words); g_host_block_scratch = words; g_host_block_lane = 0; }
+    ~KwHostScratch() { g_host_block_scratch = nullptr; }
+    KwHostScratch(const KwHostScratch&) = delete;
+    KwHostScratch& operator=(const KwHostScratch&) = delete;
+};
+
 void kw_store(const KwGame& g, uint64_t unknown, ismcts_kw_state* s)
 {
     for (uint32_t p = 0; p < ISMCTS_KW_MAX_PLAYERS; ++p) s->hands[p] = g.hand_ids(p);
@@ -46,9 +55,8 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     const uint32_t np = num_players < 2 ? 2 : num_players > 7 ? 7 : num_players;
     std::memset(out, 0, sizeof *out);
     out->num_players = (uint8_t)np;
-    uint64_t hands[KwGame::kHandWords] = {0};
+    KwHostScratch scratch;
     KwGame g;
-    g.bind(hands, 1, 0);
     ismcts_kw_state blank;
     std::memset(&blank, 0, sizeof blank);
     blank.num_players = (uint8_t)np; blank.alive_mask = (uint8_t)((1u << np) - 1u);
@@ -58,10 +66,11 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     LaneRng rng;
     rng.init(seed, stream, kDealTree, ring, 1);
     rng.begin_iteration(kDealIteration);
-    g.start_deal();
-    while (g.chance_pending()) g.chance_draw(rng.below(g.chance_count()));
+    KwGame::Deal deal;
+    g.start_deal(deal);
+    while (g.chance_pending()) g.chance_draw(deal, rng.below(g.chance_count(deal)));
     // one of the remaining cards is turned up for trumps and leaves the unknown set (:50-53)
-    uint64_t unknown = g.pile_set();
+    uint64_t unknown = g.pile_set(deal);
     rng.align();
     const uint32_t up = kth_bit64(unknown, rng.below(popc64(unknown)));
     unknown &= ~((uint64_t)1 << up);
@@ -73,9 +82,8 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
 uint64_t ismcts_kw_legal(const ismcts_kw_state* s)
 {
     if (!s) return 0;
-    uint64_t hands[KwGame::kHandWords];
+    KwHostScratch scratch;
     KwGame g;
-    g.bind(hands, 1, 0);
     g.load(s);
     return g.legal().w;
 }
@@ -84,9 +92,8 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
 {
     if (!s) return ISMCTS_ERR_INVALID;
     if (move >= ISMCTS_KW_CARDS) return ISMCTS_ERR_ILLEGAL_MOVE;
-    uint64_t hands[KwGame::kHandWords];
+    KwHostScratch scratch;
     KwGame g;
-    g.bind(hands, 1, 0);
     g.load(s);
     // doMove accepts any card while trumps are requested (knockoutwhist.cpp:97-102); otherwise
     // the card must be in the mover's hand or std::out_of_range is thrown (:105-109)
@@ -102,9 +109,10 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
     if (g.chance_pending()) {
         // the chance events of a round end (tie-break, deal) start a Philox block, and so does what follows
         rng.align();
-        while (g.chance_pending()) g.chance_draw(rng.below(g.chance_count()));
+        KwGame::Deal deal{};
+        while (g.chance_pending()) g.chance_draw(deal, rng.below(g.chance_count(deal)));
         rng.align();
-        unknown = g.pile_set(); // deal, :138-152: the undealt rest of the deck is unknown to everyone
+        unknown = g.pile_set(deal); // deal, :138-152: the undealt rest of the deck is unknown to everyone
     }
     if (draw_counter) *draw_counter = rng.consumed();
     // the cards of the trick in progress (m_currentTrick)

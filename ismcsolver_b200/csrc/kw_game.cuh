@@ -36,8 +36,17 @@
 // generate their blocks in the same steps: chance_phase() and play_phase() below
 // keep the current block in registers.  oracle/oracle.c states all of this
 // sequentially (hand_append, okw_rollout_move, pile_draw, rng_align).
+//
+// Where a game lives.  The game object is 14 words and holds no pointer: its scratch (hands,
+// pile) is the column of its thread in the block's scratch (devdefs.cuh: block_scratch).
+// While a deal is in progress its state is a separate `Deal` that lives in the loop that deals
+// (chance_phase); between two such loops no deal is ever in progress.  That makes the pile dead
+// whenever the tree operations of the search run, and the search keeps the game objects of the
+// 32 lanes of a warp in the memory of the warp's piles meanwhile (home(): 32 x 56 bytes = the seven
+// pile rows), i.e. in shared memory at no cost, instead of in the thread's local memory.
 #pragma once
 
+#include <type_traits>
 #include "devdefs.cuh"
 #include "bitset.cuh"
 #include "../../include/ismcts_b200.h"
@@ -60,18 +69,61 @@ struct alignas(16) KwPrepared {
 };
 static_assert(sizeof(KwPrepared) == 128, "eight 16-byte loads");
 
+// The place of the j-th set bit of a 7-bit set, 3 bits per j: the table behind "the j-th legal
+// card".  In shared memory on the device (filled by init_block at the start of a kernel); one table
+// for every form of the game.
+struct KwPlaceTable {
+    ISMCTS_DEV static uint32_t entry(uint32_t set)
+    {
+        uint32_t e = 0, j = 0;
+        for (uint32_t place = 0; place < 7; ++place)
+            if ((set >> place) & 1u) e |= place << (3u * j++);
+        return e;
+    }
+    ISMCTS_DEV static uint32_t* table()
+    {
+#if defined(__CUDA_ARCH__)
+        __shared__ uint32_t t[128];
+        return t;
+#else
+        static uint32_t t[128];
+        static bool ready = false;
+        if (!ready) { for (uint32_t s = 0; s < 128; ++s) t[s] = entry(s); ready = true; }
+        return t;
+#endif
+    }
+    // Called by every thread of a block before any game runs (followed by a block barrier).
+    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads)
+    {
+#if defined(__CUDA_ARCH__)
+        uint32_t* t = table();
+        for (uint32_t s = thread; s < 128; s += threads) t[s] = entry(s);
+#else
+        (void)thread; (void)threads;
+#endif
+    }
+};
+
 // kSeats: the highest player id + 1 the scratch has room for (7; 4 for positions whose records say so:
 // less shared memory per block leaves more of it to L1).
-template <uint32_t kSeats>
-struct KwGameT {
+// kCarry: a copy of the game that carries the addresses of its scratch with it (the loops of the phases work
+// on such copies, `Hot`: the addresses are values the compiler keeps or derives from the thread index as it
+// likes); the game proper (`Core`) finds its scratch from the thread index whenever it needs it.
+struct KwNoAddresses {};
+struct KwAddresses { uint64_t* hands_; uint32_t* helds_; uint64_t* pile_; };
+
+template <uint32_t kSeats, bool kCarry = false>
+struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
+    using Core = KwGameT<kSeats, false>;
+    using Hot = KwGameT<kSeats, true>;
     static constexpr uint32_t kGameId = ISMCTS_GAME_KW;
     static constexpr uint32_t kMoveStride = 64;
     static constexpr uint32_t kPlaces = 7;                          // cards a hand can hold
     static constexpr uint32_t kPileWords = 7;                       // 52 cards, one per byte
     // 8-byte words of per-thread scratch: one list per player, the pile, `held` of the players (4 bytes each)
-    static constexpr uint32_t kPileRow = kSeats;
-    static constexpr uint32_t kHeldRow = kPileRow + kPileWords;
-    static constexpr uint32_t kHandWords = kHeldRow + (kSeats + 1) / 2;
+    static constexpr uint32_t kHeldRow = kSeats;
+    static constexpr uint32_t kPileRow = kHeldRow + (kSeats + 1) / 2;   // (the last rows: home())
+    static constexpr uint32_t kHandWords = kPileRow + kPileWords;
     static constexpr uint32_t kMaxPlayers = ISMCTS_KW_MAX_PLAYERS;
     static constexpr uint32_t kMaxLegal = ISMCTS_KW_CARDS;
     static constexpr uint32_t kMaxDepth = 208;  // plies are bounded by 6 + players * 28 (gametest.cpp:166-178)
@@ -79,17 +131,28 @@ struct KwGameT {
     using Root = ismcts_kw_state;
     using Prepared = KwPrepared;
 
-    enum Mode : uint32_t { kPlay = 0, kDeal = 1, kTie = 2 };
+    enum Mode : uint32_t { kPlay = 0, kDeal = 1, kTie = 2, kStart = 3 };   // kStart: the determinisation has not begun (start())
 
     static constexpr uint64_t kFullDeck = (uint64_t(1) << 52) - 1;
     static constexpr uint64_t kTrumpChoices = uint64_t(1) | (uint64_t(1) << 13) | (uint64_t(1) << 26) | (uint64_t(1) << 39);
     static constexpr uint32_t kOnes = 0x1111111u; // bit 4p for each of the 7 players
 
-    // per-thread scratch: 8-byte word w is hands[w * stride]; `held` of player p is held[p * stride]
-    // (rows of 4-byte words behind the 8-byte rows)
-    uint64_t* hands;
-    uint32_t* held;
-    uint32_t stride;
+    // The scratch of this thread's game.  Lists and `held`: rows of one column per thread of the block —
+    // list of player p = hands()[p * kStride], `held` of player p = helds()[p * kStride] (rows of 4-byte words
+    // behind the rows of lists).  The pile: seven rows of one column per lane of the warp, warp after warp
+    // behind those (pile word w = pile()[w * kPileStride]), so that the piles of a warp are one piece of
+    // memory (home()).
+    static constexpr uint32_t kStride = kBlockLanes;
+    static constexpr uint32_t kPileStride = kWarpLanes;
+    ISMCTS_DEV static uint64_t* hands_of(uint64_t* scratch, uint32_t column) { return scratch + column; }
+    ISMCTS_DEV static uint32_t* helds_of(uint64_t* scratch, uint32_t column) { return reinterpret_cast<uint32_t*>(scratch + kHeldRow * kStride) + column; }
+    ISMCTS_DEV static uint64_t* pile_of(uint64_t* scratch, uint32_t column)
+    {   // the column of the thread's lane in the piles of its warp
+        return scratch + kPileRow * kStride + column + (column >> 5) * ((kPileWords - 1) * kPileStride);
+    }
+    ISMCTS_DEV uint64_t* hands() const { if constexpr (kCarry) return this->hands_; else return hands_of(block_scratch(), block_lane()); }
+    ISMCTS_DEV uint32_t* helds() const { if constexpr (kCarry) return this->helds_; else return helds_of(block_scratch(), block_lane()); }
+    ISMCTS_DEV uint64_t* pile() const { if constexpr (kCarry) return this->pile_; else return pile_of(block_scratch(), block_lane()); }
 
     uint32_t player, dealer, trump, tricks_left, request_trump;
     uint32_t alive4;     // bit 4p: player p is still in (m_players)
@@ -101,11 +164,36 @@ struct KwGameT {
     uint32_t win_player; // who played that card
     uint32_t mode;       // pending chance event, if any
     uint32_t tied;       // kTie: the players tied on most tricks (bit 4p)
-    uint32_t pile_n;     // kDeal: cards left in the pile
-    uint32_t deal_player, deal_left; // kDeal: who is being dealt to and how many more cards
-    uint32_t need;       // kDeal: 4 bits per player, cards the players after deal_player still get
-    uint32_t deal_place; // kDeal: the place the next card of deal_player goes to
-    uint32_t deal_held;  // kDeal: `held` of deal_player while it is being dealt, stored when it is complete
+
+    // A deal in progress (mode == kDeal): lives in the loop that deals, see the head of this file.
+    struct Deal {
+        uint32_t pile_n;                  // cards left in the pile
+        uint32_t deal_player, deal_left;  // who is being dealt to and how many more cards
+        uint32_t need;                    // 4 bits per player, cards the players after deal_player still get
+        uint32_t deal_place;              // the place the next card of deal_player goes to
+        uint32_t deal_held;               // `held` of deal_player while it is being dealt, stored when it is complete
+    };
+
+    // Where the search keeps this thread's game while no deal can be in progress: the memory of the
+    // warp's piles (seven rows of 32 x 8 bytes), one 56-byte object per lane — 32 objects fill the
+    // piles of a warp exactly, so the objects of a block are one array.  The lanes of a warp must pass
+    // a warp_sync() between their last use of the pile and the first use of these objects, and back.
+    ISMCTS_DEV static Core* home() { return reinterpret_cast<Core*>(block_scratch() + kPileRow * kStride) + block_lane(); }
+    static constexpr bool kHomeInScratch = true;
+
+    // the state of another copy of the game
+    template <bool kOther>
+    ISMCTS_DEV void take(const KwGameT<kSeats, kOther>& o)
+    {
+        player = o.player; dealer = o.dealer; trump = o.trump; tricks_left = o.tricks_left; request_trump = o.request_trump;
+        alive4 = o.alive4; tricks = o.tricks; best = o.best; trick_len = o.trick_len; lead_suit = o.lead_suit;
+        win_key = o.win_key; win_player = o.win_player; mode = o.mode; tied = o.tied;
+    }
+    KwGameT() = default;
+    template <bool kOther, bool kMine = kCarry, class = std::enable_if_t<kMine != kOther>>
+    ISMCTS_DEV explicit KwGameT(const KwGameT<kSeats, kOther>& o) { take(o); }
+    template <bool kOther, bool kMine = kCarry, class = std::enable_if_t<kMine != kOther>>
+    ISMCTS_DEV KwGameT& operator=(const KwGameT<kSeats, kOther>& o) { take(o); return *this; }
 
     // ---- cards and hands
 
@@ -126,10 +214,10 @@ struct KwGameT {
     ISMCTS_DEV static uint32_t top_place(uint32_t held) { return 32u - clz32(occupied(held)); }
     ISMCTS_DEV static uint32_t code_at(uint64_t list, uint32_t place) { return (uint32_t)(list >> (8u * place)) & 0xFFu; }
 
-    ISMCTS_DEV uint64_t list_of(uint32_t p) const { return hands[p * stride]; }
-    ISMCTS_DEV void set_list(uint32_t p, uint64_t v) { hands[p * stride] = v; }
-    ISMCTS_DEV uint32_t held_of(uint32_t p) const { return held[p * stride]; }
-    ISMCTS_DEV void set_held(uint32_t p, uint32_t v) { held[p * stride] = v; }
+    ISMCTS_DEV uint64_t list_of(uint32_t p) const { return hands()[p * kStride]; }
+    ISMCTS_DEV void set_list(uint32_t p, uint64_t v) const { hands()[p * kStride] = v; }
+    ISMCTS_DEV uint32_t held_of(uint32_t p) const { return helds()[p * kStride]; }
+    ISMCTS_DEV void set_held(uint32_t p, uint32_t v) const { helds()[p * kStride] = v; }
 
     // a hand as a set of card ids (the C ABI, the tree)
     ISMCTS_DEV static uint64_t ids_of(uint64_t list, uint32_t places)
@@ -156,14 +244,14 @@ struct KwGameT {
     // card i of the pile: byte i % 8 of word i / 8
     ISMCTS_DEV uint8_t* pile_at(uint32_t i) const
     {
-        return reinterpret_cast<uint8_t*>(hands + (kPileRow + (i >> 3)) * stride) + (i & 7u);
+        return reinterpret_cast<uint8_t*>(pile() + (i >> 3) * kPileStride) + (i & 7u);
     }
-    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) { hands[(kPileRow + i) * stride] = v; }
+    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) const { pile()[i * kPileStride] = v; }
     // the cards left in the pile as a set of ids (after a deal: the cards nobody holds)
-    ISMCTS_DEV uint64_t pile_set() const
+    ISMCTS_DEV uint64_t pile_set(const Deal& d) const
     {
         uint64_t out = 0;
-        for (uint32_t i = 0; i < pile_n; ++i) out |= (uint64_t)1 << id_of_code(*pile_at(i));
+        for (uint32_t i = 0; i < d.pile_n; ++i) out |= (uint64_t)1 << id_of_code(*pile_at(i));
         return out;
     }
     // word i of the full deck in ascending order (codes)
@@ -177,46 +265,17 @@ struct KwGameT {
         return w;
     }
 
-    // The place of the j-th set bit of a 7-bit set, 3 bits per j: the table behind "the j-th legal
-    // card".  In shared memory on the device (filled by init_block at the start of a kernel).
-    ISMCTS_DEV static uint32_t place_table_entry(uint32_t set)
-    {
-        uint32_t entry = 0, j = 0;
-        for (uint32_t place = 0; place < kPlaces; ++place)
-            if ((set >> place) & 1u) entry |= place << (3u * j++);
-        return entry;
-    }
-    ISMCTS_DEV static uint32_t* place_table()
-    {
-#if defined(__CUDA_ARCH__)
-        __shared__ uint32_t table[128];
-        return table;
-#else
-        static uint32_t table[128];
-        static bool ready = false;
-        if (!ready) { for (uint32_t s = 0; s < 128; ++s) table[s] = place_table_entry(s); ready = true; }
-        return table;
-#endif
-    }
-    // Called by every thread of a block before any game runs (followed by a block barrier).
-    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads)
-    {
-#if defined(__CUDA_ARCH__)
-        uint32_t* table = place_table();
-        for (uint32_t s = thread; s < 128; s += threads) table[s] = place_table_entry(s);
-#else
-        (void)thread; (void)threads;
-#endif
-    }
+    ISMCTS_DEV static uint32_t* place_table() { return KwPlaceTable::table(); }
+    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads) { KwPlaceTable::init_block(thread, threads); }
 
-    // `scratch`: the block's scratch, rows of `scratch_stride` 8-byte words; this game owns column `column`
-    ISMCTS_DEV void bind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column) { rebind(scratch, scratch_stride, column); mode = kPlay; }
-    // the same columns again (a copy of the game whose pointers the compiler can follow)
-    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t scratch_stride, uint32_t column)
+    // (the scratch is found from the thread index: nothing to bind)
+    ISMCTS_DEV void bind(uint64_t*, uint32_t, uint32_t) { mode = kPlay; }
+    // kCarry: `scratch` is the block's scratch and `column` the index of the thread in its block
+    ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t, uint32_t column)
     {
-        hands = scratch + column;
-        held = reinterpret_cast<uint32_t*>(scratch + kHeldRow * scratch_stride) + column;
-        stride = scratch_stride;
+        if constexpr (kCarry) {
+            this->hands_ = hands_of(scratch, column); this->helds_ = helds_of(scratch, column); this->pile_ = pile_of(scratch, column);
+        }
     }
 
     // bit p -> bit 4p
@@ -262,15 +321,14 @@ struct KwGameT {
         trick_len = r->trick_len;
         lead_suit = 0; win_key = 0; win_player = 0;
         for (uint32_t i = 0; i < trick_len; ++i) fold_trick(i, r->trick_player[i], code_of_id(r->trick_card[i]));
-        mode = kPlay; tied = 0; pile_n = 0; deal_player = 0; deal_left = 0; need = 0;
-        deal_place = 0; deal_held = 0;
+        mode = kPlay; tied = 0;
     }
 
     // The start of an iteration for `observer` = the root's player to move.
     ISMCTS_DEV static void prepare(const Root* r, Prepared* out, uint64_t* scratch)
     {
-        KwGameT g;
-        g.bind(scratch, 1, 0);
+        (void)scratch;                                 // (the game finds its scratch itself: block_scratch)
+        Core g;
         g.load(r);
         Prepared p;
         p.observer = g.player;
@@ -300,19 +358,24 @@ struct KwGameT {
         *out = p;
     }
 
-    // Clone of the root with the determinisation pending (sosolver.h:46).
+    // Clone of the root with the determinisation pending (sosolver.h:46).  Does not touch the pile
+    // (see home()): the loop that deals begins with begin_start().
     ISMCTS_DEV void start(const Prepared* q)
     {
         for (uint32_t p = 0; p < kSeats; ++p) set_held(p, 0);                     // nobody holds a card ...
-        for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, q->pile[i]);
         set_list(q->observer, q->list_obs);                                        // ... but the observer
         set_held(q->observer, q->held_obs);
         player = q->player; dealer = q->dealer; trump = q->trump; tricks_left = q->tricks_left;
         request_trump = q->request_trump; alive4 = q->alive4; tricks = q->tricks; best = q->best;
         trick_len = q->trick_len; lead_suit = q->lead_suit; win_key = q->win_key; win_player = q->win_player;
-        mode = kPlay; tied = 0;
-        pile_n = q->pile_n;
-        begin_deal(q->sizes);
+        mode = kStart; tied = 0;
+    }
+    // mode == kStart: the pile of the determinisation and its deal (cloneAndRandomise, knockoutwhist.cpp:56-76)
+    ISMCTS_DEV void begin_start(Deal& d, const Prepared* q)
+    {
+        for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, q->pile[i]);
+        d.pile_n = q->pile_n;
+        begin_deal(d, q->sizes);
     }
 
     ISMCTS_DEV uint32_t current_player() const { return player; }
@@ -358,51 +421,51 @@ struct KwGameT {
     // after the last card held.  The cards go straight to their places in shared memory (a played
     // card stays on its place, only `held` says whether a place counts), `held` is stored when the
     // hand is complete.
-    ISMCTS_DEV void open_hand()
+    ISMCTS_DEV void open_hand(Deal& d) const
     {
-        deal_held = held_of(deal_player);
-        deal_place = top_place(deal_held);
+        d.deal_held = held_of(d.deal_player);
+        d.deal_place = top_place(d.deal_held);
     }
-    ISMCTS_DEV void close_hand() { set_held(deal_player, deal_held); }
-    ISMCTS_DEV void deal_card(uint32_t code)
+    ISMCTS_DEV void close_hand(const Deal& d) const { set_held(d.deal_player, d.deal_held); }
+    ISMCTS_DEV void deal_card(Deal& d, uint32_t code) const
     {
-        if (deal_place < kPlaces) {
-            reinterpret_cast<uint8_t*>(hands + deal_player * stride)[deal_place] = (uint8_t)code;
-            deal_held |= 1u << (8u * (code >> 4) + deal_place);
-            ++deal_place;
+        if (d.deal_place < kPlaces) {
+            reinterpret_cast<uint8_t*>(hands() + d.deal_player * kStride)[d.deal_place] = (uint8_t)code;
+            d.deal_held |= 1u << (8u * (code >> 4) + d.deal_place);
+            ++d.deal_place;
         }
     }
 
     // Starts dealing from the pile: `sizes` holds 4 bits per player, the number of cards each
     // gets, ascending id.
-    ISMCTS_DEV void begin_deal(uint32_t sizes)
+    ISMCTS_DEV void begin_deal(Deal& d, uint32_t sizes)
     {
-        need = sizes;
-        next_hand();
+        d.need = sizes;
+        next_hand(d);
     }
 
     // The next player to deal to, or the end of the deal.
-    ISMCTS_DEV void next_hand()
+    ISMCTS_DEV void next_hand(Deal& d)
     {
-        if (need) {
-            const uint32_t shift = ctz32(need) & ~3u;
-            deal_player = shift >> 2;
-            deal_left = (need >> shift) & 15u;
-            need &= ~(15u << shift);
+        if (d.need) {
+            const uint32_t shift = ctz32(d.need) & ~3u;
+            d.deal_player = shift >> 2;
+            d.deal_left = (d.need >> shift) & 15u;
+            d.need &= ~(15u << shift);
             mode = kDeal;
-            open_hand();
+            open_hand(d);
         } else {
             mode = kPlay;
         }
     }
 
     // deal, knockoutwhist.cpp:138-152: a fresh deck, tricks_left cards to each remaining player.
-    ISMCTS_DEV void start_deal()
+    ISMCTS_DEV void start_deal(Deal& d)
     {
 #pragma unroll
         for (uint32_t i = 0; i < kPileWords; ++i) set_pile_word(i, deck_word(i));
-        pile_n = ISMCTS_KW_CARDS;
-        begin_deal(alive4 * tricks_left);
+        d.pile_n = ISMCTS_KW_CARDS;
+        begin_deal(d, alive4 * tricks_left);
     }
 
     // finishRound, knockoutwhist.cpp:163-180
@@ -425,36 +488,36 @@ struct KwGameT {
     // (prepare() normalises root records that are finished in some other way).
     ISMCTS_DEV bool terminal() const { return tricks_left == 0; }
 
-    // A pending chance event is one uniform draw below chance_count().
-    ISMCTS_DEV uint32_t chance_count() const { return mode == kDeal ? pile_n : popc32(tied); }
+    // A pending chance event (mode kDeal or kTie) is one uniform draw below chance_count().
+    ISMCTS_DEV uint32_t chance_count(const Deal& d) const { return mode == kDeal ? d.pile_n : popc32(tied); }
 
     // The last card of the pile takes the place of card `j`, which is dealt.
-    ISMCTS_DEV uint32_t take_from_pile(uint32_t j)
+    ISMCTS_DEV uint32_t take_from_pile(Deal& d, uint32_t j) const
     {
         uint8_t* at = pile_at(j);
         const uint32_t code = *at;
-        *at = *pile_at(--pile_n);
+        *at = *pile_at(--d.pile_n);
         return code;
     }
 
     // The tie-break: the j-th of the tied players has won the round and calls trumps
     // (roundWinner, knockoutwhist.cpp:198-210), then the cards are dealt.
-    ISMCTS_DEV void break_tie(uint32_t j)
+    ISMCTS_DEV void break_tie(Deal& d, uint32_t j)
     {
         player = kth_bit32(tied, j) >> 2;
         dealer = next_alive(dealer);
         tricks = 0; best = 0;
-        start_deal();
+        start_deal(d);
     }
 
     // The pending chance event with draw `j` (uniform below chance_count()).
-    ISMCTS_DEV void chance_draw(uint32_t j)
+    ISMCTS_DEV void chance_draw(Deal& d, uint32_t j)
     {
         if (mode == kDeal) {
-            deal_card(take_from_pile(j));
-            if (--deal_left == 0) { close_hand(); next_hand(); }
+            deal_card(d, take_from_pile(d, j));
+            if (--d.deal_left == 0) { close_hand(d); next_hand(d); }
         } else {
-            break_tie(j);
+            break_tie(d, j);
         }
     }
 
@@ -466,15 +529,15 @@ struct KwGameT {
     // memory — a tree operation — the compiler must assume that a store to a hand changes it.)
     ISMCTS_DEV void play_place(uint32_t place, uint64_t& list, uint32_t& held)
     {
-        uint64_t* const lists = hands;
-        uint32_t* const helds = this->held;
-        const uint32_t pitch = stride, alive = alive4, trumps = trump;
+        uint64_t* const lists = hands();
+        uint32_t* const held_rows = helds();
+        const uint32_t pitch = kStride, alive = alive4, trumps = trump;
         uint32_t who = player, len = trick_len, lead = lead_suit, key_won = win_key, who_won = win_player;
         uint32_t taken_all = tricks, most = best;
 
         const uint32_t code = code_at(list, place);
         const uint32_t suit = code >> 4, rank = code & 15u;
-        helds[who * pitch] = held & ~(1u << (8u * suit + place));
+        held_rows[who * pitch] = held & ~(1u << (8u * suit + place));
         // trickWinner, :182-196, as in fold_trick()
         if (len == 0) lead = suit;
         const uint32_t key = rank + (suit == trumps ? 32u : suit == lead ? 16u : 0u);
@@ -492,7 +555,7 @@ struct KwGameT {
             who = who_won;
         }
         list = lists[who * pitch];
-        held = helds[who * pitch];
+        held = held_rows[who * pitch];
         player = who; trick_len = len; lead_suit = lead; win_key = key_won; win_player = who_won;
         tricks = taken_all; best = most;
         if (held == 0) finish_round();
@@ -552,11 +615,15 @@ struct KwGameT {
 
     // Every pending chance event of the warp: the tie-break (it starts a deal), then the deal
     // card by card.  `active`: the lane takes part in the search (it may have nothing pending).
-    template <class Rng>
-    ISMCTS_DEV void chance_phase(Rng& rng, bool active)
+    // `prep_of()`: the lane's position (asked for when mode == kStart: the determinisation begins here).
+    template <class Rng, class PrepOf>
+    ISMCTS_DEV void chance_phase(Rng& rng, bool active, PrepOf prep_of)
     {
         const bool mine = active && mode != kPlay;
         if (!warp_any(mine)) return;
+        Deal deal;
+        deal.pile_n = 0; deal.deal_player = 0; deal.deal_left = 0; deal.need = 0; deal.deal_place = 0; deal.deal_held = 0;
+        if (mine && mode == kStart) begin_start(deal, prep_of());
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;
         BlockWords words;
         uint32_t draws = 0;
@@ -566,7 +633,7 @@ struct KwGameT {
             for (uint32_t half = 0; half < 2; ++half) {
                 if (active && mode != kPlay) {
                     ++draws;
-                    chance_draw(words.below(chance_count()));
+                    chance_draw(deal, words.below(chance_count(deal)));
                 }
             }
         }
@@ -616,6 +683,8 @@ struct KwGameT {
         if (mine) rng.phase_end(first_block, draws);
     }
 };
+
+static_assert(std::is_trivially_copyable<KwGameT<4>>::value && sizeof(KwGameT<4>) == 56 && sizeof(KwGameT<ISMCTS_KW_MAX_PLAYERS>) == 56, "home(): 32 games in the seven pile rows of a warp");
 
 using KwGame = KwGameT<ISMCTS_KW_MAX_PLAYERS>;
 using KwGame4 = KwGameT<4>;   // positions with at most four players (ISMCTS_FLAG_KW_MAX4)

@@ -29,6 +29,8 @@
 // lane performs exactly the sequential sequence of operations of its tree.
 #pragma once
 
+#include <new>
+#include <type_traits>
 #include "devdefs.cuh"
 #include "philox.cuh"
 #include "pool.cuh"
@@ -71,8 +73,29 @@ ISMCTS_DEV uint64_t tree_iterations(uint64_t total, uint32_t trees_total, uint32
 enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
 
 // Games that bring their own phase loops for the lock-step schedule (chance_phase, play_phase).
-template <class G> constexpr auto game_is_phased(int) -> decltype(G::kPhased) { return G::kPhased; }
-template <class G> constexpr bool game_is_phased(long) { return false; }
+template <class G> ISMCTS_HDI constexpr auto game_is_phased(int) -> decltype(G::kPhased) { return G::kPhased; }
+template <class G> ISMCTS_HDI constexpr bool game_is_phased(long) { return false; }
+
+// Games whose object lives in their own scratch while the tree operations run (Game::home(), kw_game.cuh):
+// shared memory instead of the thread's local memory.
+template <class G> ISMCTS_HDI constexpr auto game_home_in_scratch(int) -> decltype(G::kHomeInScratch) { return G::kHomeInScratch; }
+template <class G> ISMCTS_HDI constexpr bool game_home_in_scratch(long) { return false; }
+
+// The copy of a game the loops of the phases work on (Game::Hot where a game has one).
+template <class G, class = void> struct GameHot { using type = G; };
+template <class G> struct GameHot<G, std::void_t<typename G::Hot>> { using type = typename G::Hot; };
+
+template <class Game, bool kHome>
+struct LaneGameStore {
+    Game g_;
+    ISMCTS_DEV Game& game() { return g_; }
+    ISMCTS_DEV const Game& game() const { return g_; }
+};
+template <class Game>
+struct LaneGameStore<Game, true> {
+    ISMCTS_DEV Game& game() { return *Game::home(); }
+    ISMCTS_DEV const Game& game() const { return *Game::home(); }
+};
 
 // Solver kinds of a lane.  kPlayout: determinise + rollout only
 // (SolverBase::simulate after cloneAndRandomise), one iteration per lane, no tree.
@@ -85,7 +108,9 @@ enum LaneKind : uint32_t { kPlayout = 0, kSO = 1, kMO = 2 };
 // lanes away from the path while its playout is still running.  MO-ISMCTS shares the trees of all
 // players the same way; EXP3 updates its scores with floating-point atomics.
 template <class Game, class SlotType, uint32_t kKind, bool kShared = false>
-struct Lane {
+struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
+    using LaneGameStore<Game, game_home_in_scratch<Game>(0)>::game;
+    static constexpr bool kHome = game_home_in_scratch<Game>(0);
     using Mask = typename Game::Mask;
     using Prepared = typename Game::Prepared;
     using Slot = SlotType;
@@ -96,7 +121,6 @@ struct Lane {
     static constexpr uint32_t kTrees = kMulti ? Game::kMaxPlayers : 1;
 
     const SearchParams& P;
-    Game g;
     LaneRng rng;
     TreePool<Slot> tree;
     const Prepared* prep;    // this lane's position, ready to start an iteration from
@@ -127,7 +151,7 @@ struct Lane {
     ISMCTS_DEV void start_iteration()
     {
         rng.begin_iteration(first_iteration + done * iteration_stride);
-        g.start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
+        game().start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
         depth = 0; plies = 0;
         if (kMulti) {
             for (uint32_t t = 0; t < kTrees; ++t) { node[t] = t; node_children[t] = load_slot(&tree.slots[t]).child_mask; }
@@ -147,7 +171,7 @@ struct Lane {
     // Node::update + updateData of one node (node.h:74-80; ucb1.h:53-56; exp3.h:45-48).
     ISMCTS_DEV void update_node(uint32_t slot, uint32_t who, double prob)
     {
-        const uint32_t r2 = g.result2(who);
+        const uint32_t r2 = game().result2(who);
         if (!kExp3) {
             // one 64-bit reduction: visits += 1 in the low word, score2 += 2 * reward in the high word
             red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[slot]), 1u | ((uint64_t)r2 << 32));
@@ -174,14 +198,14 @@ struct Lane {
                 // the visits were counted on the way down (virtual loss); now the rewards
                 for (uint32_t i = 0; i < depth; ++i)
                     red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[path[i] & 0xFFFFFFu]),
-                                (uint64_t)g.result2(path[i] >> 24) << 32);
+                                (uint64_t)game().result2(path[i] >> 24) << 32);
             } else if (kShared) {
                 // the same along the parent links of every tree
                 for (uint32_t t = 0; t < kTrees; ++t) {
                     uint32_t n = node[t];
                     while (n >= tree.roots) {
                         const Slot s = load_slot(&tree.slots[n]);
-                        add_reward_shared(&tree.slots[n], g.result2(s.player), slot_prob(s));
+                        add_reward_shared(&tree.slots[n], game().result2(s.player), slot_prob(s));
                         n = slot_parent_of(s.key);
                     }
                 }
@@ -199,7 +223,7 @@ struct Lane {
                 }
             }
         } else {
-            P.playout_out[gtid] = (g.outcome() & 0xFFu) | ((plies & 0xFFFu) << 8) | ((rng.consumed() & 0xFFFu) << 20);
+            P.playout_out[gtid] = (game().outcome() & 0xFFu) | ((plies & 0xFFFu) << 8) | ((rng.consumed() & 0xFFFu) << 20);
         }
         ++done;
         if (budget_left()) start_iteration();
@@ -290,9 +314,9 @@ struct Lane {
     ISMCTS_DEV_CALL void descend()
     {
         for (;;) {
-            const Mask legal = g.legal();
+            const Mask legal = game().legal();
             if (!legal.any()) return;                             // terminal: selectNode, solverbase.h:53-56
-            const uint32_t who = g.current_player();              // newChild, solverbase.h:74-80: before the move
+            const uint32_t who = game().current_player();              // newChild, solverbase.h:74-80: before the move
             const uint32_t a = kMulti ? who : 0;                  // the deciding tree
             const Mask untried = legal.minus(node_children[a]);   // untriedMoves, node.h:82-91
             const bool expand = untried.any();
@@ -321,9 +345,9 @@ struct Lane {
             // which is the mover when the node was created — in games where the same move can be made by
             // different players in different determinisations (phantom m,n,k) not necessarily today's mover
             if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : chosen.player) << 24);
-            g.step(move);
+            game().step(move);
             if (expand) { phase = kRollout; return; }
-            if (g.chance_pending()) return;
+            if (game().chance_pending()) return;
         }
     }
 
@@ -371,9 +395,9 @@ struct Lane {
     {
         if constexpr (kShared) {
             for (;;) {
-                const Mask legal = g.legal();
+                const Mask legal = game().legal();
                 if (!legal.any()) return;
-                const uint32_t who = g.current_player();
+                const uint32_t who = game().current_player();
                 const uint32_t a = kMulti ? who : 0;                  // the deciding tree
                 const Mask kids = Mask::load_shared(&tree.slots[node[a]].child_mask); // other lanes add children
                 const Mask untried = legal.minus(kids);
@@ -397,9 +421,9 @@ struct Lane {
                     node[t] = next;
                 }
                 if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : stored) << 24);
-                g.step(move);
+                game().step(move);
                 if (expand) { phase = kRollout; return; }
-                if (g.chance_pending()) return;
+                if (game().chance_pending()) return;
             }
         }
     }
@@ -411,7 +435,7 @@ struct Lane {
     // bandit values) do not count against the loops that run most of the time.  Those loops —
     // chance events and rollout moves — work on copies of the game and of the stream, which
     // are registers, between two tree operations.
-    ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !g.chance_pending() && !g.terminal(); }
+    ISMCTS_DEV bool wants_descent() const { return phase == kSelect && !game().chance_pending() && !game().terminal(); }
 
     // `scratch` + `column`, `ring`: the columns the game and the stream are bound to, handed in again so
     // that the copies the loops work on address them as shared memory (the lane object itself lives in
@@ -421,8 +445,9 @@ struct Lane {
         for (;;) {
             if (!warp_any(phase != kDone)) break;
             {
-                Game hot = g;
+                typename GameHot<Game>::type hot(game());
                 LaneRng stream = rng;
+                if (kHome) warp_sync();                           // every lane holds its game: the piles may be written
                 hot.rebind(scratch, scratch_stride, column);
                 stream.ring = ring; stream.stride = ring_stride;
                 const uint32_t ph = phase;
@@ -430,7 +455,7 @@ struct Lane {
                 for (;;) {
                     // every pending chance event of the warp
                     if constexpr (game_is_phased<Game>(0)) {
-                        hot.chance_phase(stream, ph != kDone);
+                        hot.chance_phase(stream, ph != kDone, [this] { return prep; });
                     } else {
                         for (uint32_t s = 0; warp_any(ph != kDone && hot.chance_pending()); ++s) {
                             if ((s & 3u) == 0u && ph != kDone && stream.low()) stream.refill();
@@ -455,7 +480,8 @@ struct Lane {
                         }
                     }
                 }
-                g = hot;
+                if (kHome) warp_sync();                           // no lane uses its pile any more
+                game() = hot;
                 rng = stream;
                 plies += moves;
             }
@@ -473,15 +499,16 @@ struct Lane {
 // parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
 // lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
 // statistics of the root children are collected afterwards by collect_roots.
+// The body of lane_tree_search on a lane object that lives wherever the caller put it.
 template <class Game, class Slot, uint32_t kKind, bool kShared>
-ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
-                                 uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
+ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, const SearchParams& P, uint32_t gtid, bool valid,
+                                    uint64_t* scratch, uint32_t scratch_stride, uint32_t column, uint32_t* ring,
+                                    uint32_t ring_stride, uint32_t* path)
 {
     using Mask = typename Game::Mask;
     using L = Lane<Game, Slot, kKind, kShared>;
-    L lane(P);
     lane.path = path;
-    lane.g.bind(scratch, scratch_stride, column);
+    lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
     lane.iteration_stride = 1; lane.node_counter = nullptr;
     lane.root_children = Mask::none();
@@ -514,6 +541,36 @@ ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool vali
     if (!valid) return;
     if (kShared) atomic_add_u64(P.iters_done + tree_index, lane.done);
     else P.iters_done[tree_index] = lane.done;
+}
+
+// The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees, or — tree
+// parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
+// lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
+// statistics of the root children are collected afterwards by collect_roots.
+// `lane_mem`: where the lane object lives (shared memory, lane_stride() bytes per thread); null = on the
+// thread's stack (local memory).
+template <class Game, class Slot, uint32_t kKind, bool kShared, bool kLaneSm = false>
+ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
+                                 uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path,
+                                 void* lane_mem = nullptr)
+{
+    using L = Lane<Game, Slot, kKind, kShared>;
+    if constexpr (kLaneSm) {
+        L* lane = new (lane_mem) L(P);
+        lane_tree_search_on<Game, Slot, kKind, kShared>(*lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path);
+    } else {
+        L lane(P);
+        lane_tree_search_on<Game, Slot, kKind, kShared>(lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path);
+    }
+}
+
+// Bytes per thread of a lane object kept in shared memory: a multiple of 8 whose eighth is odd, so that the
+// 8-byte accesses of the 32 lanes of a warp fall into different banks (4-byte accesses: two lanes per bank).
+template <class L>
+ISMCTS_HDI constexpr uint32_t lane_stride()
+{
+    uint32_t units = ((uint32_t)sizeof(L) + 7u) / 8u;
+    return 8u * (units | 1u);
 }
 
 // Shared trees: the root node(s) and the node counter of tree `index`, before the search starts.
@@ -564,7 +621,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
     using Mask = typename Game::Mask;
     Lane<Game, SlotUcb<Mask>, kPlayout> lane(P);
     lane.path = nullptr;
-    lane.g.bind(scratch, scratch_stride, column);
+    lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
     lane.iteration_stride = 1; lane.node_counter = nullptr;
     lane.root_children = Mask::none();

@@ -36,6 +36,10 @@ class FiberWarp {
 public:
     explicit FiberWarp(size_t lanes) : fibers_(lanes) {}
 
+    // The scratch of games that find it themselves (devdefs.cuh: block_scratch): lanes 128 k .. 128 k + 127
+    // are the threads of the k-th "block" and use the k-th piece of `words_per_block` words.
+    void set_scratch(uint64_t* base, size_t words_per_block) { scratch_ = base; words_per_warp_ = words_per_block; }
+
     // Runs body(lane) for every lane as one warp.
     void run(const std::function<void(uint32_t)>& body)
     {
@@ -57,6 +61,8 @@ public:
                 Fiber& f = fibers_[i];
                 if (f.finished) continue;
                 current_ = i;
+                g_host_block_scratch = scratch_ ? scratch_ + (i / kBlockLanes) * words_per_warp_ : nullptr;
+                g_host_block_lane = (uint32_t)(i % kBlockLanes);
                 swapcontext(&main_, &f.ctx);          // until its next vote, or its end
                 if (!f.finished) { alive = true; any = any || f.ballot; }
             }
@@ -64,6 +70,7 @@ public:
             result_ = any;
         }
         g_host_warp_any = nullptr;
+        g_host_block_scratch = nullptr;
         active_ = nullptr;
     }
 
@@ -94,6 +101,8 @@ private:
 
     static FiberWarp* active_;
     std::vector<Fiber> fibers_;
+    uint64_t* scratch_ = nullptr;
+    size_t words_per_warp_ = 0;
     ucontext_t main_;
     size_t current_ = 0;
     bool result_ = false;
@@ -141,11 +150,25 @@ int dump_table(const Slot* table, size_t cap, uint32_t n_roots, uint32_t root_sl
 // Per-lane scratch of a warp of `width` lanes, laid out as in a CTA (one column per lane).
 template <class Game>
 struct WarpScratch {
-    std::vector<uint64_t> scratch;
+    static constexpr size_t kWordsPerWarp = (size_t)Game::kHandWords * kBlockLanes;   // (per block of 128 lanes)
+    std::vector<uint64_t> blocked;            // the scratch of the lanes, block of 128 lanes after block (as in the kernels)
     std::vector<uint32_t> ring, path;
     explicit WarpScratch(uint32_t w)
-        : scratch((size_t)Game::kHandWords * w), ring((size_t)LaneRng::kRingWords * w), path((size_t)Game::kMaxDepth * w) {}
+        : blocked(kWordsPerWarp * ((w + kBlockLanes - 1) / kBlockLanes)),
+          ring((size_t)LaneRng::kRingWords * w), path((size_t)Game::kMaxDepth * w) {}
 };
+
+// Game::prepare with the scratch of one lane installed.
+template <class Game>
+void prepare_root(const void* root, typename Game::Prepared* prepared)
+{
+    std::vector<uint64_t> blocked(WarpScratch<Game>::kWordsPerWarp);
+    uint64_t prep_scratch[Game::kHandWords];
+    g_host_block_scratch = blocked.data();
+    g_host_block_lane = 0;
+    Game::prepare((const typename Game::Root*)root, prepared, prep_scratch);
+    g_host_block_scratch = nullptr;
+}
 
 template <class Game>
 uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_t iteration)
@@ -155,13 +178,13 @@ uint32_t playout_t(const void* root, uint64_t seed, uint32_t pos, uint32_t itera
     uint32_t out = 0;
     // position `pos` of the caller is record 0 here: shift pos_base instead of the pointer
     typename Game::Prepared prepared;
-    uint64_t prep_scratch[Game::kHandWords];
-    Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
+    prepare_root<Game>(root, &prepared);
     P.prepared = &prepared; P.n_positions = 1; P.pos_base = pos; P.seed = seed; P.playout_out = &out - iteration;
     WarpScratch<Game> ws(1);
     // thread `iteration` of a launch with per_position > iteration plays playout `iteration` of record 0
     FiberWarp warp(1);
-    warp.run([&](uint32_t) { lane_playout<Game>(P, iteration, true, 0x7FFFFFFFu, ws.scratch.data(), 1, 0, ws.ring.data(), 1); });
+    warp.set_scratch(ws.blocked.data(), WarpScratch<Game>::kWordsPerWarp);
+    warp.run([&](uint32_t) { lane_playout<Game>(P, iteration, true, 0x7FFFFFFFu, ws.blocked.data(), kBlockLanes, 0, ws.ring.data(), 1); });
     return out;
 }
 
@@ -184,8 +207,7 @@ int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos,
     SearchParams P;
     std::memset(&P, 0, sizeof P);
     typename Game::Prepared prepared;
-    uint64_t prep_scratch[Game::kHandWords];
-    Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
+    prepare_root<Game>(root, &prepared);
     P.prepared = &prepared; P.n_positions = 1; P.trees = width; P.trees_total = first_tree + width; P.tree_base = first_tree;
     P.pos_base = pos; P.iterations = iterations * P.trees_total; P.seed = seed; P.exploration = exploration;
     P.pool = tables.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
@@ -194,8 +216,10 @@ int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos,
     P.lanes_per_tree = 1;
     WarpScratch<Game> ws(width);
     FiberWarp warp(width);
+    warp.set_scratch(ws.blocked.data(), WarpScratch<Game>::kWordsPerWarp);
     warp.run([&](uint32_t lane) {
-        lane_tree_search<Game, Slot, kKind, false>(P, lane, true, ws.scratch.data(), width, lane, ws.ring.data() + lane, width,
+        lane_tree_search<Game, Slot, kKind, false>(P, lane, true, ws.blocked.data() + (lane / kBlockLanes) * WarpScratch<Game>::kWordsPerWarp,
+                                                   kBlockLanes, lane % kBlockLanes, ws.ring.data() + lane, width,
                                                    ws.path.data() + (size_t)lane * Game::kMaxDepth);
     });
     for (uint32_t i = 0; i < width; ++i) if (it[i] != iterations) return 6;
@@ -233,8 +257,7 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     std::vector<uint64_t> v(Game::kMoveStride), s2(Game::kMoveStride), a(Game::kMoveStride), it(1);
     uint32_t counter = 0;
     typename Game::Prepared prepared;
-    uint64_t prep_scratch[Game::kHandWords];
-    Game::prepare((const typename Game::Root*)root, &prepared, prep_scratch);
+    prepare_root<Game>(root, &prepared);
     SearchParams P;
     std::memset(&P, 0, sizeof P);
     P.prepared = &prepared; P.n_positions = 1; P.trees = 1; P.trees_total = 1; P.iterations = iterations;
@@ -245,8 +268,10 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     init_shared_root<Slot>(P, 0, n_roots);
     WarpScratch<Game> ws(width);
     FiberWarp warp(width);
+    warp.set_scratch(ws.blocked.data(), WarpScratch<Game>::kWordsPerWarp);
     warp.run([&](uint32_t lane) {
-        lane_tree_search<Game, Slot, kKind, true>(P, lane, true, ws.scratch.data(), width, lane, ws.ring.data() + lane, width,
+        lane_tree_search<Game, Slot, kKind, true>(P, lane, true, ws.blocked.data() + (lane / kBlockLanes) * WarpScratch<Game>::kWordsPerWarp,
+                                                  kBlockLanes, lane % kBlockLanes, ws.ring.data() + lane, width,
                                                   ws.path.data() + (size_t)lane * Game::kMaxDepth);
     });
     *done_out = it[0];
