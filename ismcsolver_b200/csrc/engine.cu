@@ -35,7 +35,8 @@ template <class Game>
 __host__ __device__ constexpr size_t block_smem()
 {
     // (a game whose loops keep their Philox blocks in registers needs no ring: more of the SM's memory stays L1)
-    return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + (game_is_phased<Game>(0) ? 0 : LaneRng::kRingWords) * sizeof(uint32_t));
+    return (size_t)kBlock * (Game::kHandWords * sizeof(uint64_t) + (game_is_phased<Game>(0) ? 0 : LaneRng::kRingWords) * sizeof(uint32_t))
+         + game_block_extra_bytes<Game>(0);   // (per-block tables of the game, behind the scratch: Knockout Whist has no ring)
 }
 
 // Root records -> the register image every iteration starts from (one thread per position).

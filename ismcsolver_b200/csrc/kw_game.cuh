@@ -70,9 +70,11 @@ struct alignas(16) KwPrepared {
 static_assert(sizeof(KwPrepared) == 128, "eight 16-byte loads");
 
 // The place of the j-th set bit of a 7-bit set, 3 bits per j: the table behind "the j-th legal
-// card".  In shared memory on the device (filled by init_block at the start of a kernel); one table
-// for every form of the game.
+// card".  On the device it lives in the block's dynamic shared memory right behind the scratch of the
+// games (filled by init_block at the start of a kernel), so that its address derives from the same base as
+// theirs; host builds use one static table.
 struct KwPlaceTable {
+    static constexpr uint32_t kBytes = 128 * sizeof(uint32_t);
     ISMCTS_DEV static uint32_t entry(uint32_t set)
     {
         uint32_t e = 0, j = 0;
@@ -80,12 +82,13 @@ struct KwPlaceTable {
             if ((set >> place) & 1u) e |= place << (3u * j++);
         return e;
     }
-    ISMCTS_DEV static uint32_t* table()
+    // `behind`: the end of the games' scratch
+    ISMCTS_DEV static uint32_t* table(uint64_t* behind)
     {
 #if defined(__CUDA_ARCH__)
-        __shared__ uint32_t t[128];
-        return t;
+        return reinterpret_cast<uint32_t*>(behind);
 #else
+        (void)behind;
         static uint32_t t[128];
         static bool ready = false;
         if (!ready) { for (uint32_t s = 0; s < 128; ++s) t[s] = entry(s); ready = true; }
@@ -93,13 +96,13 @@ struct KwPlaceTable {
 #endif
     }
     // Called by every thread of a block before any game runs (followed by a block barrier).
-    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads)
+    ISMCTS_DEV static void init_block(uint64_t* behind, uint32_t thread, uint32_t threads)
     {
 #if defined(__CUDA_ARCH__)
-        uint32_t* t = table();
+        uint32_t* t = table(behind);
         for (uint32_t s = thread; s < 128; s += threads) t[s] = entry(s);
 #else
-        (void)thread; (void)threads;
+        (void)behind; (void)thread; (void)threads;
 #endif
     }
 };
@@ -110,7 +113,7 @@ struct KwPlaceTable {
 // on such copies, `Hot`: the addresses are values the compiler keeps or derives from the thread index as it
 // likes); the game proper (`Core`) finds its scratch from the thread index whenever it needs it.
 struct KwNoAddresses {};
-struct KwAddresses { uint64_t* hands_; uint32_t* helds_; uint64_t* pile_; };
+struct KwAddresses { uint64_t* hands_; uint32_t* helds_; uint64_t* pile_; const uint32_t* table_; };
 
 template <uint32_t kSeats, bool kCarry = false>
 struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
@@ -265,8 +268,12 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         return w;
     }
 
-    ISMCTS_DEV static uint32_t* place_table() { return KwPlaceTable::table(); }
-    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads) { KwPlaceTable::init_block(thread, threads); }
+    static constexpr uint32_t kBlockExtraBytes = KwPlaceTable::kBytes;       // behind the scratch of the block's games
+    ISMCTS_DEV const uint32_t* place_table() const
+    {
+        if constexpr (kCarry) return this->table_; else return KwPlaceTable::table(block_scratch() + kHandWords * kStride);
+    }
+    ISMCTS_DEV static void init_block(uint32_t thread, uint32_t threads) { KwPlaceTable::init_block(block_scratch() + kHandWords * kStride, thread, threads); }
 
     // (the scratch is found from the thread index: nothing to bind)
     ISMCTS_DEV void bind(uint64_t*, uint32_t, uint32_t) { mode = kPlay; }
@@ -275,6 +282,7 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
     {
         if constexpr (kCarry) {
             this->hands_ = hands_of(scratch, column); this->helds_ = helds_of(scratch, column); this->pile_ = pile_of(scratch, column);
+            this->table_ = KwPlaceTable::table(scratch + kHandWords * kStride);
         }
     }
 

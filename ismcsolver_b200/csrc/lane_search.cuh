@@ -76,6 +76,10 @@ enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
 template <class G> ISMCTS_HDI constexpr auto game_is_phased(int) -> decltype(G::kPhased) { return G::kPhased; }
 template <class G> ISMCTS_HDI constexpr bool game_is_phased(long) { return false; }
 
+// Bytes of per-block tables a game keeps behind the scratch of the block's games (Game::kBlockExtraBytes).
+template <class G> ISMCTS_HDI constexpr auto game_block_extra_bytes(int) -> decltype(G::kBlockExtraBytes) { return G::kBlockExtraBytes; }
+template <class G> ISMCTS_HDI constexpr uint32_t game_block_extra_bytes(long) { return 0; }
+
 // Games whose object lives in their own scratch while the tree operations run (Game::home(), kw_game.cuh):
 // shared memory instead of the thread's local memory.
 template <class G> ISMCTS_HDI constexpr auto game_home_in_scratch(int) -> decltype(G::kHomeInScratch) { return G::kHomeInScratch; }
