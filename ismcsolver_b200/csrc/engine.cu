@@ -27,6 +27,7 @@
 namespace ismcts {
 
 constexpr int kBlock = 128;
+static_assert(kBlock == (int)kBlockLanes, "games that find their scratch from the thread index assume this block size");
 
 // Shared memory of a block: the per-thread game scratch (hands / stones, one
 // 8-byte column per thread) followed by the per-thread Philox rings (one 4-byte
@@ -52,7 +53,7 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
 
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
-template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks, bool kLaneSm = false>
+template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams params)
 {
     // the tree operations are real calls that reach the parameters through a pointer: one copy per block
@@ -66,13 +67,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
-    // kLaneSm: the lane objects live in shared memory behind the scratch (their fields are what the tree
-    // operations work on; on the stack they are local memory, most of which misses L1)
-    using L = Lane<Game, Slot, kKind, kShared>;
-    constexpr size_t kScratchBytes = block_smem<Game>();
-    constexpr uint32_t kLaneBytes = lane_stride<L>();
-    void* lane_mem = kLaneSm ? reinterpret_cast<unsigned char*>(smem) + kScratchBytes + (size_t)threadIdx.x * kLaneBytes : nullptr;
-    lane_tree_search<Game, Slot, kKind, kShared, kLaneSm>(P, gtid, gtid < lanes, smem, kBlock, threadIdx.x, ring, kBlock, path, lane_mem);
+    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, smem, kBlock, threadIdx.x, ring, kBlock, path);
 }
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
@@ -323,25 +318,11 @@ static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32
     const size_t smem = block_smem<Game>();
     if constexpr (kTuned) {
         // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
-        if (std::getenv("ISMCTS_LANE_SHARED")) {
-            // experiment: lane objects in shared memory
-            const size_t smem_l = smem + (size_t)kBlock * lane_stride<Lane<Game, Slot, kKind, false>>();
-            auto go = [&](auto kernel) {
-                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
-                kernel<<<grid, kBlock, smem_l, ctx->stream>>>(P);
-            };
-            switch (ctx->min_blocks) {
-            case 4: go(search_kernel<Game, Slot, kKind, false, 4, true>); return;
-            case 5: go(search_kernel<Game, Slot, kKind, false, 5, true>); return;
-            default: go(search_kernel<Game, Slot, kKind, false, 6, true>); return;
-            }
-        }
         switch (ctx->min_blocks) {
         case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        default:
-            search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
+        default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
         }
     } else {
         search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);

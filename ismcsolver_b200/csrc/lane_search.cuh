@@ -551,30 +551,12 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
 // parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
 // lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
 // statistics of the root children are collected afterwards by collect_roots.
-// `lane_mem`: where the lane object lives (shared memory, lane_stride() bytes per thread); null = on the
-// thread's stack (local memory).
-template <class Game, class Slot, uint32_t kKind, bool kShared, bool kLaneSm = false>
+template <class Game, class Slot, uint32_t kKind, bool kShared>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
-                                 uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path,
-                                 void* lane_mem = nullptr)
+                                 uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
-    using L = Lane<Game, Slot, kKind, kShared>;
-    if constexpr (kLaneSm) {
-        L* lane = new (lane_mem) L(P);
-        lane_tree_search_on<Game, Slot, kKind, kShared>(*lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path);
-    } else {
-        L lane(P);
-        lane_tree_search_on<Game, Slot, kKind, kShared>(lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path);
-    }
-}
-
-// Bytes per thread of a lane object kept in shared memory: a multiple of 8 whose eighth is odd, so that the
-// 8-byte accesses of the 32 lanes of a warp fall into different banks (4-byte accesses: two lanes per bank).
-template <class L>
-ISMCTS_HDI constexpr uint32_t lane_stride()
-{
-    uint32_t units = ((uint32_t)sizeof(L) + 7u) / 8u;
-    return 8u * (units | 1u);
+    Lane<Game, Slot, kKind, kShared> lane(P);
+    lane_tree_search_on<Game, Slot, kKind, kShared>(lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path);
 }
 
 // Shared trees: the root node(s) and the node counter of tree `index`, before the search starts.
