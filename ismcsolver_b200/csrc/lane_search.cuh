@@ -214,7 +214,14 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                     }
                 }
             } else if (!kMulti && !kExp3) {
-                for (uint32_t i = 0; i < depth; ++i) update_node(path[i] & 0xFFFFFFu, path[i] >> 24, 1.0);
+                // (four path entries at a time: their loads are in flight together)
+                uint32_t i = 0;
+                for (; i + 4 <= depth; i += 4) {
+                    const uint32_t a = path[i], b = path[i + 1], c = path[i + 2], d = path[i + 3];
+                    update_node(a & 0xFFFFFFu, a >> 24, 1.0); update_node(b & 0xFFFFFFu, b >> 24, 1.0);
+                    update_node(c & 0xFFFFFFu, c >> 24, 1.0); update_node(d & 0xFFFFFFu, d >> 24, 1.0);
+                }
+                for (; i < depth; ++i) update_node(path[i] & 0xFFFFFFu, path[i] >> 24, 1.0);
             } else {
                 // walk the parent links (the key of a node holds its parent's slot)
                 for (uint32_t t = 0; t < kTrees; ++t) {

@@ -158,7 +158,7 @@ struct TreePool {
     {
         const uint32_t key = slot_make_key(parent, move);
         uint32_t i = home(key);
-        while (i < roots || load_slot(&slots[i]).key != 0) i = (i + 1u) & mask;
+        while (i < roots || load_u32_cg(&slots[i].key) != 0) i = (i + 1u) & mask;
         Slot s;
         s.set_fresh();
         s.key = key; s.created = created; s.player = player; s.child_mask = Mask::none();
