@@ -41,9 +41,9 @@
 // pile) is the column of its thread in the block's scratch (devdefs.cuh: block_scratch).
 // While a deal is in progress its state is a separate `Deal` that lives in the loop that deals
 // (chance_phase); between two such loops no deal is ever in progress.  That makes the pile dead
-// whenever the tree operations of the search run, and the search keeps the game objects of the
-// 32 lanes of a warp in the memory of the warp's piles meanwhile (home(): 32 x 56 bytes = the seven
-// pile rows), i.e. in shared memory at no cost, instead of in the thread's local memory.
+// whenever the tree operations of the search run, and the search keeps the game object in the 56
+// bytes of its pile meanwhile (home()), i.e. in shared memory at no cost, instead of in the thread's
+// local memory.
 #pragma once
 
 #include <type_traits>
@@ -142,17 +142,13 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
 
     // The scratch of this thread's game.  Lists and `held`: rows of one column per thread of the block —
     // list of player p = hands()[p * kStride], `held` of player p = helds()[p * kStride] (rows of 4-byte words
-    // behind the rows of lists).  The pile: seven rows of one column per lane of the warp, warp after warp
-    // behind those (pile word w = pile()[w * kPileStride]), so that the piles of a warp are one piece of
-    // memory (home()).
+    // behind the rows of lists).  The pile: 56 consecutive bytes per thread behind those (card i = byte i:
+    // no row arithmetic for a card picked at random; consecutive threads are seven 8-byte words apart, which
+    // keeps the 8-byte accesses of a warp free of bank conflicts).
     static constexpr uint32_t kStride = kBlockLanes;
-    static constexpr uint32_t kPileStride = kWarpLanes;
     ISMCTS_DEV static uint64_t* hands_of(uint64_t* scratch, uint32_t column) { return scratch + column; }
     ISMCTS_DEV static uint32_t* helds_of(uint64_t* scratch, uint32_t column) { return reinterpret_cast<uint32_t*>(scratch + kHeldRow * kStride) + column; }
-    ISMCTS_DEV static uint64_t* pile_of(uint64_t* scratch, uint32_t column)
-    {   // the column of the thread's lane in the piles of its warp
-        return scratch + kPileRow * kStride + column + (column >> 5) * ((kPileWords - 1) * kPileStride);
-    }
+    ISMCTS_DEV static uint64_t* pile_of(uint64_t* scratch, uint32_t column) { return scratch + kPileRow * kStride + column * kPileWords; }
     ISMCTS_DEV uint64_t* hands() const { if constexpr (kCarry) return this->hands_; else return hands_of(block_scratch(), block_lane()); }
     ISMCTS_DEV uint32_t* helds() const { if constexpr (kCarry) return this->helds_; else return helds_of(block_scratch(), block_lane()); }
     ISMCTS_DEV uint64_t* pile() const { if constexpr (kCarry) return this->pile_; else return pile_of(block_scratch(), block_lane()); }
@@ -177,11 +173,8 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         uint32_t deal_held;               // `held` of deal_player while it is being dealt, stored when it is complete
     };
 
-    // Where the search keeps this thread's game while no deal can be in progress: the memory of the
-    // warp's piles (seven rows of 32 x 8 bytes), one 56-byte object per lane — 32 objects fill the
-    // piles of a warp exactly, so the objects of a block are one array.  The lanes of a warp must pass
-    // a warp_sync() between their last use of the pile and the first use of these objects, and back.
-    ISMCTS_DEV static Core* home() { return reinterpret_cast<Core*>(block_scratch() + kPileRow * kStride) + block_lane(); }
+    // Where the search keeps this thread's game while no deal can be in progress: the 56 bytes of its pile.
+    ISMCTS_DEV static Core* home() { return reinterpret_cast<Core*>(pile_of(block_scratch(), block_lane())); }
     static constexpr bool kHomeInScratch = true;
 
     // the state of another copy of the game
@@ -247,9 +240,9 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
     // card i of the pile: byte i % 8 of word i / 8
     ISMCTS_DEV uint8_t* pile_at(uint32_t i) const
     {
-        return reinterpret_cast<uint8_t*>(pile() + (i >> 3) * kPileStride) + (i & 7u);
+        return reinterpret_cast<uint8_t*>(pile()) + i;
     }
-    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) const { pile()[i * kPileStride] = v; }
+    ISMCTS_DEV void set_pile_word(uint32_t i, uint64_t v) const { pile()[i] = v; }
     // the cards left in the pile as a set of ids (after a deal: the cards nobody holds)
     ISMCTS_DEV uint64_t pile_set(const Deal& d) const
     {
@@ -692,7 +685,7 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
     }
 };
 
-static_assert(std::is_trivially_copyable<KwGameT<4>>::value && sizeof(KwGameT<4>) == 56 && sizeof(KwGameT<ISMCTS_KW_MAX_PLAYERS>) == 56, "home(): 32 games in the seven pile rows of a warp");
+static_assert(std::is_trivially_copyable<KwGameT<4>>::value && sizeof(KwGameT<4>) == 56 && sizeof(KwGameT<ISMCTS_KW_MAX_PLAYERS>) == 56, "home(): a game fits the 56 bytes of its pile");
 
 using KwGame = KwGameT<ISMCTS_KW_MAX_PLAYERS>;
 using KwGame4 = KwGameT<4>;   // positions with at most four players (ISMCTS_FLAG_KW_MAX4)

@@ -458,7 +458,6 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             {
                 typename GameHot<Game>::type hot(game());
                 LaneRng stream = rng;
-                if (kHome) warp_sync();                           // every lane holds its game: the piles may be written
                 hot.rebind(scratch, scratch_stride, column);
                 stream.ring = ring; stream.stride = ring_stride;
                 const uint32_t ph = phase;
@@ -491,7 +490,6 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                         }
                     }
                 }
-                if (kHome) warp_sync();                           // no lane uses its pile any more
                 game() = hot;
                 rng = stream;
                 plies += moves;
