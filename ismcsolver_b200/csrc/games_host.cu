@@ -65,6 +65,7 @@ int ismcts_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_
     uint32_t ring[LaneRng::kRingWords];
     LaneRng rng;
     rng.init(seed, stream, kDealTree, ring, 1);
+    rng.per_word = KwGame::kDrawsPerWord;
     rng.begin_iteration(kDealIteration);
     KwGame::Deal deal;
     g.start_deal(deal);
@@ -103,6 +104,7 @@ int ismcts_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t s
     uint32_t ring[LaneRng::kRingWords];
     LaneRng rng;
     rng.init(seed, stream, kApplyTree, ring, 1);
+    rng.per_word = KwGame::kDrawsPerWord;
     rng.begin_iteration(0, draw_counter ? *draw_counter : 0);
     g.step(move);
     uint64_t unknown = s->unknown;

@@ -585,13 +585,14 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
 
     // ---- phases of the lock-step loop (lane_search.cuh): the same transitions as chance_draw() and
     // play() with the same draws, as tight loops over ONE kind of step.  Every lane that takes
-    // part makes one draw per step from an aligned stream, so draw s of the phase is half s % 2 of
-    // word (s / 2) % 4 of block s / 8 for all of them: the block is generated in registers by all
+    // part makes one draw per step from an aligned stream, so draw s of the phase is third s % 3 of
+    // word (s / 3) % 4 of block s / 12 for all of them: the block is generated in registers by all
     // lanes in the same steps and no ring is involved.
     static constexpr bool kPhased = true;
+    static constexpr uint32_t kDrawsPerWord = 3;      // choices are among at most 52 (philox.cuh)
 
-    // A block of the stream in registers.  A turn of a phase loop is two steps (the two draws of
-    // one word); every fourth turn generates the next block.
+    // A block of the stream in registers.  A turn of a phase loop is three steps (the three draws
+    // of one word); every fourth turn generates the next block.
     struct BlockWords {
         uint32_t w, b1, b2, b3;   // the word being used up, the words not started yet
         template <class Rng>
@@ -631,14 +632,14 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         for (uint32_t t = 0; warp_any(active && mode != kPlay); ++t) {
             words.turn(rng, first_block, t);
 #pragma unroll
-            for (uint32_t half = 0; half < 2; ++half) {
+            for (uint32_t part = 0; part < kDrawsPerWord; ++part) {
                 if (active && mode != kPlay) {
                     ++draws;
                     chance_draw(deal, words.below(chance_count(deal)));
                 }
             }
         }
-        if (mine) { rng.phase_end(first_block, draws); rng.align(); }
+        if (mine) { rng.phase_end(first_block, (draws + kDrawsPerWord - 1u) / kDrawsPerWord); rng.align(); }
     }
 
     // One move of the default policy (simulate, solverbase.h:36-43) from the hand (`list`, `held`)
@@ -673,7 +674,7 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         for (uint32_t t = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++t) {
             words.turn(rng, first_block, t);
 #pragma unroll
-            for (uint32_t half = 0; half < 2; ++half) {
+            for (uint32_t part = 0; part < kDrawsPerWord; ++part) {
                 if (rolling && mode == kPlay && tricks_left != 0) {
                     ++draws;
                     rollout_step(words, table, list, held);
@@ -681,7 +682,7 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
             }
         }
         plies += draws;
-        if (mine) rng.phase_end(first_block, draws);
+        if (mine) rng.phase_end(first_block, (draws + kDrawsPerWord - 1u) / kDrawsPerWord);
     }
 };
 

@@ -76,6 +76,10 @@ enum LanePhase : uint32_t { kSelect = 0, kRollout = 1, kDone = 2 };
 template <class G> ISMCTS_HDI constexpr auto game_is_phased(int) -> decltype(G::kPhased) { return G::kPhased; }
 template <class G> ISMCTS_HDI constexpr bool game_is_phased(long) { return false; }
 
+// Draws a word of the stream serves in a game (philox.cuh): Game::kDrawsPerWord, else two.
+template <class G> ISMCTS_HDI constexpr auto game_draws_per_word(int) -> decltype(G::kDrawsPerWord) { return G::kDrawsPerWord; }
+template <class G> ISMCTS_HDI constexpr uint32_t game_draws_per_word(long) { return LaneRng::kDrawsPerWord; }
+
 // Bytes of per-block tables a game keeps behind the scratch of the block's games (Game::kBlockExtraBytes).
 template <class G> ISMCTS_HDI constexpr auto game_block_extra_bytes(int) -> decltype(G::kBlockExtraBytes) { return G::kBlockExtraBytes; }
 template <class G> ISMCTS_HDI constexpr uint32_t game_block_extra_bytes(long) { return 0; }
@@ -533,6 +537,7 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
         if (!kShared) lane.tree.init_roots();                 // shared trees: init_shared_roots
         lane.tree_players = Game::root_players(lane.prep);
         lane.rng.init(P.seed, P.pos_base + pos, tree_global, ring, ring_stride);
+        lane.rng.per_word = game_draws_per_word<Game>(0);
         if (P.iterations > 0) {
             // the iterations of a tree, dealt round-robin to its lanes
             const uint64_t of_tree = tree_iterations(P.iterations, P.trees_total, tree_global);
@@ -621,6 +626,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
         lane.first_iteration = gtid % per_position;
         lane.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
         lane.rng.init(P.seed, P.pos_base + pos, 0, ring, ring_stride);
+        lane.rng.per_word = game_draws_per_word<Game>(0);
         lane.start_iteration();
     }
     lane.run(gtid, scratch, scratch_stride, column, ring, ring_stride);

@@ -8,8 +8,10 @@
 // random choice can be recomputed from its coordinates alone and the result of a
 // search does not depend on how trees map to threads, warps or GPUs.  A random
 // choice is "uniform integer below n" = the high half of word * n; the low half
-// is the word of the next choice, so a word serves TWO consecutive choices (the
-// pair deviates from uniform by less than n1 * n2 / 2^32 < 1e-6).  align() moves
+// is the word of the next choice, so a word serves several consecutive choices: TWO
+// in general (the pair deviates from uniform by less than n1 * n2 / 2^32 < 1e-6
+// for n <= 225), THREE in Knockout Whist (n <= 52: n1 * n2 * n3 / 2^32 < 3.3e-5; a
+// rollout triple, n <= 7, less than 1e-7) — `per_word`.  align() moves
 // on to the next block of four words: Knockout Whist aligns around every sequence
 // of chance events and at the start of the rollout, which makes the lanes of a
 // warp generate their blocks in the same steps (kw_game.cuh).  The oracle
@@ -43,19 +45,20 @@ ISMCTS_DEV void philox4x32_10(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3
 // (phase_begin / block / phase_end).
 struct LaneRng {
     static constexpr uint32_t kRingWords = 8;
-    static constexpr uint32_t kDrawsPerWord = 2;
+    static constexpr uint32_t kDrawsPerWord = 2;   // unless a game says otherwise (Game::kDrawsPerWord)
     uint32_t k0, k1;      // key = seed
     uint32_t c1, c2, c3;  // iteration, tree, position
     uint32_t next_block;  // next block (d / 4) to generate into the ring
     uint32_t d;           // next word to hand out; words [d, 4 * next_block) wait in the ring
     uint32_t w, left;     // the word being used up and the draws it still serves
+    uint32_t per_word;    // draws a word serves
     uint32_t* ring;       // ring[(d % 8) * stride]
     uint32_t stride;
 
     ISMCTS_DEV void init(uint64_t seed, uint32_t pos, uint32_t tree, uint32_t* ring_base, uint32_t ring_stride)
     {
         k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
-        c1 = 0; c2 = tree; c3 = pos; next_block = 0; d = 0; w = 0; left = 0;
+        c1 = 0; c2 = tree; c3 = pos; next_block = 0; d = 0; w = 0; left = 0; per_word = kDrawsPerWord;
         ring = ring_base; stride = ring_stride;
     }
 
@@ -99,7 +102,7 @@ struct LaneRng {
     // Uniform integer in [0, n).
     ISMCTS_DEV uint32_t below(uint32_t n)
     {
-        if (left == 0) { w = word(); left = kDrawsPerWord; }
+        if (left == 0) { w = word(); left = per_word; }
         const uint64_t p = (uint64_t)w * n;
         w = (uint32_t)p;
         --left;
@@ -121,7 +124,7 @@ struct LaneRng {
     }
     ISMCTS_DEV uint32_t below_direct(uint32_t n)
     {
-        if (left == 0) { w = word_direct(); left = kDrawsPerWord; }
+        if (left == 0) { w = word_direct(); left = per_word; }
         const uint64_t p = (uint64_t)w * n;
         w = (uint32_t)p;
         --left;
@@ -136,14 +139,13 @@ struct LaneRng {
     }
 
     // A phase that generates its blocks in registers: aligns and returns the index of its first
-    // block; `draws` draws later (two per word, four words per block) phase_end() moves the
-    // stream past the words they used.  The ring is empty afterwards and the words up to the
+    // block; `words` words later (four words per block) phase_end() moves the stream past them.  The ring is empty afterwards and the words up to the
     // next block boundary are NOT in it: the next use of the stream must be an align() — which is
     // what follows every phase of Knockout Whist — or the end of the iteration.
     ISMCTS_DEV uint32_t phase_begin() { align(); return d >> 2; }
-    ISMCTS_DEV void phase_end(uint32_t first_block, uint32_t draws)
+    ISMCTS_DEV void phase_end(uint32_t first_block, uint32_t words)
     {
-        d = 4u * first_block + ((draws + 1u) >> 1);
+        d = 4u * first_block + words;
         next_block = (d + 3u) >> 2;
         left = 0;
     }

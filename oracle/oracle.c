@@ -47,9 +47,12 @@ uint32_t orc_draw_word(uint64_t seed, uint32_t pos, uint32_t tree, uint32_t iter
 }
 
 /* A random stream position.  The words of one iteration are d = 0, 1, 2, ... of the stream
- * (seed; pos, tree, iteration).  A word serves TWO consecutive draws: "uniform integer below
- * n" is the high half of word * n and the low half is the word of the second draw (the
- * deviation from uniform of the pair is below n1 * n2 / 2^32 < 1e-6).  rng_align() moves on to
+ * (seed; pos, tree, iteration).  A word serves several consecutive draws: "uniform integer below
+ * n" is the high half of word * n and the low half is the word of the next draw.  TWO draws per
+ * word in general (the deviation from uniform of the pair is below n1 * n2 / 2^32 < 1e-6 for the
+ * choices of m,n,k, n <= 225); THREE in Knockout Whist, whose choices are among at most 52 (the
+ * triple deviates by less than n1 * n2 * n3 / 2^32 < 3.3e-5, a rollout triple, n <= 7, by less than
+ * 1e-7).  rng_align() moves on to
  * the start of the next Philox block of four words: Knockout Whist aligns the stream around
  * every sequence of chance events and at the start of the rollout, so that all playouts of a
  * position consume their words in the same rhythm (on the GPU: the lanes of a warp generate
@@ -59,9 +62,12 @@ typedef struct rng {
     uint32_t pos, tree, iteration, d;
     orc_counters* cnt;
     uint32_t w, left;      /* the word being used up and the draws it still serves */
+    uint32_t per_word;     /* draws a word serves (0 = RNG_DRAWS_PER_WORD) */
 } rng;
 
-enum { RNG_DRAWS_PER_WORD = 2 };
+enum { RNG_DRAWS_PER_WORD = 2, RNG_DRAWS_PER_WORD_KW = 3 };
+
+static uint32_t draws_per_word_of(uint32_t game) { return game == ISMCTS_GAME_KW ? RNG_DRAWS_PER_WORD_KW : RNG_DRAWS_PER_WORD; }
 
 /* The next whole word (EXP3 samples with all 32 bits); drops what is left of the current one. */
 static uint32_t rng_word(rng* r)
@@ -74,7 +80,7 @@ static uint32_t rng_word(rng* r)
 /* Uniform integer in [0, n). */
 static uint32_t rng_below(rng* r, uint32_t n)
 {
-    if (r->left == 0) { r->w = rng_word(r); r->left = RNG_DRAWS_PER_WORD; }
+    if (r->left == 0) { r->w = rng_word(r); r->left = r->per_word ? r->per_word : RNG_DRAWS_PER_WORD; }
     const uint64_t p = (uint64_t)r->w * n;
     r->w = (uint32_t)p;
     r->left--;
@@ -716,16 +722,16 @@ static uint32_t og_stride(uint32_t kind) { return kind == ISMCTS_GAME_MNK || kin
 
 /* ======================================================== exported game API */
 
-static rng generator_rng(uint64_t seed, uint32_t stream, uint32_t tree, uint32_t iteration, uint32_t d)
+static rng generator_rng(uint64_t seed, uint32_t stream, uint32_t tree, uint32_t iteration, uint32_t d, uint32_t game)
 {
-    rng r = { seed, stream, tree, iteration, d, NULL, 0, 0 };
+    rng r = { seed, stream, tree, iteration, d, NULL, 0, 0, draws_per_word_of(game) };
     return r;
 }
 
 int orc_kw_deal(uint64_t seed, uint32_t stream, uint32_t num_players, ismcts_kw_state* out)
 {
     okw g;
-    rng r = generator_rng(seed, stream, 0xFFFFFFFFu, 0xFFFFFFFFu, 0);
+    rng r = generator_rng(seed, stream, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, ISMCTS_GAME_KW);
     okw_new(&g, (int)num_players, &r);
     okw_to_pod(&g, out);
     return 0;
@@ -744,7 +750,7 @@ int orc_kw_apply(ismcts_kw_state* s, uint32_t move, uint64_t seed, uint32_t stre
 {
     okw g;
     okw_from_pod(&g, s);
-    rng r = generator_rng(seed, stream, 0xFFFFFFFEu, 0, draw_counter ? *draw_counter : 0);
+    rng r = generator_rng(seed, stream, 0xFFFFFFFEu, 0, draw_counter ? *draw_counter : 0, ISMCTS_GAME_KW);
     const int rc = okw_apply(&g, (int)move, &r);
     if (rc) return rc;
     if (draw_counter) *draw_counter = r.d;
@@ -762,7 +768,7 @@ int orc_kw_determinise(ismcts_kw_state* s, uint32_t observer, uint64_t seed, uin
                        uint32_t iteration, uint32_t* draw_counter)
 {
     okw g; okw_from_pod(&g, s);
-    rng r = generator_rng(seed, pos, tree, iteration, draw_counter ? *draw_counter : 0);
+    rng r = generator_rng(seed, pos, tree, iteration, draw_counter ? *draw_counter : 0, ISMCTS_GAME_KW);
     okw_determinise(&g, (int)observer, &r);
     if (draw_counter) *draw_counter = r.d;
     okw_to_pod(&g, s);
@@ -837,7 +843,7 @@ int orc_goof_init(uint64_t seed, uint32_t stream, ismcts_goof_state* out)
        uniformly random prize not placed yet */
     ogoof g;
     memset(&g, 0, sizeof g);
-    rng r = generator_rng(seed, stream, 0xFFFFFFFFu, 0xFFFFFFFFu, 0);
+    rng r = generator_rng(seed, stream, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, ISMCTS_GAME_GOOF);
     unsigned char left[13];
     memset(left, 1, sizeof left);
     for (int p = 0; p < 2; ++p) for (int k = 0; k < 13; ++k) g.hand[p][k] = 1;
@@ -909,7 +915,7 @@ uint32_t orc_playout(uint32_t game, const void* root, uint64_t seed, uint32_t po
 {
     ogame g;
     if (og_load(&g, game, root)) return 0xFFFFFFFFu;
-    rng r = { seed, pos, tree, iteration, 0, NULL, 0, 0 };
+    rng r = { seed, pos, tree, iteration, 0, NULL, 0, 0, draws_per_word_of(game) };
     og_determinise(&g, og_player(&g), &r);
     const uint32_t plies = og_rollout(&g, &r);
     uint32_t winner;
@@ -1127,7 +1133,7 @@ int orc_so_search(uint32_t game, const void* root, uint32_t policy, double explo
     if (og_load(&g, game, root)) return ISMCTS_ERR_INVALID;
     otree t;
     otree_init(&t);
-    rng r = { seed, pos, tree, 0, 0, counters, 0, 0 };
+    rng r = { seed, pos, tree, 0, 0, counters, 0, 0, draws_per_word_of(game) };
     for (uint64_t it = 0; it < iterations; ++it) {
         r.iteration = (uint32_t)it;
         so_iteration(&t, &g, policy, exploration, &r);
@@ -1206,7 +1212,7 @@ int orc_mo_search(uint32_t game, const void* root, uint32_t policy, double explo
     if (og_load(&g, game, root)) return ISMCTS_ERR_INVALID;
     motrees m;
     mo_init(&m, &g);
-    rng r = { seed, pos, tree, 0, 0, counters, 0, 0 };
+    rng r = { seed, pos, tree, 0, 0, counters, 0, 0, draws_per_word_of(game) };
     for (uint64_t it = 0; it < iterations; ++it) {
         r.iteration = (uint32_t)it;
         mo_iteration(&m, &g, policy, exploration, &r);
@@ -1260,7 +1266,7 @@ int orc_root_parallel(uint32_t game, uint32_t solver, const void* root, uint32_t
     for (uint32_t j = 0; j < trees; ++j) {
         const uint32_t tg = tree_base + j;
         const uint64_t n_it = orc_tree_iterations(iterations, trees_total, tg);
-        rng r = { seed, pos, tg, 0, 0, counters, 0, 0 };
+        rng r = { seed, pos, tg, 0, 0, counters, 0, 0, draws_per_word_of(game) };
         if (solver == ISMCTS_SOLVER_SO) {
             otree t;
             otree_init(&t);
