@@ -461,3 +461,36 @@ def test_phantom_determinisation_keeps_known_positions():
     nodes = O.so_search(O.GAME_PHANTOM, s, 400, seed=3)
     top = nodes[1:][nodes[1:]["parent"] == 0]
     assert sorted(top["move"].tolist()) == O.phantom_legal(s) == [0, 1, 2, 3, 5, 7, 8]
+
+
+# ---- the generator: Philox4x32-10 (Salmon et al., SC'11), pinned by the published known-answer vectors
+# of the Random123 distribution (kat_vectors: "philox4x32 10 ...")
+
+PHILOX_KAT = [
+    ([0x00000000] * 4, [0x00000000] * 2, [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+    ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+    ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+     [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+]
+
+
+@pytest.mark.parametrize("ctr,key,expected", PHILOX_KAT)
+def test_oracle_philox_matches_the_published_vectors(ctr, key, expected):
+    L = O.lib()
+    out = (C.c_uint32 * 4)()
+    L.orc_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    assert list(out) == expected
+
+
+def test_stream_word_is_the_philox_block_of_its_coordinates():
+    # word d of (seed; pos, tree, iteration) = Philox(counter = (d / 4, iteration, tree, pos), key = seed)[d % 4]
+    L = O.lib()
+    seed, pos, tree, iteration = 0x299F31D0A4093822, 0x03707344, 0x13198A2E, 0x85A308D3
+    out = (C.c_uint32 * 4)()
+    for block in (0, 1, 0x243F6A88):
+        L.orc_philox4x32_10((C.c_uint32 * 4)(block, iteration, tree, pos),
+                            (C.c_uint32 * 2)(seed & 0xFFFFFFFF, seed >> 32), out)
+        for i in range(4):
+            d = (4 * block + i) & 0xFFFFFFFF
+            if d >> 2 == block:
+                assert L.orc_draw_word(seed, pos, tree, iteration, d) == out[i]
