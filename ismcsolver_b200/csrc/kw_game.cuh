@@ -134,7 +134,8 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
     using Root = ismcts_kw_state;
     using Prepared = KwPrepared;
 
-    enum Mode : uint32_t { kPlay = 0, kDeal = 1, kTie = 2, kStart = 3 };   // kStart: the determinisation has not begun (start())
+    // kStart: the determinisation has not begun (start()); kRoundEnd: inside play_phase only, the round is over
+    enum Mode : uint32_t { kPlay = 0, kDeal = 1, kTie = 2, kStart = 3, kRoundEnd = 4 };
 
     static constexpr uint64_t kFullDeck = (uint64_t(1) << 52) - 1;
     static constexpr uint64_t kTrumpChoices = uint64_t(1) | (uint64_t(1) << 13) | (uint64_t(1) << 26) | (uint64_t(1) << 39);
@@ -528,6 +529,8 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
     // doMove, knockoutwhist.cpp:95-115.  Leaves the hand of the next player to move in (`list`, `held`).
     // (The state is read before the first store and written after the last load: when the game lives in
     // memory — a tree operation — the compiler must assume that a store to a hand changes it.)
+    // kDefer: the end of a round is only recorded (mode = kRoundEnd); the caller runs finish_round() later.
+    template <bool kDefer = false>
     ISMCTS_DEV void play_place(uint32_t place, uint64_t& list, uint32_t& held)
     {
         uint64_t* const lists = hands();
@@ -559,7 +562,7 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         held = held_rows[who * pitch];
         player = who; trick_len = len; lead_suit = lead; win_key = key_won; win_player = who_won;
         tricks = taken_all; best = most;
-        if (held == 0) finish_round();
+        if (held == 0) { if constexpr (kDefer) mode = kRoundEnd; else finish_round(); }
     }
 
     // doMove for a card id (a move of the tree or of a caller; no chance event pending).
@@ -628,37 +631,30 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         if (mine && mode == kStart) begin_start(deal, prep_of());
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;
         BlockWords words;
-        uint32_t draws = 0;
+        words.turn(rng, first_block, 0);
+        // A tie-break is the first draw of its lane (the first third of word 0) and is made here, once, so that
+        // the loop below is the deal step alone (three copies of it: the shorter they are the better they are
+        // fetched).  `used`: thirds of the current word the lane has used before the loop.
+        uint32_t draws = 0, used = 0;
+        if (mine && mode == kTie) { draws = 1; used = 1; break_tie(deal, words.below(popc32(tied))); }
         for (uint32_t t = 0; warp_any(active && mode != kPlay); ++t) {
-            words.turn(rng, first_block, t);
+            if (t != 0) words.turn(rng, first_block, t);
 #pragma unroll
             for (uint32_t part = 0; part < kDrawsPerWord; ++part) {
-                if (active && mode != kPlay) {
+                if (active && mode == kDeal && (part != 0 || used == 0)) {
                     ++draws;
-                    chance_draw(deal, words.below(chance_count(deal)));
+                    deal_card(deal, take_from_pile(deal, words.below(deal.pile_n)));
+                    if (--deal.deal_left == 0) { close_hand(deal); next_hand(deal); }
                 }
             }
+            used = 0;
         }
         if (mine) { rng.phase_end(first_block, (draws + kDrawsPerWord - 1u) / kDrawsPerWord); rng.align(); }
     }
 
-    // One move of the default policy (simulate, solverbase.h:36-43) from the hand (`list`, `held`)
-    // of the player to move: uniform over validMoves(), knockoutwhist.cpp:122-136.
-    ISMCTS_DEV void rollout_step(BlockWords& words, const uint32_t* table, uint64_t& list, uint32_t& held)
-    {
-        if (request_trump) {
-            play(13u * words.below(4));                   // the round winner calls trumps: one of the four suits
-            list = list_of(player);
-            held = held_of(player);
-        } else {
-            const uint32_t places = legal_places(held);
-            const uint32_t j = words.below(popc32(places));
-            play_place((table[places] >> (3u * j)) & 7u, list, held);
-        }
-    }
-
-    // Rollout moves for the lanes with `rolling` until their round ends (a chance event becomes
-    // pending) or their game does.  `plies` counts the moves.
+    // Rollout moves (simulate, solverbase.h:36-43: uniform over validMoves(), knockoutwhist.cpp:122-136) for the
+    // lanes with `rolling` until their round ends (a chance event becomes pending) or their game does.
+    // `plies` counts the moves.
     template <class Rng>
     ISMCTS_DEV void play_phase(Rng& rng, bool rolling, uint32_t& plies)
     {
@@ -667,20 +663,29 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;   // the rollout and every round start a block
         const uint32_t* table = place_table();
         BlockWords words;
-        uint32_t draws = 0;
+        words.turn(rng, first_block, 0);
+        // The round winner calls trumps: one of the four suits.  Only the first move of a phase can be that
+        // (the request is made by the end of a round, which ends the phase), so it is made here, once, and the
+        // loop below is the card step alone; the end of a round is recorded there and run after the loop.
+        uint32_t draws = 0, used = 0;
+        if (mine && request_trump) { draws = 1; used = 1; play(13u * words.below(4)); }
         // the hand of the player to move (lanes that do not take part may hold no game at all)
         uint64_t list = mine ? list_of(player) : 0;
         uint32_t held = mine ? held_of(player) : 0;
         for (uint32_t t = 0; warp_any(rolling && mode == kPlay && tricks_left != 0); ++t) {
-            words.turn(rng, first_block, t);
+            if (t != 0) words.turn(rng, first_block, t);
 #pragma unroll
             for (uint32_t part = 0; part < kDrawsPerWord; ++part) {
-                if (rolling && mode == kPlay && tricks_left != 0) {
+                if (rolling && mode == kPlay && tricks_left != 0 && (part != 0 || used == 0)) {
                     ++draws;
-                    rollout_step(words, table, list, held);
+                    const uint32_t places = legal_places(held);
+                    const uint32_t j = words.below(popc32(places));
+                    play_place<true>((table[places] >> (3u * j)) & 7u, list, held);
                 }
             }
+            used = 0;
         }
+        if (mode == kRoundEnd) { mode = kPlay; finish_round(); }
         plies += draws;
         if (mine) rng.phase_end(first_block, (draws + kDrawsPerWord - 1u) / kDrawsPerWord);
     }
