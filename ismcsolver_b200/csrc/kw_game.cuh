@@ -429,13 +429,14 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         d.deal_place = top_place(d.deal_held);
     }
     ISMCTS_DEV void close_hand(const Deal& d) const { set_held(d.deal_player, d.deal_held); }
+    // (A hand never gets an eighth card in a legal game; one that did would land on the unused eighth byte of
+    // the list and set no `held` bit: dropped, without a branch.)
     ISMCTS_DEV void deal_card(Deal& d, uint32_t code) const
     {
-        if (d.deal_place < kPlaces) {
-            reinterpret_cast<uint8_t*>(hands() + d.deal_player * kStride)[d.deal_place] = (uint8_t)code;
-            d.deal_held |= 1u << (8u * (code >> 4) + d.deal_place);
-            ++d.deal_place;
-        }
+        const uint32_t place = d.deal_place < kPlaces ? d.deal_place : kPlaces;
+        reinterpret_cast<uint8_t*>(hands() + d.deal_player * kStride)[place] = (uint8_t)code;
+        d.deal_held |= (1u << (8u * (code >> 4) + place)) & 0x7F7F7F7Fu;
+        ++d.deal_place;
     }
 
     // Starts dealing from the pile: `sizes` holds 4 bits per player, the number of cards each
