@@ -653,6 +653,23 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         if (mine) { rng.phase_end(first_block, (draws + kDrawsPerWord - 1u) / kDrawsPerWord); rng.align(); }
     }
 
+    struct PlaceTableRef {
+#if defined(__CUDA_ARCH__)
+        uint32_t address;
+        ISMCTS_DEV explicit PlaceTableRef(const uint32_t* t) : address((uint32_t)__cvta_generic_to_shared(t)) { asm volatile("" : "+r"(address)); }
+        ISMCTS_DEV uint32_t at(uint32_t i) const
+        {
+            uint32_t v;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(address + 4u * i));
+            return v;
+        }
+#else
+        const uint32_t* table;
+        ISMCTS_DEV explicit PlaceTableRef(const uint32_t* t) : table(t) {}
+        ISMCTS_DEV uint32_t at(uint32_t i) const { return table[i]; }
+#endif
+    };
+
     // Rollout moves (simulate, solverbase.h:36-43: uniform over validMoves(), knockoutwhist.cpp:122-136) for the
     // lanes with `rolling` until their round ends (a chance event becomes pending) or their game does.
     // `plies` counts the moves.
@@ -662,7 +679,9 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
         const bool mine = rolling && mode == kPlay && tricks_left != 0;
         if (!warp_any(mine)) return;
         const uint32_t first_block = mine ? rng.phase_begin() : 0u;   // the rollout and every round start a block
-        const uint32_t* table = place_table();
+        // (the table is addressed through a 32-bit shared-memory address the compiler cannot recompute: ptxas
+        // would otherwise derive the address of the block's shared memory again in every step, four instructions)
+        const PlaceTableRef table(place_table());
         BlockWords words;
         words.turn(rng, first_block, 0);
         // The round winner calls trumps: one of the four suits.  Only the first move of a phase can be that
@@ -681,7 +700,7 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
                     ++draws;
                     const uint32_t places = legal_places(held);
                     const uint32_t j = words.below(popc32(places));
-                    play_place<true>((table[places] >> (3u * j)) & 7u, list, held);
+                    play_place<true>((table.at(places) >> (3u * j)) & 7u, list, held);
                 }
             }
             used = 0;
