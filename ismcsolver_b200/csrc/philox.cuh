@@ -63,7 +63,16 @@ struct LaneRng {
     }
 
     // Block `index` of the current iteration.
-    ISMCTS_DEV void block(uint32_t index, uint32_t out[4]) const { philox4x32_10(index, c1, c2, c3, k0, k1, out); }
+    ISMCTS_DEV void block(uint32_t index, uint32_t out[4]) const
+    {
+        uint32_t a = k0, b = k1;
+#if defined(__CUDA_ARCH__)
+        // (the key as the compiler cannot see through it: the round keys are then derived inside the block — two
+        // additions per round — instead of twenty registers held for them across the loops that call this)
+        asm volatile("" : "+r"(a), "+r"(b));
+#endif
+        philox4x32_10(index, c1, c2, c3, a, b, out);
+    }
 
     // Generates the next block of four words into its half of the ring.
     ISMCTS_DEV void refill()
