@@ -275,6 +275,10 @@ struct KwGameT : std::conditional_t<kCarry, KwAddresses, KwNoAddresses> {
     ISMCTS_DEV void rebind(uint64_t* scratch, uint32_t, uint32_t column)
     {
         if constexpr (kCarry) {
+#if defined(__CUDA_ARCH__)
+            // (the column as a value the compiler cannot read again from the thread index: S2R has a long latency)
+            asm volatile("" : "+r"(column));
+#endif
             this->hands_ = hands_of(scratch, column); this->helds_ = helds_of(scratch, column); this->pile_ = pile_of(scratch, column);
             this->table_ = KwPlaceTable::table(scratch + kHandWords * kStride);
         }
