@@ -35,10 +35,10 @@ ITERATIONS_PER_DECISION = 1_000_000
 DEAL_SEED = 0x1535C75B200           # printed with every line (config.deal_seed)
 # algorithmic node traffic of one KW4 iteration (select 1.28 KB + expand 232 B + backprop 80 B)
 ALGO_BYTES_PER_ITERATION = 1600.0
-# ncu (profiles/r01_final8_ncu_raw.txt): warp-instructions executed and DRAM bytes per iteration of the search kernel
-NCU_PROFILE = "profiles/r01_final8_ncu_raw.txt"
-NCU_WARP_INST_PER_ITERATION = 37781353979.0 / 64e6
-NCU_DRAM_BYTES_PER_ITERATION = (81.153326e9 + 30.062364e9) / 64e6
+# ncu (profiles/r01_final9_ncu_raw.txt): warp-instructions executed and DRAM bytes per iteration of the search kernel
+NCU_PROFILE = "profiles/r01_final9_ncu_raw.txt"
+NCU_WARP_INST_PER_ITERATION = 37755352886.0 / 64e6
+NCU_DRAM_BYTES_PER_ITERATION = (80.701630e9 + 29.203759e9) / 64e6
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
