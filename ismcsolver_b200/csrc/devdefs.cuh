@@ -49,6 +49,13 @@ ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p
 ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { atomicOr((unsigned long long*)p, (unsigned long long)v); }
 ISMCTS_DEV void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
 ISMCTS_DEV void fence_device() { __threadfence(); }
+ISMCTS_DEV void store_u32_release(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 // Starts bringing the line at p into L2 (no register, no wait).
 ISMCTS_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return __ldcg(p); }
@@ -84,6 +91,8 @@ ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t old
 ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { *p |= v; }
 ISMCTS_DEV void atomic_add_f64(double* p, double v) { *p = ISMCTS_DADD(*p, v); }
 ISMCTS_DEV void fence_device() {}
+ISMCTS_DEV void store_u32_release(uint32_t* p, uint32_t v) { *p = v; }
+ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p) { return *p; }
 ISMCTS_DEV void prefetch_l2(const void*) {}
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return *p; }

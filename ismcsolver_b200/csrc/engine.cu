@@ -43,9 +43,11 @@ __host__ __device__ constexpr size_t block_smem()
 // Root records -> the register image every iteration starts from (one thread per position).
 // (Games that find their scratch themselves — Knockout Whist — use the block's dynamic shared memory.)
 template <class Game>
-__global__ void prepare_kernel(const typename Game::Root* roots, typename Game::Prepared* prepared, uint32_t n)
+__global__ void prepare_kernel(const typename Game::Root* roots, typename Game::Prepared* prepared, uint32_t n,
+                               uint64_t* start_ns)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && start_ns) *start_ns = global_timer_ns();    // time mode: the clock every lane's deadline counts from
     if (i >= n) return;
     uint64_t scratch[game_home_in_scratch<Game>(0) ? 1 : Game::kHandWords];
     Game::prepare(roots + i, prepared + i, scratch);
@@ -120,6 +122,7 @@ struct ismcts_ctx {
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
     uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
+    uint64_t* start_ns = nullptr;                             // time mode: device clock at launch (prepare_kernel)
 
     int min_blocks = 8;          // resident CTAs per SM the SO/UCB1 Knockout Whist kernel is compiled for; ISMCTS_MIN_BLOCKS
 
@@ -190,6 +193,11 @@ int ismcts_create(int device, ismcts_ctx** out)
                                                       cudaGetErrorString(cudaGetLastError()));
     }
     ctx->stream = ctx->own_stream;
+    if (cudaMalloc((void**)&ctx->start_ns, sizeof(uint64_t)) != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return fail(nullptr, ISMCTS_ERR_CUDA, "cannot allocate device memory");
+    }
     if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(v);
     *out = ctx;
     return ISMCTS_OK;
@@ -201,7 +209,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
-    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters);
+    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters); cudaFree(ctx->start_ns);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -270,7 +278,7 @@ static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
     if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
     if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
-        if ((d->flags & 0xFCu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
+        if ((d->flags & 0xFF0000FCu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");   // lanes: bits 8..23
         if ((d->flags >> ISMCTS_FLAG_LANES_SHIFT) == 0) return fail(ctx, ISMCTS_ERR_INVALID, "shared tree: lanes must be > 0");
     } else if ((d->flags & ~ISMCTS_FLAG_KW_MAX4) != 0) {
         return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
@@ -279,6 +287,52 @@ static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
     if ((uint64_t)d->n_positions * d->trees > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many trees");
     if (d->trees_total < d->tree_base + d->trees) return fail(ctx, ISMCTS_ERR_INVALID, "trees_total < tree_base + trees");
     if (d->iterations == 0 && d->time_ns == 0) return fail(ctx, ISMCTS_ERR_INVALID, "iterations or time_ns must be > 0");
+    return ISMCTS_OK;
+}
+
+// Host records of root positions: everything the kernels index with must be in range (a malformed record
+// would address the scratch of another lane).  ismcts_search_device takes device records and cannot look at
+// them: its callers guarantee the same.
+static int validate_roots(ismcts_ctx* ctx, uint32_t game, const void* roots, uint32_t n)
+{
+    const size_t state = ismcts_state_size(game);
+    auto bad = [&](uint32_t p, const char* what) {
+        return fail(ctx, ISMCTS_ERR_INVALID, "position " + std::to_string(p) + ": " + what);
+    };
+    for (uint32_t p = 0; p < n; ++p) {
+        const uint8_t* rec = (const uint8_t*)roots + p * state;
+        if (game == ISMCTS_GAME_KW) {
+            const ismcts_kw_state* s = (const ismcts_kw_state*)rec;
+            if (s->num_players < 2 || s->num_players > ISMCTS_KW_MAX_PLAYERS) return bad(p, "Knockout Whist: 2..7 players");
+            const uint32_t all = (1u << s->num_players) - 1u;
+            if (s->alive_mask == 0 || (s->alive_mask & ~all)) return bad(p, "Knockout Whist: alive_mask names no player or a player that does not exist");
+            if (s->player >= s->num_players || s->dealer >= s->num_players) return bad(p, "Knockout Whist: player or dealer out of range");
+            if (s->trump > 3 || s->tricks_left > 7 || s->request_trump > 1) return bad(p, "Knockout Whist: trump, tricks_left or request_trump out of range");
+            if (s->trick_len >= 8 || s->trick_len > (uint32_t)__builtin_popcount(s->alive_mask)) return bad(p, "Knockout Whist: trick longer than the players still in");
+            for (uint32_t i = 0; i < s->trick_len; ++i)
+                if (s->trick_player[i] >= s->num_players || s->trick_card[i] >= ISMCTS_KW_CARDS) return bad(p, "Knockout Whist: trick entry out of range");
+            for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q) {
+                // a hand has seven places (the game never deals more than seven cards)
+                if (__builtin_popcountll(s->hands[q]) > 7) return bad(p, "Knockout Whist: a hand holds more than seven cards");
+                if (s->hands[q] >> ISMCTS_KW_CARDS) return bad(p, "Knockout Whist: a hand holds a card that does not exist");
+                if (q >= s->num_players && s->hands[q]) return bad(p, "Knockout Whist: a player that does not exist holds cards");
+                if (s->tricks_taken[q] > 7) return bad(p, "Knockout Whist: more than seven tricks taken");
+            }
+            if (s->unknown >> ISMCTS_KW_CARDS) return bad(p, "Knockout Whist: an unknown card that does not exist");
+        } else if (game == ISMCTS_GAME_MNK || game == ISMCTS_GAME_PHANTOM) {
+            // (both records begin with stones[2][4]; m, n, k, player, result2 follow the boards)
+            const uint8_t* f = game == ISMCTS_GAME_MNK ? &((const ismcts_mnk_state*)rec)->m : &((const ismcts_phantom_state*)rec)->m;
+            const uint32_t m = f[0], nn = f[1], k = f[2], player = f[3];
+            const int r2 = (int8_t)f[4];
+            if (m == 0 || nn == 0 || m * nn > ISMCTS_MNK_MAX_CELLS) return bad(p, "m,n,k: the board must have 1..256 cells");
+            if (k == 0 || player > 1 || r2 < -1 || r2 > 2) return bad(p, "m,n,k: k, player or result2 out of range");
+        } else {
+            const ismcts_goof_state* s = (const ismcts_goof_state*)rec;
+            if (s->n_prizes > 13 || s->player > 2 || s->draw_prize > 1 || s->current_prize > 12) return bad(p, "Goofspiel: field out of range");
+            if ((s->hands[0] | s->hands[1]) >> 13) return bad(p, "Goofspiel: a hand holds a rank that does not exist");
+            if (s->moves[0] > 12 || s->moves[1] > 12) return bad(p, "Goofspiel: bid out of range");
+        }
+    }
     return ISMCTS_OK;
 }
 
@@ -306,7 +360,7 @@ static int launch_prepare(ismcts_ctx* ctx, const void* d_roots, uint32_t n)
     if (rc) return rc;
     const size_t smem = game_home_in_scratch<Game>(0) ? (size_t)128 * Game::kHandWords * sizeof(uint64_t) : 0;
     prepare_kernel<Game><<<(n + 127) / 128, 128, smem, ctx->stream>>>((const typename Game::Root*)d_roots,
-                                                                  (typename Game::Prepared*)ctx->prepared, n);
+                                                                  (typename Game::Prepared*)ctx->prepared, n, ctx->start_ns);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return ISMCTS_OK;
@@ -448,6 +502,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
     P.playout_out = nullptr;
     P.lanes_per_tree = width; P.node_counters = ctx->counters;
+    P.start_ns = ctx->start_ns;
 
     ctx->last_log2cap = log2cap; ctx->last_lanes = tables; ctx->last_game = d->game;
     ctx->last_solver = d->solver; ctx->last_policy = d->policy;
@@ -528,6 +583,8 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     int rc = validate(ctx, d);
     if (rc) return rc;
     if (!roots || !out || !out->visits) return fail(ctx, ISMCTS_ERR_INVALID, "null host pointer");
+    rc = validate_roots(ctx, d->game, roots, d->n_positions);
+    if (rc) return rc;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const uint32_t stride = ismcts_move_stride(d->game);
     const size_t state = ismcts_state_size(d->game);
@@ -542,16 +599,10 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     uint64_t* dv = ctx->out; uint64_t* ds = dv + per_arr; uint64_t* da = ds + per_arr; uint64_t* di = da + per_arr;
     ismcts_search_desc desc = *d;
     if (d->game == ISMCTS_GAME_KW) {
-        // positions with at most four players use the denser shared-memory layout of the jobs kernel
+        // positions with at most four players use the search kernel with four seats of scratch per lane
         bool max4 = true;
-        for (uint32_t p = 0; p < d->n_positions; ++p) {
-            const ismcts_kw_state* rec = (const ismcts_kw_state*)((const uint8_t*)roots + p * state);
-            max4 = max4 && rec->num_players <= 4;
-            // a hand has seven places (the game never deals more than seven cards)
-            for (uint32_t q = 0; q < ISMCTS_KW_MAX_PLAYERS; ++q)
-                if (__builtin_popcountll(rec->hands[q]) > 7)
-                    return fail(ctx, ISMCTS_ERR_INVALID, "Knockout Whist: a hand holds more than seven cards");
-        }
+        for (uint32_t p = 0; p < d->n_positions; ++p)
+            max4 = max4 && ((const ismcts_kw_state*)((const uint8_t*)roots + p * state))->num_players <= 4;
         if (max4) desc.flags |= ISMCTS_FLAG_KW_MAX4; else desc.flags &= ~ISMCTS_FLAG_KW_MAX4;
     }
     rc = ismcts_search_device(ctx, &desc, ctx->roots, dv, ds, da, di);
@@ -590,6 +641,7 @@ extern "C" int ismcts_playouts(ismcts_ctx* ctx, uint32_t game, const void* roots
 {
     if (!ctx || !roots || !out_result || n_positions == 0 || per_position == 0) return ISMCTS_ERR_INVALID;
     if (game > ISMCTS_GAME_PHANTOM) return fail(ctx, ISMCTS_ERR_INVALID, "unknown game");
+    if (int bad = validate_roots(ctx, game, roots, n_positions)) return bad;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t root_bytes = (size_t)n_positions * ismcts_state_size(game);
     const size_t n = (size_t)n_positions * per_position;

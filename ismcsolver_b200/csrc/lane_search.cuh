@@ -61,6 +61,9 @@ struct SearchParams {
     // tree parallelisation: `lanes_per_tree` lanes search ONE tree together (1 = private trees)
     uint32_t lanes_per_tree;
     uint32_t* node_counters; // [n_positions * trees] nodes created per shared tree (root included)
+    // time mode: the device clock when the search was launched (written by prepare_kernel): ONE deadline for
+    // all lanes, whichever wave of blocks they run in (null: every lane starts its own clock)
+    const uint64_t* start_ns;
 };
 
 // Iterations of one tree in count mode: the reference drains one shared counter
@@ -173,7 +176,10 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     {
         if (kTree && !kShared && tree.count + kTrees > P.max_nodes) return false;
         if (kShared && load_u32_cg(node_counter) + P.lanes_per_tree * kTrees > P.max_nodes) return false;
-        return P.iterations > 0 || !kTree ? done < quota : global_timer_ns() < deadline;
+        if (P.iterations > 0 || !kTree) return done < quota;
+        // time mode: the availability of a node grows by one per iteration even when the tree has stopped
+        // growing (a root with one legal move), and ln() is a table: stop before its end
+        return done + 3u < P.ln_count && global_timer_ns() < deadline;
     }
 
     // Node::update + updateData of one node (node.h:74-80; ucb1.h:53-56; exp3.h:45-48).
@@ -269,13 +275,14 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             const TreePool<S> pool = tree;
             const double* const ln = P.ln_table;
             const double exploration = P.exploration;
+            const uint32_t ln_last = P.ln_count - 1u;                 // (never reached: budget_left())
             for (Mask rest = legal; rest.any();) {
                 const uint32_t move = rest.pop_lowest();
                 S c;
                 const uint32_t ci = pool.find(parent, move, c);
                 c.avail += 1;
                 pool.slots[ci].avail = c.avail;
-                const double u = ismcts_ucb_value(c.score2, c.visits, ln[c.avail], exploration);
+                const double u = ismcts_ucb_value(c.score2, c.visits, ln[c.avail < ln_last ? c.avail : ln_last], exploration);
                 if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
             }
             return best;
@@ -543,7 +550,7 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
             const uint64_t of_tree = tree_iterations(P.iterations, P.trees_total, tree_global);
             lane.quota = (uint32_t)(of_tree / width + (lane_in_tree < of_tree % width ? 1u : 0u));
         } else {
-            lane.deadline = global_timer_ns() + P.time_ns;    // time mode, utility.h:51-60
+            lane.deadline = (P.start_ns ? load_u64_cg(P.start_ns) : global_timer_ns()) + P.time_ns;    // time mode, utility.h:51-60
         }
         if (kShared) {
             lane.first_iteration = lane_in_tree; lane.iteration_stride = width;

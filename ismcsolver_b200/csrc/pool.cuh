@@ -129,8 +129,12 @@ struct TreePool {
     // Shared tree (tree parallelisation): the child of `parent` for `move`, created if no lane has
     // created it yet (Node::addChild under the node mutex, node.h:44-48,121-126, without the
     // mutex).  A slot is reserved by a compare-and-swap on its key; the winner fills in the
-    // fields nobody else writes.  `counter` numbers the nodes of the tree in creation order.
-    // The caller publishes the child in the parent's child_mask afterwards.
+    // fields nobody else writes and then PUBLISHES the node by storing its creation index (never 0 for a
+    // child: the counter starts at the number of roots) behind a fence; a lane that finds the key
+    // reserved waits for that index, so nobody reads the player, the availability or the probability of
+    // a node that is still being filled in.  The availability starts as an atomic increment of the
+    // zeroed field: increments of other lanes commute with it.  `counter` numbers the nodes of the
+    // tree in creation order.  The caller publishes the child in the parent's child_mask afterwards.
     ISMCTS_DEV uint32_t find_or_insert_shared(uint32_t parent, uint32_t move, uint32_t player, uint32_t* counter)
     {
         const uint32_t key = slot_make_key(parent, move);
@@ -139,13 +143,18 @@ struct TreePool {
             if (i >= roots) {
                 const uint32_t old = atomic_cas_u32(&slots[i].key, 0u, key);
                 if (old == 0u) {
-                    if constexpr (!Slot::kExp3) slots[i].avail = 1;   // ucb1.h:51
-                    else slots[i].prob = 1.0;                          // exp3.h:42
+                    if constexpr (!Slot::kExp3) atomic_add_u32(&slots[i].avail, 1u);   // ucb1.h:51
+                    else slots[i].prob = 1.0;                                          // exp3.h:42
                     slots[i].player = player;
-                    slots[i].created = atomic_add_u32(counter, 1u);
+                    const uint32_t index = atomic_add_u32(counter, 1u);
+                    fence_device();
+                    store_u32_release(&slots[i].created, index);
                     return i;
                 }
-                if (old == key) return i;                     // another lane was first
+                if (old == key) {                             // another lane was first
+                    while (load_u32_acquire(&slots[i].created) == 0u) {}
+                    return i;
+                }
             }
             i = (i + 1u) & mask;
         }
