@@ -35,10 +35,6 @@ ITERATIONS_PER_DECISION = 1_000_000
 DEAL_SEED = 0x1535C75B200           # printed with every line (config.deal_seed)
 # algorithmic node traffic of one KW4 iteration (select 1.28 KB + expand 232 B + backprop 80 B)
 ALGO_BYTES_PER_ITERATION = 1600.0
-# ncu (profiles/r01_final9_ncu_raw.txt): warp-instructions executed and DRAM bytes per iteration of the search kernel
-NCU_PROFILE = "profiles/r01_final9_ncu_raw.txt"
-NCU_WARP_INST_PER_ITERATION = 37755352886.0 / 64e6
-NCU_DRAM_BYTES_PER_ITERATION = (80.701630e9 + 29.203759e9) / 64e6
 REF_HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
 
 
@@ -52,6 +48,9 @@ def parse_args():
     ap.add_argument("--trees", type=int, default=2368, help="trees per position per GPU")
     ap.add_argument("--iterations", type=int, default=ITERATIONS_PER_DECISION, help="iterations per decision per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (position stream, MO+EXP3, ...)")
+    ap.add_argument("--mo-trees", type=int, default=4736, help="extra leg MO+EXP3: lanes (sets of trees) per position")
+    ap.add_argument("--single-trees", type=int, default=3906, help="extra leg single decision: trees (CudaRootParallel's own choice for 1M)")
     return ap.parse_args()
 
 
@@ -154,6 +153,41 @@ def reference_arm(args):
 
 # ----------------------------------------------------------------------------- B200 arm
 
+def position_stream(capi, n: int, seed: int = DEAL_SEED):
+    """SURVEY.md 8(d) position stream: deal i advanced by d ~ U{0..60} uniformly random legal moves, drawn again
+    if the game has ended by then."""
+    import numpy as np
+    rng = np.random.default_rng(seed & 0xFFFFFFFF)
+    out = []
+    i = 0
+    while len(out) < n:
+        s = capi.kw_deal(seed, 1_000_000 + i, 4)
+        ctr = [0]
+        for _ in range(int(rng.integers(0, 61))):
+            mask = capi.kw_legal_mask(s)
+            if not mask:
+                break
+            legal = [c for c in range(52) if mask >> c & 1]
+            capi.kw_apply(s, int(rng.choice(legal)), seed, 1_000_000 + i, ctr)
+        i += 1
+        if capi.kw_legal_mask(s):
+            out.append(s)
+    return out
+
+
+def ncu_figures():
+    """Per-iteration counters of the newest ncu capture (profiles/ncu_latest.json, written by
+    profiles/ncu_summary.py) — only if it profiled the code this library is built from."""
+    from ismcsolver_b200.build import source_hash
+    try:
+        latest = json.load(open(os.path.join(ROOT, "profiles", "ncu_latest.json")))
+    except Exception:
+        return None, "no profiles/ncu_latest.json"
+    if latest.get("source_hash") != source_hash():
+        return None, f"profiles/{latest.get('report')} profiled other sources ({latest.get('source_hash')}) than this library"
+    return latest, f"profiles/{latest.get('report')}"
+
+
 def b200_arm(args):
     import numpy as np
     import torch
@@ -177,29 +211,7 @@ def b200_arm(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     eng.set_stream(stream.cuda_stream)
-
-    B, T = args.positions, args.trees
     stride = 64
-    states = [capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)]
-    h_roots = torch.from_numpy(capi.pack_states(states)).pin_memory()
-    d_roots = h_roots.cuda(non_blocking=True)
-    d_out = torch.zeros(3 * B * stride, dtype=torch.int64, device="cuda")     # visits | score2 | avail
-    d_iters = torch.zeros(B * T, dtype=torch.int64, device="cuda")
-    per = B * stride
-
-    tree_base, my_trees = shard_trees(T * world, world, rank)
-    assert my_trees == T
-
-    def desc_for(step):
-        # trees are sharded over ranks: rank r owns global trees [r*T, (r+1)*T) of world*T;
-        # iterations per position scale with the world size (weak scaling)
-        return eng.make_desc(capi.GAME_KW, B, T, iterations=args.iterations * world, seed=0xB200 + step,
-                             trees_total=T * world, tree_base=tree_base, flags=capi.FLAG_KW_MAX4)
-
-    def device_step(step):
-        eng.search_device(desc_for(step), d_roots.data_ptr(), d_out.data_ptr(), d_out.data_ptr() + 8 * per,
-                          d_out.data_ptr() + 16 * per, d_iters.data_ptr())
-        merge_root_arrays(d_out)
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,60 +219,136 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    class Leg:
+        """One workload: `states` searched with `trees_total` trees per position sharing `iterations` iterations,
+        the trees sharded over the ranks, root arrays merged by one all-reduce per step."""
+
+        def __init__(self, states, trees_total, iterations, solver=capi.SOLVER_SO, policy=capi.POLICY_UCB1):
+            self.B = len(states)
+            self.trees_total, self.iterations = trees_total, iterations
+            self.tree_base, self.trees = shard_trees(trees_total, world, rank)
+            self.solver, self.policy = solver, policy
+            self.h_roots = torch.from_numpy(capi.pack_states(states)).pin_memory()
+            self.d_roots = self.h_roots.cuda(non_blocking=True)
+            self.per = self.B * stride
+            self.d_out = torch.zeros(3 * self.per, dtype=torch.int64, device="cuda")     # visits | score2 | avail
+            self.d_iters = torch.zeros(self.B * self.trees, dtype=torch.int64, device="cuda")
+            # the iterations this rank's trees run (execution.h:42-52: an even split, the first trees one more)
+            q, r = divmod(iterations, trees_total)
+            self.my_iterations = self.B * (q * self.trees + max(0, min(r, self.tree_base + self.trees) - min(r, self.tree_base)))
+
+        def desc(self, step):
+            return eng.make_desc(capi.GAME_KW, self.B, self.trees, iterations=self.iterations, seed=0xB200 + step,
+                                 solver=self.solver, policy=self.policy, trees_total=self.trees_total,
+                                 tree_base=self.tree_base, flags=capi.FLAG_KW_MAX4)
+
+        def launch(self, step):
+            p = self.d_out.data_ptr()
+            eng.search_device(self.desc(step), self.d_roots.data_ptr(), p, p + 8 * self.per, p + 16 * self.per,
+                              self.d_iters.data_ptr())
+
+        def device_timed(self, steps, warmup, first_step=0):
+            """(max-over-ranks ms for `steps` steps incl. the all-reduces, mean ms of this rank's search launches)"""
+            eng.set_stream(stream.cuda_stream)
+            for w in range(warmup):
+                self.launch(first_step + w)
+                merge_root_arrays(self.d_out)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            marks = []
+            ev0.record(stream)
+            for s in range(steps):
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record(stream)
+                self.launch(first_step + warmup + s)
+                k1.record(stream)
+                merge_root_arrays(self.d_out)
+                marks.append((k0, k1))
+            ev1.record(stream)
+            barrier()
+            done = int(self.d_iters.sum().item())
+            # every iteration asked for was run (ADVICE r1: `value` counts nominal iterations)
+            assert done == self.my_iterations, f"rank {rank}: {done} iterations done, {self.my_iterations} expected"
+            return max_over_ranks(ev0.elapsed_time(ev1)), sum(a.elapsed_time(b) for a, b in marks) / len(marks)
+
+        def e2e_timed(self, steps, warmup, first_step=0):
+            """Seconds (max over ranks) for `steps` host-buffer calls: H2D of the positions, search, D2H of the root
+            arrays, and at N > 1 the all-reduce of visits, scores and availabilities."""
+            eng.set_stream(None)
+            roots_np = self.h_roots.numpy()
+            for w in range(warmup):
+                eng.search(self.desc(first_step + w), roots_np)
+            barrier()
+            t0 = time.perf_counter()
+            for s in range(steps):
+                res = eng.search(self.desc(first_step + warmup + s), roots_np)
+                assert int(res["iterations_done"].sum()) == self.my_iterations
+                if world > 1:
+                    merged = torch.from_numpy(np.stack([res["visits"], res["score2"], res["avail"]]).astype(np.int64)).cuda()
+                    dist.all_reduce(merged)
+                    merged.cpu()
+            barrier()
+            return max_over_ranks(time.perf_counter() - t0)
+
+    B, T = args.positions, args.trees
+    iterations = args.iterations * world                      # weak scaling: every GPU adds its own 1M per decision
+    main = Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T * world, iterations)
+    assert main.trees == T
+
     # -------- device-resident timing
-    for w in range(args.warmup):
-        device_step(w)
-    barrier()
-    launches0 = eng.launch_count
     sampler = ClockSampler(local_rank)
+    for w in range(args.warmup):
+        main.launch(w)
+        merge_root_arrays(main.d_out)
+    barrier()
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    ev0.record(stream)
-    for s in range(args.steps):
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record(stream)
-        eng.search_device(desc_for(args.warmup + s), d_roots.data_ptr(), d_out.data_ptr(), d_out.data_ptr() + 8 * per,
-                          d_out.data_ptr() + 16 * per, d_iters.data_ptr())
-        k1.record(stream)
-        merge_root_arrays(d_out)
-        kernel_ms.append((k0, k1))
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    launches0 = eng.launch_count
+    elapsed_ms, search_ms = main.device_timed(args.steps, 0, first_step=args.warmup)
     launches = eng.launch_count - launches0
-    elapsed_ms = ev0.elapsed_time(ev1)
-    search_ms = sum(a.elapsed_time(b) for a, b in kernel_ms) / len(kernel_ms)
-    iters_done = int(d_iters.sum().item())
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    total_iterations = args.iterations * world * B * args.steps          # over all ranks
+    clocks = sampler.stop() if rank == 0 else None
+    total_iterations = iterations * B * args.steps            # over all ranks
     value = total_iterations / (elapsed_ms * 1e-3)
 
     # -------- end to end through the host-buffer C ABI call
-    eng.set_stream(None)
-    roots_np = h_roots.numpy()
-    for w in range(min(2, args.warmup)):
-        eng.search(desc_for(w), roots_np)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        res = eng.search(desc_for(args.warmup + s), roots_np)
-        if world > 1:
-            merged = torch.from_numpy(res["visits"].astype(np.int64)).cuda()
-            dist.all_reduce(merged)
-            merged.cpu()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_iterations / float(t.item())
-    h2d = h_roots.numel()
-    d2h = 3 * per * 8 + B * T * 8
+    e2e_s = main.e2e_timed(args.steps, min(2, args.warmup))
+    e2e_value = total_iterations / e2e_s
+    h2d = main.h_roots.numel()
+    d2h = 3 * main.per * 8 + B * T * 8
+
+    # -------- the other workloads north_star names, a few hundred ms each
+    extra = {}
+    if not args.no_extra:
+        def leg_line(leg, steps=2, warmup=1, **more):
+            ms, _ = leg.device_timed(steps, warmup, first_step=100)
+            return {"value": leg.iterations * leg.B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                    "positions_per_step": leg.B, "trees_per_position": leg.trees_total,
+                    "iterations_per_decision": leg.iterations, **more}
+        pos_states = position_stream(capi, B)
+        extra["position_stream"] = leg_line(
+            Leg(pos_states, T * world, iterations),
+            workload="KW4 mid-game roots: deal i + d ~ U{0..60} random plies (SURVEY 8d), SO-ISMCTS root-parallel",
+            mean_players_alive=float(np.mean([bin(s.alive_mask).count("1") for s in pos_states])))
+        extra["mo_exp3"] = leg_line(
+            Leg(main_states(capi, 16), args.mo_trees * world, iterations,
+                solver=capi.SOLVER_MO, policy=capi.POLICY_EXP3),
+            workload="KW4 MOSolver<Card, RootParallel, EXP3> (BASELINE config 4): one tree per player, trees sharded over the ranks")
+        if T % world == 0:
+            extra["strong_scaling"] = leg_line(
+                Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T, args.iterations),
+                workload=f"the N=1 job (1M iterations per decision over {T} trees) split over {world} GPU(s)")
+        # one decision at a time through the host-buffer call, as SOSolver<Card, CudaRootParallel>{1M}(game) issues it
+        single = Leg([capi.kw_deal(DEAL_SEED, 0, 4)], args.single_trees * world, iterations)
+        s_sec = single.e2e_timed(5, 2, first_step=200)
+        extra["single_decision"] = {"value": iterations * 5 / s_sec, "unit": UNIT, "ms_per_decision": 1e3 * s_sec / 5,
+                                    "trees": single.trees_total, "iterations_per_decision": iterations,
+                                    "workload": "ONE position per call, host buffers (ismcts_search), wall clock"}
 
     if rank == 0:
         peaks = {}
@@ -269,48 +357,52 @@ def b200_arm(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        per_launch_iters = args.iterations * world * B / world            # this rank's launch
+        per_launch_iters = main.my_iterations                            # this rank's launch
         achieved = per_launch_iters * ALGO_BYTES_PER_ITERATION / (search_ms * 1e-3) / 1e9
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        ncu, ncu_source = ncu_figures()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {
                 "workload": "Knockout Whist 4 players, SOSolver RootParallel (CudaRootParallel), "
-                            "1M iterations per decision",
-                "iterations_per_decision": args.iterations * world, "positions_per_step": B,
-                "trees_per_position": T * world, "iterations_per_tree": args.iterations / T,
+                            + (f"1M iterations per decision per GPU = {iterations} per decision on {world} GPUs (weak scaling)"
+                               if world > 1 else "1M iterations per decision"),
+                "iterations_per_decision": iterations, "positions_per_step": B,
+                "trees_per_position": T * world, "iterations_per_tree": iterations / (T * world),
                 "wave_width": 1, "deal_seed": hex(DEAL_SEED), "exploration": 0.7,
                 "parallelism": f"root-parallel trees sharded over {world} GPU(s), NCCL all-reduce of root arrays"
                                if world > 1 else "root-parallel, one tree per thread",
-                "l2": "node pools (>4 GB per step) are far larger than the 126 MB L2; pools are re-zeroed every step",
+                "grid": "persistent: warps claim 32 trees at a time and reuse their node tables"
+                        if B * T > 148 * 8 * 128 else "one tree per lane, one wave",
+                "l2": "the node tables in use (about 5 GB) are far larger than the 126 MB L2; every tree starts from a zeroed table",
             },
             "search_kernel_ms": search_ms,
-            "iterations_done_last_step": iters_done,
+            "iterations_done_per_step": per_launch_iters,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": NCU_DRAM_BYTES_PER_ITERATION * per_launch_iters,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this kernel and workload "
-                                  f"({NCU_PROFILE}), bytes per launch",
+                "traffic": ncu["dram_bytes_per_iteration"] * per_launch_iters if ncu else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per iteration of the search kernel x "
+                                  f"the iterations of this launch ({ncu_source})" if ncu else ncu_source,
                 "algorithmic_bytes_per_launch": per_launch_iters * ALGO_BYTES_PER_ITERATION,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "note": "the path is bound by SM instruction issue, not HBM (see DESIGN.md); "
                         "issue-slot utilisation is in profiles/",
             },
-            "issue_roofline": {
-                "bound": "sm_issue", "unit": "warp-instructions/s",
-                "peak": 148 * 4 * sm_max * 1e6,
-                "achieved": per_launch_iters / (search_ms * 1e-3) * NCU_WARP_INST_PER_ITERATION,
-                "frac": per_launch_iters / (search_ms * 1e-3) * NCU_WARP_INST_PER_ITERATION / (148 * 4 * sm_max * 1e6),
-                "warp_inst_per_iteration": NCU_WARP_INST_PER_ITERATION,
-                "note": "the binding roofline: 148 SMs x 4 schedulers x SM clock; instructions per iteration from ncu "
-                        f"smsp__inst_executed.sum ({NCU_PROFILE})",
-            },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clocks,
+            "extra": extra,
         }
+        if ncu:
+            rate = per_launch_iters / (search_ms * 1e-3) * ncu["warp_inst_per_iteration"]
+            line["issue_roofline"] = {
+                "bound": "sm_issue", "unit": "warp-instructions/s", "peak": 148 * 4 * sm_max * 1e6, "achieved": rate,
+                "frac": rate / (148 * 4 * sm_max * 1e6), "warp_inst_per_iteration": ncu["warp_inst_per_iteration"],
+                "note": "the binding roofline: 148 SMs x 4 schedulers x SM clock; instructions per iteration from ncu "
+                        f"smsp__inst_executed.sum ({ncu_source}), rate measured live",
+            }
         if not args.no_cpu_baseline and world == 1 and os.path.exists(REF_HARNESS):
             try:
                 ref = run_reference_sample(ITERATIONS_PER_DECISION, 6)
@@ -327,6 +419,10 @@ def b200_arm(args):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def main_states(capi, n):
+    return [capi.kw_deal(DEAL_SEED, i, 4) for i in range(n)]
 
 
 def main():

@@ -140,6 +140,8 @@ public:
 
     /// Statistics of the last search (root visit / reward / availability sums, iterations run).
     detail::RootStatistics const &lastStatistics() const { return m_last; }
+    /// ... of every position of the last batched search (operator() on a list of games).
+    std::vector<detail::RootStatistics> const &lastBatchStatistics() const { return m_lastBatch; }
 
 protected:
     /// Fewest iterations a tree gets when the number of trees is chosen automatically.  Spreading a
@@ -190,6 +192,21 @@ protected:
     detail::RootStatistics const &search(std::uint32_t game, void const *podState, std::uint32_t solver,
                                          std::uint32_t policy, double exploration)
     {
+        searchBatch(game, podState, 1, solver, policy, exploration);
+        m_last = m_lastBatch.front();
+        return m_last;
+    }
+
+    /// The same for `count` positions (consecutive records at `podStates`) in ONE engine call per device: every
+    /// position gets the whole budget (iterationCount() iterations, or iterationTime()), as if operator() had
+    /// been called on each of them in turn (sosolver.h:30-36), but the GPU works on all of them together.
+    std::vector<detail::RootStatistics> const &searchBatch(std::uint32_t game, void const *podStates, std::size_t count,
+                                                           std::uint32_t solver, std::uint32_t policy, double exploration)
+    {
+        if (count == 0) {
+            m_lastBatch.clear();
+            return m_lastBatch;
+        }
         if (m_contexts.empty())
             for (int device : m_devices)
                 m_contexts.push_back(std::make_unique<detail::Context>(device));
@@ -206,7 +223,7 @@ protected:
         {
             ismcts_search_desc desc;
             std::vector<std::uint64_t> visits, score2, avail, iters;
-            std::uint32_t best {0};
+            std::vector<std::uint32_t> best;
             int rc {ISMCTS_OK};
         };
         std::vector<Shard> shards(nDev);
@@ -218,7 +235,7 @@ protected:
             s.desc.game = game;
             s.desc.solver = solver;
             s.desc.policy = policy;
-            s.desc.n_positions = 1;
+            s.desc.n_positions = static_cast<std::uint32_t>(count);
             s.desc.trees = trees;
             s.desc.trees_total = treesTotal;
             s.desc.tree_base = base;
@@ -229,10 +246,13 @@ protected:
             s.desc.exploration = exploration;
             s.desc.dump_tree = 0xFFFFFFFFu;
             s.desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (lanesFor(m_iterCount) << ISMCTS_FLAG_LANES_SHIFT)) : 0;
-            s.visits.assign(stride, 0);
-            s.score2.assign(stride, 0);
-            s.avail.assign(stride, 0);
-            s.iters.assign(trees, 0);
+            if (m_materialised > 0 && count == 1)
+                s.desc.flags |= ISMCTS_FLAG_KEEP_TREES;   // currentTrees() reads trees back after the search
+            s.visits.assign(count * stride, 0);
+            s.score2.assign(count * stride, 0);
+            s.avail.assign(count * stride, 0);
+            s.iters.assign(count * trees, 0);
+            s.best.assign(count, 0);
             base += trees;
         }
         auto runShard = [&](std::size_t d) {
@@ -242,8 +262,8 @@ protected:
             out.score2 = s.score2.data();
             out.avail = s.avail.data();
             out.iterations_done = s.iters.data();
-            out.best_move = &s.best;
-            s.rc = ismcts_search(m_contexts[d]->get(), &s.desc, podState, &out);
+            out.best_move = s.best.data();
+            s.rc = ismcts_search(m_contexts[d]->get(), &s.desc, podStates, &out);
         };
         if (nDev == 1) {
             runShard(0);
@@ -254,28 +274,34 @@ protected:
             for (auto &w : workers)
                 w.join();
         }
-        m_last = detail::RootStatistics{};
-        m_last.visits.assign(stride, 0);
-        m_last.score2.assign(stride, 0);
-        m_last.available.assign(stride, 0);
-        for (std::size_t d = 0; d < nDev; ++d) {
+        for (std::size_t d = 0; d < nDev; ++d)
             m_contexts[d]->check(shards[d].rc);
-            for (std::uint32_t m = 0; m < stride; ++m) {
-                m_last.visits[m] += shards[d].visits[m];
-                m_last.score2[m] += shards[d].score2[m];
-                m_last.available[m] += shards[d].avail[m];
+        m_lastBatch.assign(count, detail::RootStatistics{});
+        for (std::size_t p = 0; p < count; ++p) {
+            detail::RootStatistics &r = m_lastBatch[p];
+            r.visits.assign(stride, 0);
+            r.score2.assign(stride, 0);
+            r.available.assign(stride, 0);
+            for (std::size_t d = 0; d < nDev; ++d) {
+                Shard const &s = shards[d];
+                for (std::uint32_t m = 0; m < stride; ++m) {
+                    r.visits[m] += s.visits[p * stride + m];
+                    r.score2[m] += s.score2[p * stride + m];
+                    r.available[m] += s.avail[p * stride + m];
+                }
+                r.iterationsPerTree.insert(r.iterationsPerTree.end(), s.iters.begin() + p * s.desc.trees,
+                                           s.iters.begin() + (p + 1) * s.desc.trees);
             }
-            m_last.iterationsPerTree.insert(m_last.iterationsPerTree.end(), shards[d].iters.begin(), shards[d].iters.end());
+            // bestMove: most visits, the first maximum in ascending move order (execution.h:126-135,209-216)
+            std::uint64_t bestVisits = 0;
+            for (std::uint32_t m = 0; m < stride; ++m)
+                if (r.visits[m] > bestVisits) {
+                    bestVisits = r.visits[m];
+                    r.bestMove = m;
+                }
         }
-        // bestMove: most visits, the first maximum in ascending move order (execution.h:126-135,209-216)
-        std::uint64_t bestVisits = 0;
-        for (std::uint32_t m = 0; m < stride; ++m)
-            if (m_last.visits[m] > bestVisits) {
-                bestVisits = m_last.visits[m];
-                m_last.bestMove = m;
-            }
-        m_lastTreesOnFirstDevice = shards[0].desc.trees;
-        return m_last;
+        m_lastTreesOnFirstDevice = count == 1 ? shards[0].desc.trees : 0;   // (batches keep no trees)
+        return m_lastBatch;
     }
 
     /// Reads tree `index` of the last search back from the first device (creation order);
@@ -310,6 +336,7 @@ private:
     unsigned int m_materialised {8};
     unsigned int m_lastTreesOnFirstDevice {0};
     detail::RootStatistics m_last;
+    std::vector<detail::RootStatistics> m_lastBatch;
 };
 
 /// Root parallelisation on the GPU: `numTrees` independent trees (0 = chosen from the budget),

@@ -49,6 +49,28 @@ public:
         return MoveCodec<Move>::fromId(result.bestMove);
     }
 
+    /// Batched form: every game of `rootStates` searched with the full budget, all in ONE engine call
+    /// (see SOSolver::operator()(std::vector<...>)).
+    std::vector<Move> operator()(std::vector<POMGame<Move> const *> const &rootStates)
+    {
+        std::vector<Move> moves;
+        if (rootStates.empty())
+            return moves;
+        std::uint32_t kind = 0;
+        auto const states = MOSolver::podsOf(rootStates, kind);
+        auto const policy = this->kernelPolicy(*rootStates.front());
+        for (auto const *g : rootStates)
+            if (g->currentMoveSimultaneous() != rootStates.front()->currentMoveSimultaneous())
+                throw std::invalid_argument("ISMCTS: the games of a batch must use the same tree policy");
+        m_policyKind = policy.kind;
+        auto const &results = this->searchBatch(kind, states.data(), rootStates.size(), ISMCTS_SOLVER_MO,
+                                                policy.kind, policy.exploration);
+        m_treesValid = false;
+        for (auto const &r : results)
+            moves.push_back(r.bestMove == 0xFFFFFFFFu ? Move{} : MoveCodec<Move>::fromId(r.bestMove));
+        return moves;
+    }
+
     /// The trees of the last search: for each materialised tree set, the root of every player's tree.
     TreeList currentTrees() const
     {

@@ -65,6 +65,26 @@ protected:
         return *pod;
     }
 
+    /// The position records of a list of games, one after the other (all games must be of the same kind).
+    template<class GameT>
+    static std::vector<unsigned char> podsOf(std::vector<GameT const *> const &games, std::uint32_t &kind)
+    {
+        std::vector<unsigned char> states;
+        kind = 0;
+        for (std::size_t i = 0; i < games.size(); ++i) {
+            if (!games[i])
+                throw std::invalid_argument("ISMCTS: null game in a batch");
+            PodGame const &pod = podOf(*games[i]);
+            if (i == 0)
+                kind = pod.podKind();
+            else if (pod.podKind() != kind)
+                throw std::invalid_argument("ISMCTS: the games of a batch must be of the same kind");
+            states.resize(states.size() + pod.podSize());
+            pod.exportPod(states.data() + states.size() - pod.podSize());
+        }
+        return states;
+    }
+
     /// Which bandit the kernels run and with which constant: the simultaneous-move policy when the
     /// game's moves are simultaneous, else the sequential one (selectChild / newRoot / newChild,
     /// solverbase.h:58-80).  The choice is made once per search, from the root position.

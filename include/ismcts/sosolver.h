@@ -43,6 +43,30 @@ public:
         return MoveCodec<Move>::fromId(result.bestMove);
     }
 
+    /// Batched form: searches every game of `rootStates` with the full budget each, all of them in ONE engine
+    /// call (the GPU is filled by positions x trees; a single position only reaches a few per cent of it), and
+    /// returns their moves in order.  Equivalent to calling operator() on each game in turn, sosolver.h:30-36.
+    /// The games must be of one kind and agree on currentMoveSimultaneous().
+    std::vector<Move> operator()(std::vector<Game<Move> const *> const &rootStates)
+    {
+        std::vector<Move> moves;
+        if (rootStates.empty())
+            return moves;
+        std::uint32_t kind = 0;
+        auto const states = SOSolver::podsOf(rootStates, kind);
+        auto const policy = this->kernelPolicy(*rootStates.front());
+        for (auto const *g : rootStates)
+            if (g->currentMoveSimultaneous() != rootStates.front()->currentMoveSimultaneous())
+                throw std::invalid_argument("ISMCTS: the games of a batch must use the same tree policy");
+        m_policyKind = policy.kind;
+        auto const &results = this->searchBatch(kind, states.data(), rootStates.size(), ISMCTS_SOLVER_SO,
+                                                policy.kind, policy.exploration);
+        m_treesValid = false;
+        for (auto const &r : results)
+            moves.push_back(r.bestMove == 0xFFFFFFFFu ? Move{} : MoveCodec<Move>::fromId(r.bestMove));
+        return moves;
+    }
+
     /// The trees of the last search, one root per tree (a copy; the first
     /// setMaterialisedTrees() trees are read back from the device).
     TreeList currentTrees() const

@@ -201,13 +201,19 @@ int ismcts_set_stream(ismcts_ctx* ctx, void* cuda_stream);
  * `time_ns` nanoseconds have passed on the device clock (utility.h:51-60).
  */
 /* Tree parallelisation (TreeParallel, execution.h:169-179): the `trees` trees of a position are ONE
- * shared tree searched by `lanes` iterations in flight with virtual loss; lanes in bits 8..23. */
+ * shared tree searched by `lanes` iterations in flight with virtual loss; lanes in bits 8..31 (the rest of
+ * the word: bits 3..7 must be zero). */
 #define ISMCTS_FLAG_SHARED_TREE 1u
 #define ISMCTS_FLAG_LANES_SHIFT 8
 /* Knockout Whist: the caller guarantees that no position has more than four players, which lets the
  * search keep more games per SM (ismcts_search sets it itself from the host records; callers of
  * ismcts_search_device may set it). */
 #define ISMCTS_FLAG_KW_MAX4 2u
+/* Keep every tree of the search in device memory for ismcts_dump_tree afterwards.  Without it, a count-mode
+ * search with more private trees than the GPU holds lanes lets its warps claim trees one after the other and
+ * reuse their node tables (memory then does not grow with n_positions * trees), and only the root statistics
+ * survive.  A descriptor that asks for a dump (dump_tree != 0xffffffff) implies it. */
+#define ISMCTS_FLAG_KEEP_TREES 4u
 
 typedef struct ismcts_search_desc {
     uint32_t game;          /* ISMCTS_GAME_* */
@@ -264,7 +270,9 @@ int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* desc, const void* r
 /* Device-resident entries (for callers that keep positions in HBM and overlap
  * copies themselves).  d_roots, d_visits, d_score2, d_avail, d_iters are DEVICE
  * pointers laid out as in ismcts_search_out.  Launch is asynchronous on the
- * context's stream. */
+ * context's stream.  The records at d_roots cannot be checked from the host: the caller guarantees
+ * what ismcts_search checks (player, dealer, trick entries below num_players <= 7, hands of at most
+ * seven existing cards, boards of at most 256 cells; ISMCTS_FLAG_KW_MAX4 only with num_players <= 4). */
 int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* desc, const void* d_roots,
                          uint64_t* d_visits, uint64_t* d_score2, uint64_t* d_avail,
                          uint64_t* d_iters);

@@ -38,6 +38,17 @@ def _inputs() -> list[str]:
     return files
 
 
+def source_hash() -> str:
+    """SHA-256 over the sources the library is built from (bench.py ties ncu captures to the code they profiled)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(_inputs()):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True

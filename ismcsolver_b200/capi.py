@@ -18,7 +18,7 @@ SOLVER_SO, SOLVER_MO = 0, 1
 POLICY_UCB1, POLICY_EXP3 = 0, 1
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_ILLEGAL_MOVE, ERR_CUDA, ERR_CAPACITY = range(6)
 NO_DUMP = 0xFFFFFFFF
-FLAG_SHARED_TREE, FLAG_KW_MAX4, FLAG_LANES_SHIFT = 1, 2, 8
+FLAG_SHARED_TREE, FLAG_KW_MAX4, FLAG_KEEP_TREES, FLAG_LANES_SHIFT = 1, 2, 4, 8
 
 EXPORTS = [
     "ismcts_state_size", "ismcts_move_stride",

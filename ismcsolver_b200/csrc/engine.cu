@@ -55,6 +55,15 @@ __global__ void prepare_kernel(const typename Game::Root* roots, typename Game::
 
 // kMinBlocks (resident CTAs per SM the register allocation must allow) trades registers per lane
 // for warps per scheduler.
+//
+// Private trees (root parallelisation): lane = tree while the trees of the launch fit the resident lanes
+// (P.unit_queue == nullptr: tree `gtid` is built in table `gtid` of the pool, which the host has zeroed).  With
+// more trees than that the grid is PERSISTENT: one resident wave of blocks whose warps claim 32 trees at a time
+// from an atomic counter until none are left, zeroing and reusing their 32 tables — a warp that finishes
+// early takes the next trees instead of leaving its slot idle while the slowest warps of a single wave finish (a
+// sixth of the warp slots in round 1, profiles/r02_persistent.md), and the pool no longer grows with the
+// number of positions.  Either way a lane adds the root statistics of its tree to the sums of its position as
+// soon as the tree is complete (RootParallel::compileVisitCounts, execution.h:219-231).
 template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams params)
 {
@@ -68,8 +77,34 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     __syncthreads();
     uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lanes = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
-    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, gtid < lanes, smem, kBlock, threadIdx.x, ring, kBlock, path);
+    const uint32_t units = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
+    if constexpr (kShared) {
+        lane_tree_search<Game, Slot, kKind, true>(P, gtid, gtid < units, smem, kBlock, threadIdx.x, ring, kBlock, path, gtid);
+    } else {
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t* const queue = P.unit_queue;
+        for (uint32_t pass = 0;; ++pass) {
+            uint32_t base = gtid - lane;
+            if (queue) {
+                if (lane == 0) base = atomicAdd(queue, 32u);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            } else if (pass) {
+                break;
+            }
+            if (base >= units) break;
+            if (queue) {
+                // the 32 tables of this warp are consecutive: zeroed together, 512 bytes per store instruction
+                uint4* const first = reinterpret_cast<uint4*>(reinterpret_cast<Slot*>(P.pool) + ((size_t)(gtid - lane) << P.log2cap));
+                const size_t words = ((size_t)32 * sizeof(Slot) / sizeof(uint4)) << P.log2cap;
+                for (size_t i = lane; i < words; i += 32) first[i] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+            }
+            const uint32_t unit = base + lane;
+            lane_tree_search<Game, Slot, kKind, false>(P, unit, unit < units, smem, kBlock, threadIdx.x, ring, kBlock, path, gtid);
+            if (unit < units) collect_roots<Game, Slot, kKind>(P, unit, gtid);
+            __syncwarp();
+        }
+    }
 }
 
 // Tree parallelisation: root node and node counter of every shared tree (one thread per tree).
@@ -80,12 +115,12 @@ __global__ void init_shared_roots_kernel(SearchParams P, uint32_t n_roots)
     if (i < P.n_positions * P.trees) init_shared_root<Slot>(P, i, n_roots);
 }
 
-// Root statistics of every tree -> per-position sums (one thread per tree), after the search.
+// Shared trees: root statistics of every tree -> per-position sums (one thread per tree), after the search.
 template <class Game, class Slot, uint32_t kKind>
 __global__ void collect_roots_kernel(SearchParams P)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n_positions * P.trees) collect_roots<Game, Slot, kKind>(P, i);
+    if (i < P.n_positions * P.trees) collect_roots<Game, Slot, kKind>(P, i, i);
 }
 
 template <class Game>
@@ -123,6 +158,8 @@ struct ismcts_ctx {
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
     uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
     uint64_t* start_ns = nullptr;                             // time mode: device clock at launch (prepare_kernel)
+    uint32_t* queue = nullptr;                                // persistent grid: next tree to claim
+    std::vector<std::pair<const void*, uint32_t>> resident;   // blocks of one resident wave, per search kernel
 
     int min_blocks = 8;          // resident CTAs per SM the SO/UCB1 Knockout Whist kernel is compiled for; ISMCTS_MIN_BLOCKS
 
@@ -193,7 +230,8 @@ int ismcts_create(int device, ismcts_ctx** out)
                                                       cudaGetErrorString(cudaGetLastError()));
     }
     ctx->stream = ctx->own_stream;
-    if (cudaMalloc((void**)&ctx->start_ns, sizeof(uint64_t)) != cudaSuccess) {
+    if (cudaMalloc((void**)&ctx->start_ns, sizeof(uint64_t)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->queue, sizeof(uint32_t)) != cudaSuccess) {
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
         return fail(nullptr, ISMCTS_ERR_CUDA, "cannot allocate device memory");
@@ -209,7 +247,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
-    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters); cudaFree(ctx->start_ns);
+    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters); cudaFree(ctx->start_ns); cudaFree(ctx->queue);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -278,9 +316,9 @@ static int validate(ismcts_ctx* ctx, const ismcts_search_desc* d)
     if (d->solver != ISMCTS_SOLVER_SO && d->solver != ISMCTS_SOLVER_MO) return fail(ctx, ISMCTS_ERR_INVALID, "unknown solver kind");
     if (d->policy != ISMCTS_POLICY_UCB1 && d->policy != ISMCTS_POLICY_EXP3) return fail(ctx, ISMCTS_ERR_INVALID, "unknown tree policy");
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
-        if ((d->flags & 0xFF0000FCu) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");   // lanes: bits 8..23
+        if ((d->flags & 0xF8u) != 0) return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");   // (lanes: bits 8..31)
         if ((d->flags >> ISMCTS_FLAG_LANES_SHIFT) == 0) return fail(ctx, ISMCTS_ERR_INVALID, "shared tree: lanes must be > 0");
-    } else if ((d->flags & ~ISMCTS_FLAG_KW_MAX4) != 0) {
+    } else if ((d->flags & ~(ISMCTS_FLAG_KW_MAX4 | ISMCTS_FLAG_KEEP_TREES)) != 0) {
         return fail(ctx, ISMCTS_ERR_INVALID, "unknown flags");
     }
     if (d->n_positions == 0 || d->trees == 0) return fail(ctx, ISMCTS_ERR_INVALID, "n_positions and trees must be > 0");
@@ -366,72 +404,77 @@ static int launch_prepare(ismcts_ctx* ctx, const void* d_roots, uint32_t n)
     return ISMCTS_OK;
 }
 
-template <class Game, class Slot, uint32_t kKind, bool kTuned>
-static void launch_search_variant(ismcts_ctx* ctx, const SearchParams& P, uint32_t grid)
+// The kernels of one search: what the descriptor selects.
+struct KernelSet {
+    const void* search = nullptr;       // search_kernel<...>
+    const void* collect = nullptr;      // shared trees: collect_roots_kernel<...>
+    const void* init_shared = nullptr;  // shared trees: init_shared_roots_kernel<...>
+    size_t smem = 0;                    // dynamic shared memory of a block of the search kernel
+    uint32_t roots_per_table = 1;
+};
+
+template <class Game, class Slot, uint32_t kKind, bool kShared, int kMinBlocks, class RootGame = Game>
+static KernelSet kernel_set()
 {
-    const size_t smem = block_smem<Game>();
-    if constexpr (kTuned) {
-        // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets
-        switch (ctx->min_blocks) {
-        case 4: search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        case 5: search_kernel<Game, Slot, kKind, false, 5><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        case 6: search_kernel<Game, Slot, kKind, false, 6><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        default: search_kernel<Game, Slot, kKind, false, 8><<<grid, kBlock, smem, ctx->stream>>>(P); return;
-        }
-    } else {
-        search_kernel<Game, Slot, kKind, false, 4><<<grid, kBlock, smem, ctx->stream>>>(P);
-    }
+    KernelSet k;
+    k.search = (const void*)search_kernel<Game, Slot, kKind, kShared, kMinBlocks>;
+    k.collect = (const void*)collect_roots_kernel<RootGame, Slot, kKind>;
+    k.init_shared = (const void*)init_shared_roots_kernel<Slot>;
+    k.smem = block_smem<Game>();
+    k.roots_per_table = kKind == kMO ? Game::kMaxPlayers : 1u;
+    return k;
 }
 
 template <class Game>
-static int launch_search(ismcts_ctx* ctx, SearchParams& P, const ismcts_search_desc* d, const void* d_roots, uint32_t lanes)
+static KernelSet choose_kernels(const ismcts_ctx* ctx, const ismcts_search_desc* d)
 {
     using Mask = typename Game::Mask;
-    int rc = launch_prepare<Game>(ctx, d_roots, P.n_positions);
-    if (rc) return rc;
-    P.prepared = ctx->prepared;
-    const uint32_t grid = (lanes + kBlock - 1) / kBlock;
-    const uint32_t tables = P.n_positions * P.trees, tgrid = (tables + 127) / 128;
     const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
         // tree parallelisation: the lanes of a group share the tree (SO) or the trees of all players (MO)
-        auto run = [&](auto slot_tag, auto kind_tag) {
-            using Slot = typename decltype(slot_tag)::Game;
-            constexpr uint32_t kKind = decltype(kind_tag)::value;
-            init_shared_roots_kernel<Slot><<<tgrid, 128, 0, ctx->stream>>>(P, kKind == kMO ? Game::kMaxPlayers : 1u);
-            search_kernel<Game, Slot, kKind, true, 4><<<grid, kBlock, block_smem<Game>(), ctx->stream>>>(P);
-            collect_roots_kernel<Game, Slot, kKind><<<tgrid, 128, 0, ctx->stream>>>(P);
-        };
-        using So = std::integral_constant<uint32_t, kSO>;
-        using Mo = std::integral_constant<uint32_t, kMO>;
-        if (so && ucb) run(GameTag<SlotUcb<Mask>>{}, So{});
-        else if (so) run(GameTag<SlotExp<Mask>>{}, So{});
-        else if (ucb) run(GameTag<SlotUcb<Mask>>{}, Mo{});
-        else run(GameTag<SlotExp<Mask>>{}, Mo{});
-        ctx->launches += 3;
-    } else {
-        if (so && ucb) {
-            if constexpr (Game::kGameId == ISMCTS_GAME_KW) {
-                // positions with at most four players: the same prepared roots, less scratch per lane
-                if (d->flags & ISMCTS_FLAG_KW_MAX4) launch_search_variant<KwGame4, SlotUcb<Mask>, kSO, true>(ctx, P, grid);
-                else launch_search_variant<Game, SlotUcb<Mask>, kSO, true>(ctx, P, grid);
-            } else {
-                launch_search_variant<Game, SlotUcb<Mask>, kSO, false>(ctx, P, grid);
-            }
-            collect_roots_kernel<Game, SlotUcb<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
-        } else if (so) {
-            launch_search_variant<Game, SlotExp<Mask>, kSO, false>(ctx, P, grid);
-            collect_roots_kernel<Game, SlotExp<Mask>, kSO><<<tgrid, 128, 0, ctx->stream>>>(P);
-        } else if (ucb) {
-            launch_search_variant<Game, SlotUcb<Mask>, kMO, false>(ctx, P, grid);
-            collect_roots_kernel<Game, SlotUcb<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
-        } else {
-            launch_search_variant<Game, SlotExp<Mask>, kMO, false>(ctx, P, grid);
-            collect_roots_kernel<Game, SlotExp<Mask>, kMO><<<tgrid, 128, 0, ctx->stream>>>(P);
-        }
-        ctx->launches += 2;
+        if (so && ucb) return kernel_set<Game, SlotUcb<Mask>, kSO, true, 4>();
+        if (so) return kernel_set<Game, SlotExp<Mask>, kSO, true, 4>();
+        if (ucb) return kernel_set<Game, SlotUcb<Mask>, kMO, true, 4>();
+        return kernel_set<Game, SlotExp<Mask>, kMO, true, 4>();
     }
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (so && ucb) {
+        if constexpr (Game::kGameId == ISMCTS_GAME_KW) {
+            // the headline path (Knockout Whist, SO, UCB1) exists at several register budgets, and for positions
+            // with at most four players with less scratch per lane (the same prepared roots)
+            const bool max4 = (d->flags & ISMCTS_FLAG_KW_MAX4) != 0;
+            switch (ctx->min_blocks) {
+            case 4: return max4 ? kernel_set<KwGame4, SlotUcb<Mask>, kSO, false, 4, Game>() : kernel_set<Game, SlotUcb<Mask>, kSO, false, 4>();
+            case 5: return max4 ? kernel_set<KwGame4, SlotUcb<Mask>, kSO, false, 5, Game>() : kernel_set<Game, SlotUcb<Mask>, kSO, false, 5>();
+            case 6: return max4 ? kernel_set<KwGame4, SlotUcb<Mask>, kSO, false, 6, Game>() : kernel_set<Game, SlotUcb<Mask>, kSO, false, 6>();
+            default: return max4 ? kernel_set<KwGame4, SlotUcb<Mask>, kSO, false, 8, Game>() : kernel_set<Game, SlotUcb<Mask>, kSO, false, 8>();
+            }
+        } else {
+            return kernel_set<Game, SlotUcb<Mask>, kSO, false, 4>();
+        }
+    }
+    if (so) return kernel_set<Game, SlotExp<Mask>, kSO, false, 4>();
+    if (ucb) return kernel_set<Game, SlotUcb<Mask>, kMO, false, 4>();
+    return kernel_set<Game, SlotExp<Mask>, kMO, false, 4>();
+}
+
+// Blocks of `kernel` one resident wave holds (occupancy x SMs), asked of the runtime once per kernel.
+static int resident_blocks(ismcts_ctx* ctx, const KernelSet& k, uint32_t* out)
+{
+    for (const auto& e : ctx->resident)
+        if (e.first == k.search) { *out = e.second; return ISMCTS_OK; }
+    int per_sm = 0, sms = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.search, kBlock, k.smem));
+    CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1 || sms < 1) return fail(ctx, ISMCTS_ERR_CUDA, "the search kernel does not fit an SM");
+    *out = (uint32_t)per_sm * (uint32_t)sms;
+    ctx->resident.emplace_back(k.search, *out);
+    return ISMCTS_OK;
+}
+
+static int launch(ismcts_ctx* ctx, const void* kernel, uint32_t grid, uint32_t block, size_t smem, void** args)
+{
+    CUDA_TRY(ctx, cudaLaunchKernel(kernel, dim3(grid), dim3(block), args, smem, ctx->stream));
+    ctx->launches++;
     return ISMCTS_OK;
 }
 
@@ -445,14 +488,25 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
 
     const bool shared = (d->flags & ISMCTS_FLAG_SHARED_TREE) != 0;
     const uint32_t width = shared ? d->flags >> ISMCTS_FLAG_LANES_SHIFT : 1u;
-    const uint32_t tables = d->n_positions * d->trees;           // node pools
-    if ((uint64_t)tables * width > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many lanes");
-    const uint32_t lanes = tables * width;                       // threads
+    const uint32_t trees = d->n_positions * d->trees;            // trees (MO: sets of trees) of this call
+    if ((uint64_t)trees * width > 0x7FFFFFFFull) return fail(ctx, ISMCTS_ERR_INVALID, "too many lanes");
+    const uint32_t lanes = trees * width;                        // threads with work
     const uint32_t stride = ismcts_move_stride(d->game);
     const uint32_t per_lane = trees_per_lane(d->game, d->solver);
     const size_t slot = slot_bytes(d->game, d->policy);
+    const KernelSet kernels = with_game(d->game, [&](auto tag) { return choose_kernels<typename decltype(tag)::Game>(ctx, d); });
 
-    // nodes per lane: every iteration adds at most one node to each of its trees
+    // Private trees in count mode that do not fit one resident wave: a persistent grid whose warps claim trees and
+    // reuse their tables (search_kernel).  The trees can then not be dumped afterwards; ISMCTS_FLAG_KEEP_TREES
+    // (or a dump asked for in the descriptor) keeps one table per tree instead.
+    uint32_t resident = 0;
+    rc = resident_blocks(ctx, kernels, &resident);
+    if (rc) return rc;
+    const bool keep = (d->flags & ISMCTS_FLAG_KEEP_TREES) != 0 || d->dump_tree != 0xFFFFFFFFu;
+    const bool recycle = !shared && d->iterations > 0 && !keep && lanes > resident * (uint32_t)kBlock;
+    const uint32_t tables = recycle ? resident * (uint32_t)kBlock : trees;   // node pools
+
+    // nodes per table: every iteration adds at most one node to each of its trees
     uint64_t max_it;
     uint32_t log2cap;
     if (d->iterations > 0) {
@@ -480,14 +534,15 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     rc = ensure_ln_table(ctx, (uint32_t)std::min<uint64_t>(max_it + 3, 0x7FFFFFFFull));
     if (rc) return rc;
 
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, pool_need, ctx->stream));
+    if (!recycle) CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, pool_need, ctx->stream));   // (recycled tables are zeroed by their warps)
     CUDA_TRY(ctx, cudaMemsetAsync(d_visits, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_score2, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
+    if (recycle) CUDA_TRY(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(uint32_t), ctx->stream));
     if (shared) {
-        rc = ensure(ctx, ctx->counters, ctx->counters_bytes, (size_t)tables * sizeof(uint32_t));
+        rc = ensure(ctx, ctx->counters, ctx->counters_bytes, (size_t)trees * sizeof(uint32_t));
         if (rc) return rc;
-        CUDA_TRY(ctx, cudaMemsetAsync(d_iters, 0, (size_t)tables * sizeof(uint64_t), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_iters, 0, (size_t)trees * sizeof(uint64_t), ctx->stream));
     }
 
     SearchParams P;
@@ -503,11 +558,26 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.playout_out = nullptr;
     P.lanes_per_tree = width; P.node_counters = ctx->counters;
     P.start_ns = ctx->start_ns;
+    P.unit_queue = recycle ? ctx->queue : nullptr;
 
-    ctx->last_log2cap = log2cap; ctx->last_lanes = tables; ctx->last_game = d->game;
+    ctx->last_log2cap = log2cap; ctx->last_lanes = recycle ? 0 : trees; ctx->last_game = d->game;
     ctx->last_solver = d->solver; ctx->last_policy = d->policy;
 
-    return with_game(d->game, [&](auto tag) { return launch_search<typename decltype(tag)::Game>(ctx, P, d, d_roots, lanes); });
+    rc = with_game(d->game, [&](auto tag) { return launch_prepare<typename decltype(tag)::Game>(ctx, d_roots, P.n_positions); });
+    if (rc) return rc;
+    P.prepared = ctx->prepared;
+    void* args[] = {&P};
+    const uint32_t tgrid = (trees + 127) / 128;
+    if (shared) {
+        uint32_t n_roots = kernels.roots_per_table;
+        void* init_args[] = {&P, &n_roots};
+        rc = launch(ctx, kernels.init_shared, tgrid, 128, 0, init_args);
+        if (rc) return rc;
+    }
+    rc = launch(ctx, kernels.search, recycle ? resident : (lanes + kBlock - 1) / kBlock, kBlock, kernels.smem, args);
+    if (rc) return rc;
+    if (shared) rc = launch(ctx, kernels.collect, tgrid, 128, 0, args);
+    return rc;
 }
 
 // One lane's table -> node records of the tree rooted at slot `root`, in creation order.
@@ -551,6 +621,7 @@ extern "C" int ismcts_dump_tree_of(ismcts_ctx* ctx, uint32_t dump_index, uint32_
                                    uint32_t capacity, uint32_t* count)
 {
     if (!ctx || !nodes || !count) return ISMCTS_ERR_INVALID;
+    if (ctx->last_lanes == 0) return fail(ctx, ISMCTS_ERR_INVALID, "the trees of the last search were not kept (ISMCTS_FLAG_KEEP_TREES)");
     if (dump_index >= ctx->last_lanes) return fail(ctx, ISMCTS_ERR_INVALID, "dump index out of range");
     const uint32_t n_roots = trees_per_lane(ctx->last_game, ctx->last_solver);
     if (ctx->last_solver == ISMCTS_SOLVER_SO) player = 0;

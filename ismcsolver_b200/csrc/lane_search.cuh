@@ -64,6 +64,9 @@ struct SearchParams {
     // time mode: the device clock when the search was launched (written by prepare_kernel): ONE deadline for
     // all lanes, whichever wave of blocks they run in (null: every lane starts its own clock)
     const uint64_t* start_ns;
+    // private trees, count mode, more trees than resident lanes: the warps of a persistent grid claim 32 trees at a
+    // time from this counter and reuse their tables (null: lane = tree, one pass)
+    uint32_t* unit_queue;
 };
 
 // Iterations of one tree in count mode: the reference drains one shared counter
@@ -515,15 +518,11 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     }
 };
 
-// The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees, or — tree
-// parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
-// lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
-// statistics of the root children are collected afterwards by collect_roots.
 // The body of lane_tree_search on a lane object that lives wherever the caller put it.
 template <class Game, class Slot, uint32_t kKind, bool kShared>
 ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, const SearchParams& P, uint32_t gtid, bool valid,
                                     uint64_t* scratch, uint32_t scratch_stride, uint32_t column, uint32_t* ring,
-                                    uint32_t ring_stride, uint32_t* path)
+                                    uint32_t ring_stride, uint32_t* path, uint32_t table)
 {
     using Mask = typename Game::Mask;
     using L = Lane<Game, Slot, kKind, kShared>;
@@ -540,7 +539,7 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
         const uint32_t pos = tree_index / P.trees;
         const uint32_t tree_global = P.tree_base + tree_index % P.trees;
         lane.prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
-        lane.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)tree_index << P.log2cap), P.log2cap, L::kTrees);
+        lane.tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)(kShared ? tree_index : table) << P.log2cap), P.log2cap, L::kTrees);
         if (!kShared) lane.tree.init_roots();                 // shared trees: init_shared_roots
         lane.tree_players = Game::root_players(lane.prep);
         lane.rng.init(P.seed, P.pos_base + pos, tree_global, ring, ring_stride);
@@ -567,13 +566,21 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
 // The whole search of lane `gtid` of this launch: one SO tree or one set of MO trees, or — tree
 // parallelisation — one of the `lanes_per_tree` lanes of a shared tree (`valid` = false for the
 // lanes that only pad the last warp: they take part in the warp votes and do nothing).  The
-// statistics of the root children are collected afterwards by collect_roots.
+// statistics of the root children are collected afterwards by collect_roots.  `table`: the table of the
+// pool a private tree is built in (a lane that searches several trees one after the other reuses its table).
+template <class Game, class Slot, uint32_t kKind, bool kShared>
+ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
+                                 uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path,
+                                 uint32_t table)
+{
+    Lane<Game, Slot, kKind, kShared> lane(P);
+    lane_tree_search_on<Game, Slot, kKind, kShared>(lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path, table);
+}
 template <class Game, class Slot, uint32_t kKind, bool kShared>
 ISMCTS_DEV void lane_tree_search(const SearchParams& P, uint32_t gtid, bool valid, uint64_t* scratch,
                                  uint32_t scratch_stride, uint32_t column, uint32_t* ring, uint32_t ring_stride, uint32_t* path)
 {
-    Lane<Game, Slot, kKind, kShared> lane(P);
-    lane_tree_search_on<Game, Slot, kKind, kShared>(lane, P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path);
+    lane_tree_search<Game, Slot, kKind, kShared>(P, gtid, valid, scratch, scratch_stride, column, ring, ring_stride, path, gtid);
 }
 
 // Shared trees: the root node(s) and the node counter of tree `index`, before the search starts.
@@ -588,14 +595,15 @@ ISMCTS_DEV void init_shared_root(const SearchParams& P, uint32_t index, uint32_t
 
 // Root children of tree `index` -> per-position sums (RootParallel::compileVisitCounts,
 // execution.h:219-231).  MO: the tree of the root's player to move decides (mosolver.h:42-46).
+// `table`: where tree `index` was built.
 template <class Game, class Slot, uint32_t kKind>
-ISMCTS_DEV void collect_roots(const SearchParams& P, uint32_t index)
+ISMCTS_DEV void collect_roots(const SearchParams& P, uint32_t index, uint32_t table)
 {
     using Mask = typename Game::Mask;
     const uint32_t pos = index / P.trees;
     const typename Game::Prepared* prep = reinterpret_cast<const typename Game::Prepared*>(P.prepared) + pos;
     TreePool<Slot> tree;
-    tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)index << P.log2cap), P.log2cap, kKind == kMO ? Game::kMaxPlayers : 1);
+    tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)table << P.log2cap), P.log2cap, kKind == kMO ? Game::kMaxPlayers : 1);
     const uint32_t root = kKind == kMO ? Game::root_player(prep) : 0;
     uint64_t* v = P.visits + (size_t)pos * Game::kMoveStride;
     uint64_t* s = P.score2 + (size_t)pos * Game::kMoveStride;

@@ -246,6 +246,7 @@ int usage()
         "ref_harness kw-playouts <hex kw_state> <count>\n"
         "ref_harness kw-time <players> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
         "ref_harness kw-vs-random <players> <seq|root> <iterations> <threads> <games>\n"
+        "ref_harness kw-moves <count|ms> <budget> <threads>      (hex kw_state per line on stdin -> move per line)\n"
         "ref_harness phantom-stats <hex phantom_state> <so|mo> <seq|root|tree> <iterations> <threads> <reps>\n"
         "ref_harness goof-stats <prize rank 0-12> <player 0 bid rank or -1> <so|mo> <iterations> <reps>\n"
         "ref_harness cores\n");
@@ -466,6 +467,33 @@ int main(int argc, char **argv)
             std::cout << (r ? ",\n " : "") << "{\"best\": " << best << ", \"seconds\": 0, \"root\": " << oss.str() << "}";
         }
         std::cout << "]\n";
+        return 0;
+    }
+    if (cmd == "kw-moves" && argc == 5) {
+        // The reference as a player: one position (hex record) per line on stdin, one decision per line on
+        // stdout — SOSolver<Card, RootParallel> with a budget of <budget> iterations ("count") or milliseconds
+        // ("ms") per decision on <threads> threads, stock operator() (sosolver.h:30-36).
+        std::string const mode = argv[2];
+        double const budget = std::atof(argv[3]);
+        unsigned const threads = unsigned(std::atoi(argv[4]));
+        std::string line;
+        while (std::getline(std::cin, line)) {
+            ismcts_kw_state s;
+            if (!fromHex(line, s))
+                return usage();
+            PosedWhist game{s};
+            auto const t0 = std::chrono::steady_clock::now();
+            int best = -1;
+            if (mode == "ms") {
+                SOSolver<Card, RootParallel> solver{std::chrono::duration<double>(budget * 1e-3), threads};
+                best = int(solver(game));
+            } else {
+                SOSolver<Card, RootParallel> solver{std::size_t(budget), threads};
+                best = int(solver(game));
+            }
+            double const secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            std::cout << best << " " << secs << std::endl;
+        }
         return 0;
     }
     if (cmd == "kw-vs-random" && argc == 7) {

@@ -1,10 +1,14 @@
 #!/usr/bin/env python
-"""Summarises an ncu report: headline raw metrics plus a per-region instruction profile of the SASS.
-usage: python tools_ncu_summary.py gpurun_out/prof.ncu-rep [iterations_per_launch]"""
-import csv, subprocess, sys, io
+"""Summarises an ncu report: headline raw metrics of the first kernel in it.
+usage: python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [iterations_per_launch [latest.json]]
+With a third argument the per-iteration figures bench.py quotes (warp-instructions, DRAM bytes) are written to
+that JSON file together with the hash of the sources in the tree (ismcsolver_b200.build.source_hash): run it on
+the tree the capture was taken from; bench.py quotes the figures only while the hash still matches."""
+import csv, json, os, subprocess, sys, io
 
 rep = sys.argv[1]
 iters = float(sys.argv[2]) if len(sys.argv) > 2 else None
+latest = sys.argv[3] if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -32,3 +36,19 @@ for k in want:
         print(f"{k:85s} {d[k][1]:>18s} {d[k][0]}")
 if iters and 'smsp__inst_executed.sum' in d:
     print("warp-instructions per iteration", float(d['smsp__inst_executed.sum'][1]) / iters)
+
+if iters and latest:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from ismcsolver_b200.build import source_hash
+    f = lambda k: float(d[k][1].replace(",", ""))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    dram = sum(f(k) * scale.get(d[k][0], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    json.dump({"report": os.path.basename(rep), "source_hash": source_hash(), "iterations_per_launch": iters,
+               "kernel": d.get("Kernel Name", ("", ""))[1],
+               "warp_inst_per_iteration": f("smsp__inst_executed.sum") / iters,
+               "dram_bytes_per_iteration": dram / iters,
+               "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
+               "kernel_ms": f("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(d["gpu__time_duration.sum"][0], 1.0)},
+              open(latest, "w"), indent=1)
+    print("wrote", latest)

@@ -309,6 +309,7 @@ void testHostOnly()
 int main(int argc, char **argv)
 {
     bool const hostOnly = argc > 1 && std::strcmp(argv[1], "--host") == 0;
+    //   solvertest --devices N   additionally: setDevices({0..N-1}) against one device
     testConstruction<SOSolver<Card, CudaRootParallel>>();
     testConstruction<SOSolver<Card, CudaTreeParallel>>();
     testConstruction<MOSolver<Card, CudaRootParallel>>();
@@ -376,6 +377,77 @@ int main(int argc, char **argv)
             auto const maps = mo.currentTrees();
             CHECK(maps.size() == 1 && maps.front().size() == 2);
         }
+    }
+    if (!hostOnly) {
+        // batched operator(): every game gets the full budget, one engine call (sosolver.h:30-36 per game)
+        std::vector<std::unique_ptr<KnockoutWhist>> games;
+        std::vector<Game<Card> const *> roots;
+        std::vector<POMGame<Card> const *> pomRoots;
+        for (unsigned g = 0; g < 12; ++g) {
+            games.push_back(std::make_unique<KnockoutWhist>(2 + g % 6, 100 + g));
+            for (unsigned ply = 0; ply < 3 * g && !games.back()->validMoves().empty(); ++ply)
+                games.back()->doMove(games.back()->validMoves().front());
+            roots.push_back(games.back().get());
+            pomRoots.push_back(games.back().get());
+        }
+        SOSolver<Card, CudaRootParallel> batch {20000};
+        batch.setSeed(7);
+        auto const moves = batch(roots);
+        CHECK(moves.size() == roots.size());
+        CHECK(batch.lastBatchStatistics().size() == roots.size());
+        for (std::size_t g = 0; g < roots.size(); ++g) {
+            CHECK(isValid(*roots[g], moves[g]));
+            CHECK(batch.lastBatchStatistics()[g].iterations() == 20000);
+        }
+        auto const first = batch.lastBatchStatistics().front();
+        SOSolver<Card, CudaRootParallel> single {20000};
+        single.setSeed(7);
+        CHECK(single(*roots.front()) == moves.front());
+        CHECK(single.lastStatistics().visits == first.visits);
+        CHECK(single.lastStatistics().score2 == first.score2);
+        MOSolver<Card, CudaRootParallel> moBatch {5000};
+        auto const moMoves = moBatch(pomRoots);
+        for (std::size_t g = 0; g < roots.size(); ++g)
+            CHECK(isValid(*roots[g], moMoves[g]));
+        SOSolver<Card, CudaTreeParallel> treeBatch {4000, 64};
+        auto const treeMoves = treeBatch(roots);
+        for (std::size_t g = 0; g < roots.size(); ++g)
+            CHECK(isValid(*roots[g], treeMoves[g]));
+        CHECK(batch(std::vector<Game<Card> const *>{}).empty());
+        // a budget that takes more trees than the GPU holds lanes (persistent grid) through the C++ layer
+        SOSolver<Card, CudaRootParallel> wide {400000, 20000};
+        wide.setSeed(3);
+        auto const wideMoves = wide(roots);
+        for (std::size_t g = 0; g < roots.size(); ++g) {
+            CHECK(isValid(*roots[g], wideMoves[g]));
+            CHECK(wide.lastBatchStatistics()[g].iterations() == 400000);
+        }
+    }
+    if (argc > 2 && std::strcmp(argv[1], "--devices") == 0) {
+        // setDevices: the trees of a search sharded over several GPUs, root arrays summed on the host —
+        // identical to the search on one GPU at a fixed seed (tree ids are global)
+        int const n = std::atoi(argv[2]);
+        std::vector<int> devices;
+        for (int d = 0; d < n; ++d)
+            devices.push_back(d);
+        KnockoutWhist game {4, 42};
+        SOSolver<Card, CudaRootParallel> one {100000, 64}, many {100000, 64};
+        one.setSeed(11);
+        many.setSeed(11);
+        many.setDevices(devices);
+        Card const a = one(game), b = many(game);
+        CHECK(a == b);
+        CHECK(one.lastStatistics().visits == many.lastStatistics().visits);
+        CHECK(one.lastStatistics().score2 == many.lastStatistics().score2);
+        CHECK(one.lastStatistics().available == many.lastStatistics().available);
+        CHECK(many.lastStatistics().iterations() == 100000);
+        MOSolver<Card, CudaRootParallel, EXP3> moOne {30000, 32}, moMany {30000, 32};
+        moOne.setSeed(5);
+        moMany.setSeed(5);
+        moMany.setDevices(devices);
+        CHECK(moOne(game) == moMany(game));
+        CHECK(moOne.lastStatistics().visits == moMany.lastStatistics().visits);
+        std::printf("devices: %d\n", n);
     }
     std::printf("%d checks, %d failures\n", checks, failures);
     return failures ? 1 : 0;

@@ -28,3 +28,14 @@ def test_solver_conformance_on_device(solvertest):
     out = subprocess.run([solvertest], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "0 failures" in out.stdout
+
+
+@pytest.mark.gpu
+def test_set_devices_shards_trees_over_two_gpus(solvertest):
+    """CudaExecutionPolicy::setDevices({0, 1}): merged statistics equal the one-GPU ones at a fixed seed."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    out = subprocess.run([solvertest, "--devices", "2"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "devices: 2" in out.stdout and "0 failures" in out.stdout

@@ -465,3 +465,32 @@ def test_phantom_playouts_and_trees_bit_exact(engine):
                     for f in FIELDS:
                         assert (nodes[f] == want[f]).all(), (solver, i, t, player, f)
             assert int(res["best_move"][i]) in capi.phantom_legal(s)
+
+
+def test_persistent_grid_recycles_tables(engine):
+    """More private trees than the GPU holds lanes: the warps of a persistent grid claim trees and reuse their
+    tables (engine.cu: search_kernel).  The root sums must equal the oracle's and those of the same search with
+    one table per tree (ISMCTS_FLAG_KEEP_TREES); afterwards the trees cannot be dumped."""
+    n_pos, trees = 5, 40000                       # 200,000 trees > 148 SMs x 8 blocks x 128 lanes
+    iterations = trees * 5 + 3
+    states = [_midgame(33, i, i * 6) for i in range(n_pos)]
+    roots = capi.pack_states(states)
+    recycled = engine.search(engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=404), roots)
+    with pytest.raises(capi.EngineError):
+        engine.dump_tree(0, 16)
+    kept = engine.search(engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=404,
+                                          flags=capi.FLAG_KEEP_TREES), roots)
+    assert len(engine.dump_tree(n_pos * trees - 1, 16)) >= 2
+    for k in ("visits", "score2", "avail", "iterations_done", "best_move"):
+        assert (recycled[k] == kept[k]).all(), k
+    assert int(recycled["iterations_done"].sum()) == n_pos * iterations
+    for i in (0, n_pos - 1):
+        v, sc, av, best = O.root_parallel(O.GAME_KW, _okw(states[i]), iterations, trees, seed=404, pos=i)
+        assert (recycled["visits"][i] == v).all() and (recycled["score2"][i] == sc).all()
+        assert (recycled["avail"][i] == av).all() and int(recycled["best_move"][i]) == best
+    # MO-ISMCTS + EXP3 tables (96-byte slots, seven roots) through the same path
+    mo = [engine.search(engine.make_desc(capi.GAME_KW, 2, 90000, iterations=90000 * 3, seed=11, solver=capi.SOLVER_MO,
+                                         policy=capi.POLICY_EXP3, flags=f), roots[:2 * 96])
+          for f in (0, capi.FLAG_KEEP_TREES)]
+    for k in ("visits", "score2", "avail", "iterations_done"):
+        assert (mo[0][k] == mo[1][k]).all(), k

@@ -34,7 +34,14 @@ def _position(seed, stream, players, plies):
 
 
 def _knocked_out_root(players):
-    """A mid-game root of a `players`-player deal in which at least one player has been knocked out."""
+    """A mid-game root of a `players`-player deal in which at least one player has been knocked out (two
+    players: a knock-out ends the game, so a root in a late round instead)."""
+    if players == 2:
+        for stream in range(200):
+            for plies in range(20, 56, 3):
+                s = _position(41, stream, players, plies)
+                if capi.kw_legal_mask(s) and s.tricks_left <= 4:
+                    return s
     for stream in range(200):
         for plies in range(players * 7, players * 28, 3):
             s = _position(41, stream, players, plies)
