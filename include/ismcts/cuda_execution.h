@@ -177,13 +177,17 @@ protected:
 
     bool sharedTree() const { return m_sharedTree; }
 
-    /// Tree parallel: iterations in flight on the shared tree.  Every lane in flight adds a virtual
-    /// loss, so a small budget keeps at least four iterations per lane (16 iterations -> 4 lanes).
+    /// Tree parallel: iterations in flight on the shared tree.  Every lane in flight adds a virtual loss and
+    /// searches on statistics that are `lanes` iterations old, so the lanes are capped at
+    /// iterations / minIterationsPerLane: measured on m,n,k boards from 5x5 to 13x13 and on Knockout Whist at 1M
+    /// iterations (profiles/r02_tree_parallel_quality.md), the decision equals the sequential one down to about
+    /// 120 iterations per lane, begins to drift at 30 and is lost at 7 (16 iterations -> 1 lane, 1M -> 7812).
+    static constexpr std::size_t minIterationsPerLane = 128;
     unsigned int lanesFor(std::size_t iterations) const
     {
         if (iterations == 0)
             return m_parallelism;
-        return static_cast<unsigned int>(std::max<std::size_t>(1, std::min<std::size_t>(m_parallelism, iterations / 4)));
+        return static_cast<unsigned int>(std::max<std::size_t>(1, std::min<std::size_t>(m_parallelism, iterations / minIterationsPerLane)));
     }
 
     /// Runs one search of `podState` (a position record of include/ismcts_b200.h) on the configured

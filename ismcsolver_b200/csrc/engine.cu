@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
                 // the 32 tables of this warp are consecutive: zeroed together, 512 bytes per store instruction
                 uint4* const first = reinterpret_cast<uint4*>(reinterpret_cast<Slot*>(P.pool) + ((size_t)(gtid - lane) << P.log2cap));
                 const size_t words = ((size_t)32 * sizeof(Slot) / sizeof(uint4)) << P.log2cap;
-                for (size_t i = lane; i < words; i += 32) first[i] = make_uint4(0, 0, 0, 0);
+                for (size_t i = lane; i < words; i += 32) __stcs(first + i, make_uint4(0, 0, 0, 0));   // (streaming: not kept in L2)
                 __syncwarp();
             }
             const uint32_t unit = base + lane;
@@ -531,7 +531,9 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     }
     rc = ensure(ctx, ctx->pool, ctx->pool_bytes, pool_need);
     if (rc) return rc;
-    rc = ensure_ln_table(ctx, (uint32_t)std::min<uint64_t>(max_it + 3, 0x7FFFFFFFull));
+    // (shared trees: every lane in flight counts towards the availability of a node before its iteration is complete,
+    // and max_nodes below must not stop a tree short of its budget)
+    rc = ensure_ln_table(ctx, (uint32_t)std::min<uint64_t>(max_it + 3 + (shared ? (uint64_t)width + 1 : 0), 0x7FFFFFFFull));
     if (rc) return rc;
 
     if (!recycle) CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, pool_need, ctx->stream));   // (recycled tables are zeroed by their warps)

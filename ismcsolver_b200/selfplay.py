@@ -32,6 +32,32 @@ class SeatSearch:
         return (capi.FLAG_SHARED_TREE | (self.lanes << capi.FLAG_LANES_SHIFT)) if self.lanes else 0
 
 
+class ReferenceSeat:
+    """A seat played by the UNMODIFIED reference: SOSolver<Card, RootParallel> through oracle/_ref/ref_harness
+    (`kw-moves`), one position per request.  Harness code for the strength comparisons only."""
+
+    def __init__(self, harness: str, mode: str, budget: float, threads: int, label: str = "reference"):
+        import subprocess
+        self.label, self.mode, self.budget, self.threads = label, mode, budget, threads
+        self.proc = subprocess.Popen([harness, "kw-moves", mode, str(budget), str(threads)], stdin=subprocess.PIPE,
+                                     stdout=subprocess.PIPE, text=True, bufsize=1)
+        self.seconds = 0.0
+
+    def decide(self, state) -> int:
+        self.proc.stdin.write(bytes(state).hex() + "\n")
+        self.proc.stdin.flush()
+        move, secs = self.proc.stdout.readline().split()
+        self.seconds += float(secs)
+        return int(move)
+
+    def close(self):
+        try:
+            self.proc.stdin.close()
+            self.proc.wait(timeout=10)
+        except Exception:
+            self.proc.kill()
+
+
 @dataclass
 class SelfPlayReport:
     games: int
@@ -57,7 +83,7 @@ class SelfPlayReport:
         return d
 
 
-def play_match(engine: capi.Engine, games: int, players: int, seats: dict[int, SeatSearch], seed: int = 1,
+def play_match(engine: capi.Engine, games: int, players: int, seats: dict, seed: int = 1,
                skip_forced: bool = False, first_game: int = 0, on_round=None) -> SelfPlayReport:
     """Plays `games` games (deals `first_game`.. of the deal stream of `seed`).  Seats in `seats` move by search,
     the other seats uniformly at random (benchmark.cpp:78-81).  Every round, all games whose player to move is
@@ -93,6 +119,16 @@ def play_match(engine: capi.Engine, games: int, players: int, seats: dict[int, S
                 report.forced += int(seat in seats)
         for seat, queue in waiting.items():
             cfg = seats[seat]
+            if isinstance(cfg, ReferenceSeat):
+                t0 = time.perf_counter()
+                for g in queue:
+                    move = cfg.decide(states[g])
+                    assert capi.kw_legal_mask(states[g]) >> move & 1, "the reference returned an illegal move"
+                    capi.kw_apply(states[g], move, seed, g, counters[g])
+                    report.plies += 1
+                ps = report.per_seat[seat]
+                ps["decisions"] += len(queue); ps["search_seconds"] += time.perf_counter() - t0
+                continue
             for lo in range(0, len(queue), cfg.max_batch):
                 batch = queue[lo:lo + cfg.max_batch]
                 desc = engine.make_desc(capi.GAME_KW, len(batch), cfg.trees, iterations=cfg.iterations,
