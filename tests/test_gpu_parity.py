@@ -494,3 +494,23 @@ def test_persistent_grid_recycles_tables(engine):
           for f in (0, capi.FLAG_KEEP_TREES)]
     for k in ("visits", "score2", "avail", "iterations_done"):
         assert (mo[0][k] == mo[1][k]).all(), k
+
+
+def test_tree_parallel_lanes_cap_keeps_the_decision(engine):
+    """Tree parallelisation at 1M iterations on the empty 9x9 board (k = 5): with the lanes capped at
+    iterations / 128 (cuda_execution.h: lanesFor) all of eight independent searches play the centre, as the
+    sequential search does (profiles/r02_tree_parallel_quality.md); with 151,552 lanes in flight — 6.6 iterations
+    per lane, what round 1 benchmarked — most of them do not."""
+    iterations, seeds, centre = 1_000_000, 8, 40
+    roots = capi.pack_states([capi.mnk_init(9, 9, 5)] * seeds)
+
+    def decisions(lanes):
+        res = engine.search(engine.make_desc(capi.GAME_MNK, seeds, 1, iterations=iterations, seed=20262,
+                                             flags=_shared_flags(lanes)), roots)
+        assert (res["iterations_done"].sum(axis=1) == iterations).all()
+        return [int(b) for b in res["best_move"]]
+
+    capped = decisions(iterations // 128 // 32 * 32)
+    assert capped == [centre] * seeds, capped
+    flooded = decisions(151552)
+    assert sum(b == centre for b in flooded) <= seeds // 2, flooded
