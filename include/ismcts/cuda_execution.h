@@ -31,7 +31,6 @@
 #include <random>
 #include <stdexcept>
 #include <string>
-#include <thread>
 #include <vector>
 
 namespace ISMCTS
@@ -221,90 +220,51 @@ protected:
         unsigned int treesTotal = m_parallelism && !m_sharedTree ? m_parallelism : treesFor(m_iterCount);
         if (m_iterCount > 0)
             treesTotal = static_cast<unsigned int>(std::min<std::size_t>(treesTotal, m_iterCount));
-        std::size_t const nDev = std::min<std::size_t>(m_contexts.size(), treesTotal);
 
-        struct Shard
-        {
-            ismcts_search_desc desc;
-            std::vector<std::uint64_t> visits, score2, avail, iters;
-            std::vector<std::uint32_t> best;
-            int rc {ISMCTS_OK};
-        };
-        std::vector<Shard> shards(nDev);
-        unsigned int base = 0;
-        for (std::size_t d = 0; d < nDev; ++d) {
-            unsigned int const trees = treesTotal / nDev + (d < treesTotal % nDev ? 1 : 0);
-            Shard &s = shards[d];
-            s.desc = ismcts_search_desc{};
-            s.desc.game = game;
-            s.desc.solver = solver;
-            s.desc.policy = policy;
-            s.desc.n_positions = static_cast<std::uint32_t>(count);
-            s.desc.trees = trees;
-            s.desc.trees_total = treesTotal;
-            s.desc.tree_base = base;
-            s.desc.pos_base = 0;
-            s.desc.iterations = m_iterCount;
-            s.desc.time_ns = static_cast<std::uint64_t>(m_iterTime.count() * 1e9);
-            s.desc.seed = m_seed;
-            s.desc.exploration = exploration;
-            s.desc.dump_tree = 0xFFFFFFFFu;
-            s.desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (lanesFor(m_iterCount) << ISMCTS_FLAG_LANES_SHIFT)) : 0;
-            if (m_materialised > 0 && count == 1)
-                s.desc.flags |= ISMCTS_FLAG_KEEP_TREES;   // currentTrees() reads trees back after the search
-            s.visits.assign(count * stride, 0);
-            s.score2.assign(count * stride, 0);
-            s.avail.assign(count * stride, 0);
-            s.iters.assign(count * trees, 0);
-            s.best.assign(count, 0);
-            base += trees;
-        }
-        auto runShard = [&](std::size_t d) {
-            Shard &s = shards[d];
-            ismcts_search_out out {};
-            out.visits = s.visits.data();
-            out.score2 = s.score2.data();
-            out.avail = s.avail.data();
-            out.iterations_done = s.iters.data();
-            out.best_move = s.best.data();
-            s.rc = ismcts_search(m_contexts[d]->get(), &s.desc, podStates, &out);
-        };
-        if (nDev == 1) {
-            runShard(0);
-        } else {
-            std::vector<std::thread> workers;
-            for (std::size_t d = 0; d < nDev; ++d)
-                workers.emplace_back(runShard, d);
-            for (auto &w : workers)
-                w.join();
-        }
-        for (std::size_t d = 0; d < nDev; ++d)
-            m_contexts[d]->check(shards[d].rc);
+        ismcts_search_desc desc {};
+        desc.game = game;
+        desc.solver = solver;
+        desc.policy = policy;
+        desc.n_positions = static_cast<std::uint32_t>(count);
+        desc.trees = treesTotal;
+        desc.trees_total = treesTotal;
+        desc.tree_base = 0;
+        desc.pos_base = 0;
+        desc.iterations = m_iterCount;
+        desc.time_ns = static_cast<std::uint64_t>(m_iterTime.count() * 1e9);
+        desc.seed = m_seed;
+        desc.exploration = exploration;
+        desc.dump_tree = 0xFFFFFFFFu;
+        desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (lanesFor(m_iterCount) << ISMCTS_FLAG_LANES_SHIFT)) : 0;
+        if (m_materialised > 0 && count == 1)
+            desc.flags |= ISMCTS_FLAG_KEEP_TREES;   // currentTrees() reads trees back after the search
+
+        std::vector<std::uint64_t> visits(count * stride), score2(count * stride), avail(count * stride), iters(count * treesTotal);
+        std::vector<std::uint32_t> best(count);
+        ismcts_search_out out {};
+        out.visits = visits.data();
+        out.score2 = score2.data();
+        out.avail = avail.data();
+        out.iterations_done = iters.data();
+        out.best_move = best.data();
+        // the trees are sharded over the configured devices by the library (ismcts_search_multi)
+        std::vector<ismcts_ctx *> contexts;
+        for (auto const &c : m_contexts)
+            contexts.push_back(c->get());
+        m_contexts.front()->check(ismcts_search_multi(contexts.data(), static_cast<std::uint32_t>(contexts.size()), &desc, podStates, &out));
+
         m_lastBatch.assign(count, detail::RootStatistics{});
         for (std::size_t p = 0; p < count; ++p) {
             detail::RootStatistics &r = m_lastBatch[p];
-            r.visits.assign(stride, 0);
-            r.score2.assign(stride, 0);
-            r.available.assign(stride, 0);
-            for (std::size_t d = 0; d < nDev; ++d) {
-                Shard const &s = shards[d];
-                for (std::uint32_t m = 0; m < stride; ++m) {
-                    r.visits[m] += s.visits[p * stride + m];
-                    r.score2[m] += s.score2[p * stride + m];
-                    r.available[m] += s.avail[p * stride + m];
-                }
-                r.iterationsPerTree.insert(r.iterationsPerTree.end(), s.iters.begin() + p * s.desc.trees,
-                                           s.iters.begin() + (p + 1) * s.desc.trees);
-            }
-            // bestMove: most visits, the first maximum in ascending move order (execution.h:126-135,209-216)
-            std::uint64_t bestVisits = 0;
-            for (std::uint32_t m = 0; m < stride; ++m)
-                if (r.visits[m] > bestVisits) {
-                    bestVisits = r.visits[m];
-                    r.bestMove = m;
-                }
+            r.visits.assign(visits.begin() + p * stride, visits.begin() + (p + 1) * stride);
+            r.score2.assign(score2.begin() + p * stride, score2.begin() + (p + 1) * stride);
+            r.available.assign(avail.begin() + p * stride, avail.begin() + (p + 1) * stride);
+            r.iterationsPerTree.assign(iters.begin() + p * treesTotal, iters.begin() + (p + 1) * treesTotal);
+            r.bestMove = best[p];   // most visits, the first maximum in ascending move order (execution.h:126-135,209-216)
         }
-        m_lastTreesOnFirstDevice = count == 1 ? shards[0].desc.trees : 0;   // (batches keep no trees)
+        std::size_t const nDev = std::min<std::size_t>(m_contexts.size(), treesTotal);
+        unsigned int const treesOnFirst = treesTotal / nDev + (treesTotal % nDev ? 1 : 0);
+        m_lastTreesOnFirstDevice = count == 1 ? treesOnFirst : 0;   // (batches keep no trees)
         return m_lastBatch;
     }
 

@@ -278,6 +278,14 @@ int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* desc, const 
                          uint64_t* d_iters);
 int ismcts_synchronize(ismcts_ctx* ctx);
 
+/* Several devices: the `desc->trees` trees of the request (global ids tree_base ...) are split over the `n_ctx`
+ * contexts, one CUDA device each, searched concurrently and the root arrays summed on the host —
+ * RootParallel::compileVisitCounts (execution.h:219-231) across devices.  The result is that of ismcts_search
+ * with the same descriptor on one device (tree ids are global).  `out->iterations_done` is
+ * [n_positions * desc->trees] as for one device.  Errors are reported on ctxs[0].  No tree dump. */
+int ismcts_search_multi(ismcts_ctx* const* ctxs, uint32_t n_ctx, const ismcts_search_desc* desc, const void* roots,
+                        ismcts_search_out* out);
+
 /* Reads back tree `dump_index` (= position * trees + tree of the last search)
  * as node records in creation order. */
 int ismcts_dump_tree(ismcts_ctx* ctx, uint32_t dump_index, ismcts_node_rec* nodes,

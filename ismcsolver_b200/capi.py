@@ -27,7 +27,7 @@ EXPORTS = [
     "ismcts_goof_init", "ismcts_goof_legal", "ismcts_goof_apply", "ismcts_goof_result2",
     "ismcts_phantom_init", "ismcts_phantom_legal", "ismcts_phantom_apply", "ismcts_phantom_result2",
     "ismcts_create", "ismcts_destroy", "ismcts_last_error", "ismcts_set_stream",
-    "ismcts_search", "ismcts_search_device", "ismcts_synchronize", "ismcts_dump_tree", "ismcts_dump_tree_of",
+    "ismcts_search", "ismcts_search_device", "ismcts_search_multi", "ismcts_synchronize", "ismcts_dump_tree", "ismcts_dump_tree_of",
     "ismcts_playouts", "ismcts_launch_count", "ismcts_version",
 ]
 
@@ -140,6 +140,7 @@ def load_library() -> C.CDLL:
     L.ismcts_set_stream.argtypes = [vp, vp]
     L.ismcts_search.argtypes = [vp, C.POINTER(SearchDesc), vp, C.POINTER(SearchOut)]
     L.ismcts_search_device.argtypes = [vp, C.POINTER(SearchDesc), vp, vp, vp, vp, vp]
+    L.ismcts_search_multi.argtypes = [C.POINTER(vp), u32, C.POINTER(SearchDesc), vp, C.POINTER(SearchOut)]
     L.ismcts_synchronize.argtypes = [vp]
     L.ismcts_dump_tree.argtypes = [vp, u32, vp, u32, C.POINTER(u32)]
     L.ismcts_dump_tree_of.argtypes = [vp, u32, u32, vp, u32, C.POINTER(u32)]
@@ -227,6 +228,20 @@ class Engine:
         self._check(self.lib.ismcts_search(self.ctx, C.byref(desc), roots.ctypes.data, C.byref(out)))
         if dump_capacity:
             res["nodes"] = nodes[:out.dump_count].copy()
+        return res
+
+    def search_multi(self, others: list, desc: SearchDesc, roots: np.ndarray) -> dict:
+        """ismcts_search_multi over this engine and `others` (engines on other devices)."""
+        stride = self.lib.ismcts_move_stride(desc.game)
+        n = desc.n_positions
+        res = {"visits": np.zeros((n, stride), dtype=np.uint64), "score2": np.zeros((n, stride), dtype=np.uint64),
+               "avail": np.zeros((n, stride), dtype=np.uint64), "iterations_done": np.zeros((n, desc.trees), dtype=np.uint64),
+               "best_move": np.zeros(n, dtype=np.uint32)}
+        out = SearchOut(res["visits"].ctypes.data, res["score2"].ctypes.data, res["avail"].ctypes.data,
+                        res["iterations_done"].ctypes.data, res["best_move"].ctypes.data, None, 0, 0)
+        ctxs = (C.c_void_p * (1 + len(others)))(self.ctx, *[e.ctx for e in others])
+        roots = np.ascontiguousarray(roots)
+        self._check(self.lib.ismcts_search_multi(ctxs, 1 + len(others), C.byref(desc), roots.ctypes.data, C.byref(out)))
         return res
 
     def search_device(self, desc: SearchDesc, d_roots: int, d_visits: int, d_score2: int, d_avail: int,

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -706,6 +707,78 @@ extern "C" int ismcts_search(ismcts_ctx* ctx, const ismcts_search_desc* d, const
     out->dump_count = 0;
     if (d->dump_tree != 0xFFFFFFFFu && out->dump_nodes)
         return ismcts_dump_tree(ctx, d->dump_tree, out->dump_nodes, out->dump_capacity, &out->dump_count);
+    return ISMCTS_OK;
+}
+
+// The trees of one request sharded over several devices (one context each): host threads launch the shards, the
+// root arrays are summed on the host (RootParallel::compileVisitCounts, execution.h:219-231, across devices).  Tree
+// ids stay global, so the result equals that of the same request on one device.
+extern "C" int ismcts_search_multi(ismcts_ctx* const* ctxs, uint32_t n_ctx, const ismcts_search_desc* d, const void* roots,
+                                   ismcts_search_out* out)
+{
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return ISMCTS_ERR_INVALID;
+    ismcts_ctx* first = ctxs[0];
+    int rc = validate(first, d);
+    if (rc) return rc;
+    if (!roots || !out || !out->visits) return fail(first, ISMCTS_ERR_INVALID, "null host pointer");
+    if (d->dump_tree != 0xFFFFFFFFu) return fail(first, ISMCTS_ERR_INVALID, "ismcts_search_multi does not dump trees");
+    for (uint32_t i = 0; i < n_ctx; ++i)
+        if (!ctxs[i]) return fail(first, ISMCTS_ERR_INVALID, "null context");
+    const uint32_t used = std::min<uint32_t>(n_ctx, d->trees);
+    if (used == 1) return ismcts_search(first, d, roots, out);
+    const uint32_t stride = ismcts_move_stride(d->game);
+    const size_t per_arr = (size_t)d->n_positions * stride;
+    struct Shard {
+        ismcts_search_desc desc;
+        std::vector<uint64_t> visits, score2, avail, iters;
+        int rc = ISMCTS_OK;
+    };
+    std::vector<Shard> shards(used);
+    uint32_t base = d->tree_base;
+    for (uint32_t i = 0; i < used; ++i) {
+        Shard& s = shards[i];
+        s.desc = *d;
+        s.desc.trees = d->trees / used + (i < d->trees % used ? 1u : 0u);
+        s.desc.tree_base = base;
+        base += s.desc.trees;
+        s.visits.assign(per_arr, 0); s.score2.assign(per_arr, 0); s.avail.assign(per_arr, 0);
+        s.iters.assign((size_t)d->n_positions * s.desc.trees, 0);
+    }
+    std::vector<std::thread> workers;
+    for (uint32_t i = 0; i < used; ++i)
+        workers.emplace_back([&, i] {
+            Shard& s = shards[i];
+            ismcts_search_out o;
+            std::memset(&o, 0, sizeof o);
+            o.visits = s.visits.data(); o.score2 = s.score2.data(); o.avail = s.avail.data(); o.iterations_done = s.iters.data();
+            s.rc = ismcts_search(ctxs[i], &s.desc, roots, &o);
+        });
+    for (auto& w : workers) w.join();
+    for (uint32_t i = 0; i < used; ++i)
+        if (shards[i].rc) return fail(first, shards[i].rc, "device " + std::to_string(ctxs[i]->device) + ": " + ctxs[i]->error);
+    for (size_t k = 0; k < per_arr; ++k) {
+        uint64_t v = 0, s2 = 0, a = 0;
+        for (const Shard& s : shards) { v += s.visits[k]; s2 += s.score2[k]; a += s.avail[k]; }
+        out->visits[k] = v;
+        if (out->score2) out->score2[k] = s2;
+        if (out->avail) out->avail[k] = a;
+    }
+    if (out->iterations_done)
+        for (uint32_t p = 0; p < d->n_positions; ++p) {
+            uint64_t* dst = out->iterations_done + (size_t)p * d->trees;
+            for (const Shard& s : shards) {
+                std::copy(s.iters.begin() + (size_t)p * s.desc.trees, s.iters.begin() + (size_t)(p + 1) * s.desc.trees, dst);
+                dst += s.desc.trees;
+            }
+        }
+    if (out->best_move)
+        for (uint32_t p = 0; p < d->n_positions; ++p) {
+            uint32_t best = 0xFFFFFFFFu; uint64_t best_v = 0;
+            for (uint32_t m = 0; m < stride; ++m)
+                if (out->visits[(size_t)p * stride + m] > best_v) { best_v = out->visits[(size_t)p * stride + m]; best = m; }
+            out->best_move[p] = best;
+        }
+    out->dump_count = 0;
     return ISMCTS_OK;
 }
 

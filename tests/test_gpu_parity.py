@@ -514,3 +514,32 @@ def test_tree_parallel_lanes_cap_keeps_the_decision(engine):
     assert capped == [centre] * seeds, capped
     flooded = decisions(151552)
     assert sum(b == centre for b in flooded) <= seeds // 2, flooded
+
+
+def test_search_multi_equals_one_context(engine):
+    """ismcts_search_multi shards the trees of a request over several contexts (one per device on a multi-GPU box;
+    here several contexts on the same device, which exercises the same sharding, threading and summing) and returns
+    what one context returns."""
+    import torch
+    n_pos, trees, iterations = 3, 50, 50 * 120 + 7
+    states = [_midgame(61, i, i * 8) for i in range(n_pos)]
+    roots = capi.pack_states(states)
+    desc = engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=99)
+    one = engine.search(desc, roots)
+    devices = list(range(torch.cuda.device_count()))
+    others = [capi.Engine(d) for d in (devices[1:] if len(devices) > 1 else [0, 0])]
+    try:
+        many = engine.search_multi(others, desc, roots)
+    finally:
+        for e in others:
+            e.close()
+    for k in ("visits", "score2", "avail", "iterations_done", "best_move"):
+        assert (one[k] == many[k]).all(), k
+    mo = engine.make_desc(capi.GAME_KW, n_pos, 9, iterations=9 * 300, seed=5, solver=capi.SOLVER_MO, policy=capi.POLICY_EXP3)
+    others = [capi.Engine(0)]
+    try:
+        a, b = engine.search(mo, roots), engine.search_multi(others, mo, roots)
+    finally:
+        others[0].close()
+    for k in ("visits", "score2", "avail", "iterations_done", "best_move"):
+        assert (a[k] == b[k]).all(), k
