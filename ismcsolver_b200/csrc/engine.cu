@@ -433,6 +433,16 @@ static KernelSet choose_kernels(const ismcts_ctx* ctx, const ismcts_search_desc*
     const bool so = d->solver == ISMCTS_SOLVER_SO, ucb = d->policy == ISMCTS_POLICY_UCB1;
     if (d->flags & ISMCTS_FLAG_SHARED_TREE) {
         // tree parallelisation: the lanes of a group share the tree (SO) or the trees of all players (MO)
+        if constexpr (Game::kGameId == ISMCTS_GAME_KW) {
+            // Knockout Whist, SO, UCB1 — root parallelisation with tree parallelisation inside (a block of lanes per
+            // tree) is the engine's way of running the reference's own geometry (few deep trees) at full occupancy:
+            // the same register budget and scratch layouts as the private-tree kernel
+            if (so && ucb) {
+                const bool max4 = (d->flags & ISMCTS_FLAG_KW_MAX4) != 0;
+                if (ctx->min_blocks == 4) return max4 ? kernel_set<KwGame4, SlotUcb<Mask>, kSO, true, 4, Game>() : kernel_set<Game, SlotUcb<Mask>, kSO, true, 4>();
+                return max4 ? kernel_set<KwGame4, SlotUcb<Mask>, kSO, true, 8, Game>() : kernel_set<Game, SlotUcb<Mask>, kSO, true, 8>();
+            }
+        }
         if (so && ucb) return kernel_set<Game, SlotUcb<Mask>, kSO, true, 4>();
         if (so) return kernel_set<Game, SlotExp<Mask>, kSO, true, 4>();
         if (ucb) return kernel_set<Game, SlotUcb<Mask>, kMO, true, 4>();

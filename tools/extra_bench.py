@@ -103,7 +103,7 @@ def main():
             T, W = (int(x) for x in item.split("x"))
             B = max(1, 151552 // (T * W))
             states = [capi.kw_deal(0x1535C75B200, i, 4) for i in range(B)]
-            flags = (1 | (W << 8)) if W > 1 else capi.FLAG_KW_MAX4
+            flags = ((1 | (W << 8)) if W > 1 else 0) | capi.FLAG_KW_MAX4
             desc = eng.make_desc(capi.GAME_KW, B, T, iterations=args.iterations, seed=5, flags=flags)
             ms, done, _ = device_search(eng, torch, desc, capi.pack_states(states), 64)
             print(json.dumps({"workload": "Knockout Whist 4 players, SO-ISMCTS, UCB1: trees x lanes per tree",
