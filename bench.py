@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--positions", type=int, default=64, help="root positions per step (batch)")
     ap.add_argument("--trees", type=int, default=2368, help="trees per position per GPU")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (tree parallelisation with virtual loss inside every tree); 0/1 = one lane per tree")
     ap.add_argument("--iterations", type=int, default=ITERATIONS_PER_DECISION, help="iterations per decision per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (position stream, MO+EXP3, ...)")
@@ -229,8 +230,9 @@ def b200_arm(args):
         """One workload: `states` searched with `trees_total` trees per position sharing `iterations` iterations,
         the trees sharded over the ranks, root arrays merged by one all-reduce per step."""
 
-        def __init__(self, states, trees_total, iterations, solver=capi.SOLVER_SO, policy=capi.POLICY_UCB1):
+        def __init__(self, states, trees_total, iterations, solver=capi.SOLVER_SO, policy=capi.POLICY_UCB1, lanes=0):
             self.B = len(states)
+            self.flags = capi.FLAG_KW_MAX4 | ((capi.FLAG_SHARED_TREE | (lanes << capi.FLAG_LANES_SHIFT)) if lanes > 1 else 0)
             self.trees_total, self.iterations = trees_total, iterations
             self.tree_base, self.trees = shard_trees(trees_total, world, rank)
             self.solver, self.policy = solver, policy
@@ -246,7 +248,7 @@ def b200_arm(args):
         def desc(self, step):
             return eng.make_desc(capi.GAME_KW, self.B, self.trees, iterations=self.iterations, seed=0xB200 + step,
                                  solver=self.solver, policy=self.policy, trees_total=self.trees_total,
-                                 tree_base=self.tree_base, flags=capi.FLAG_KW_MAX4)
+                                 tree_base=self.tree_base, flags=self.flags)
 
         def launch(self, step):
             p = self.d_out.data_ptr()
@@ -298,7 +300,7 @@ def b200_arm(args):
 
     B, T = args.positions, args.trees
     iterations = args.iterations * world                      # weak scaling: every GPU adds its own 1M per decision
-    main = Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T * world, iterations)
+    main = Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T * world, iterations, lanes=args.lanes)
     assert main.trees == T
 
     # -------- device-resident timing

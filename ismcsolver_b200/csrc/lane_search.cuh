@@ -336,44 +336,80 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     // descent resumes).  MO: the tree of the player to move decides, then the
     // cursor of EVERY tree moves to the child for that move, which is created where
     // it does not exist yet (findOrAddChild, node.h:50-56).
-    ISMCTS_DEV_CALL void descend()
+    //
+    // Every lane of the warp makes the call (`active`: the lane has a descent to make) and the warp goes down level
+    // by level: on each level the lanes first decide — some select, some expand, their paths through that code
+    // differ — then, together again, make their moves.  Left to itself the compiler joins the expanding and the
+    // selecting lanes only at the end of the descent and runs the move once for each group with a handful of lanes
+    // (7 of 32 measured, profiles/r02_level_sync.md); the barrier between the two halves of a level keeps them one
+    // instruction stream.  A tree is not affected: each lane still performs the sequential operations of its tree.
+    ISMCTS_DEV_CALL void descend(bool active)
     {
+        const uint32_t ahead = expansion_word_ahead(active);
         for (;;) {
-            const Mask legal = game().legal();
-            if (!legal.any()) return;                             // terminal: selectNode, solverbase.h:53-56
-            const uint32_t who = game().current_player();              // newChild, solverbase.h:74-80: before the move
-            const uint32_t a = kMulti ? who : 0;                  // the deciding tree
-            const Mask untried = legal.minus(node_children[a]);   // untriedMoves, node.h:82-91
-            const bool expand = untried.any();
-            uint32_t move = 0, chosen_slot = 0;
-            Slot chosen;
-            chosen.child_mask = Mask::none();
-            if (expand) move = untried.kth(draw_below(untried.count()));  // expand, sosolver.h:63-71
-            else chosen_slot = select_child(node[a], legal, chosen, move);
-            for (uint32_t t = 0; t < kTrees; ++t) {
-                if (kMulti && !((tree_players >> t) & 1u)) continue;
-                if (t == a && !expand) {
-                    node[t] = chosen_slot; node_children[t] = chosen.child_mask;
-                } else if (node_children[t].test(move)) {         // MO: the child exists in this tree
-                    Slot c;
-                    node[t] = tree.find(node[t], move, c);
-                    node_children[t] = c.child_mask;
+            if (!warp_any(active)) return;
+            uint32_t move = 0;
+            bool expand = false;
+            if (active) {
+                const Mask legal = game().legal();
+                if (!legal.any()) {
+                    active = false;                                   // terminal: selectNode, solverbase.h:53-56
                 } else {
-                    const Mask grown = node_children[t].with(move);
-                    tree.slots[node[t]].child_mask = grown;
-                    if (!kMulti && node[t] == 0) root_children = grown;
-                    node[t] = tree.insert(node[t], move, who, tree.count);
-                    node_children[t] = Mask::none();
+                    const uint32_t who = game().current_player();          // newChild, solverbase.h:74-80: before the move
+                    const uint32_t a = kMulti ? who : 0;                  // the deciding tree
+                    const Mask untried = legal.minus(node_children[a]);   // untriedMoves, node.h:82-91
+                    expand = untried.any();
+                    uint32_t chosen_slot = 0;
+                    Slot chosen;
+                    chosen.child_mask = Mask::none();
+                    if (expand) move = untried.kth(draw_expansion(untried.count(), ahead));  // expand, sosolver.h:63-71
+                    else chosen_slot = select_child(node[a], legal, chosen, move);
+                    for (uint32_t t = 0; t < kTrees; ++t) {
+                        if (kMulti && !((tree_players >> t) & 1u)) continue;
+                        if (t == a && !expand) {
+                            node[t] = chosen_slot; node_children[t] = chosen.child_mask;
+                        } else if (node_children[t].test(move)) {         // MO: the child exists in this tree
+                            Slot c;
+                            node[t] = tree.find(node[t], move, c);
+                            node_children[t] = c.child_mask;
+                        } else {
+                            const Mask grown = node_children[t].with(move);
+                            tree.slots[node[t]].child_mask = grown;
+                            if (!kMulti && node[t] == 0) root_children = grown;
+                            node[t] = tree.insert(node[t], move, who, tree.count);
+                            node_children[t] = Mask::none();
+                        }
+                    }
+                    // the reward is credited from the point of view of the player stored in the node (ucb1.h:53-56),
+                    // which is the mover when the node was created — in games where the same move can be made by
+                    // different players in different determinisations (phantom m,n,k) not necessarily today's mover
+                    if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : chosen.player) << 24);
                 }
             }
-            // the reward is credited from the point of view of the player stored in the node (ucb1.h:53-56),
-            // which is the mover when the node was created — in games where the same move can be made by
-            // different players in different determinisations (phantom m,n,k) not necessarily today's mover
-            if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : chosen.player) << 24);
-            game().step(move);
-            if (expand) { phase = kRollout; return; }
-            if (game().chance_pending()) return;
+            warp_sync();
+            if (active) {
+                game().step(move);
+                if (expand) { phase = kRollout; active = false; }
+                else if (game().chance_pending()) active = false;
+            }
         }
+    }
+
+    // The one draw a descent of SO-ISMCTS with UCB1 makes is the pick of its expansion.  In Knockout Whist the word it
+    // comes from is always the first of a fresh Philox block (every phase leaves the stream aligned), generated in
+    // registers: the lanes generate it here, together, before they part ways in the tree, instead of each group of
+    // expanding lanes for itself on its level.  Other games and policies draw when they get there (0 is returned
+    // and not used).
+    static constexpr bool kWordAhead = game_is_phased<Game>(0) && !kExp3 && !kMulti;
+    ISMCTS_DEV uint32_t expansion_word_ahead(bool active) const
+    {
+        if constexpr (kWordAhead) return active ? rng.peek_word_direct() : 0u;
+        else return 0u;
+    }
+    ISMCTS_DEV uint32_t draw_expansion(uint32_t n, uint32_t ahead)
+    {
+        if constexpr (kWordAhead) return rng.below_with_word(ahead, n);
+        else return draw_below(n);
     }
 
     // A visit of `slot` counted now (virtual loss): the reward follows at backpropagation.
@@ -416,39 +452,51 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     // select + expand on trees shared with other lanes (tree parallelisation): SO-ISMCTS on one tree,
     // MO-ISMCTS on the trees of all players (the children of the other players' trees are found or
     // created for every move, findOrAddChild, node.h:50-56).
-    ISMCTS_DEV_CALL void descend_shared()
+    ISMCTS_DEV_CALL void descend_shared(bool active)
     {
         if constexpr (kShared) {
+            const uint32_t ahead = expansion_word_ahead(active);
             for (;;) {
-                const Mask legal = game().legal();
-                if (!legal.any()) return;
-                const uint32_t who = game().current_player();
-                const uint32_t a = kMulti ? who : 0;                  // the deciding tree
-                const Mask kids = Mask::load_shared(&tree.slots[node[a]].child_mask); // other lanes add children
-                const Mask untried = legal.minus(kids);
-                const bool expand = untried.any();
-                uint32_t move = 0, chosen = 0, stored = who;
-                if (expand) move = untried.kth(draw_below(untried.count()));
-                else chosen = select_child_shared<Slot>(node[a], legal, move, stored);
-                for (uint32_t t = 0; t < kTrees; ++t) {
-                    if (kMulti && !((tree_players >> t) & 1u)) continue;
-                    uint32_t next;
-                    if (t == a && !expand) {
-                        next = chosen;
-                        count_visit(next);
+                if (!warp_any(active)) return;
+                uint32_t move = 0;
+                bool expand = false;
+                if (active) {
+                    const Mask legal = game().legal();
+                    if (!legal.any()) {
+                        active = false;
                     } else {
-                        next = tree.find_or_insert_shared(node[t], move, who, node_counter);
-                        // count the visit before the child becomes visible: a published child has visits >= 1
-                        count_visit(next);
-                        fence_device();
-                        Mask::set_shared(&tree.slots[node[t]].child_mask, move);
+                        const uint32_t who = game().current_player();
+                        const uint32_t a = kMulti ? who : 0;                  // the deciding tree
+                        const Mask kids = Mask::load_shared(&tree.slots[node[a]].child_mask); // other lanes add children
+                        const Mask untried = legal.minus(kids);
+                        expand = untried.any();
+                        uint32_t chosen = 0, stored = who;
+                        if (expand) move = untried.kth(draw_expansion(untried.count(), ahead));
+                        else chosen = select_child_shared<Slot>(node[a], legal, move, stored);
+                        for (uint32_t t = 0; t < kTrees; ++t) {
+                            if (kMulti && !((tree_players >> t) & 1u)) continue;
+                            uint32_t next;
+                            if (t == a && !expand) {
+                                next = chosen;
+                                count_visit(next);
+                            } else {
+                                next = tree.find_or_insert_shared(node[t], move, who, node_counter);
+                                // count the visit before the child becomes visible: a published child has visits >= 1
+                                count_visit(next);
+                                fence_device();
+                                Mask::set_shared(&tree.slots[node[t]].child_mask, move);
+                            }
+                            node[t] = next;
+                        }
+                        if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : stored) << 24);
                     }
-                    node[t] = next;
                 }
-                if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : stored) << 24);
-                game().step(move);
-                if (expand) { phase = kRollout; return; }
-                if (game().chance_pending()) return;
+                warp_sync();                                              // (see descend())
+                if (active) {
+                    game().step(move);
+                    if (expand) { phase = kRollout; active = false; }
+                    else if (game().chance_pending()) active = false;
+                }
             }
         }
     }
@@ -508,9 +556,12 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                 rng = stream;
                 plies += moves;
             }
-            if (kTree && warp_any(wants_descent())) {
-                if (wants_descent()) { if (kShared) descend_shared(); else descend(); }
-                continue;
+            if (kTree) {
+                const bool down = wants_descent();
+                if (warp_any(down)) {
+                    if (kShared) descend_shared(down); else descend(down);
+                    continue;
+                }
             }
             // every lane still at work has reached the end of its game
             if (phase != kDone) finish_iteration(gtid);

@@ -140,6 +140,28 @@ struct LaneRng {
         return (uint32_t)(p >> 32);
     }
 
+    // word_direct() without taking the word (the stream does not move): for a draw whose word is generated ahead of
+    // its use.  below_with_word(word, n) then makes the draw below_direct(n) would have made at the same position.
+    ISMCTS_DEV uint32_t peek_word_direct() const
+    {
+        uint32_t b[4];
+        block(d >> 2, b);
+        const uint32_t i = d & 3u;
+        return i == 0 ? b[0] : i == 1 ? b[1] : i == 2 ? b[2] : b[3];
+    }
+    ISMCTS_DEV uint32_t below_with_word(uint32_t word, uint32_t n)
+    {
+        if (left == 0) {
+            ++d;
+            next_block = (d + 3u) >> 2;
+            w = word; left = per_word;
+        }
+        const uint64_t p = (uint64_t)w * n;
+        w = (uint32_t)p;
+        --left;
+        return (uint32_t)(p >> 32);
+    }
+
     // On to the start of the next block (a no-op at the start of a block with nothing used).
     ISMCTS_DEV void align()
     {
