@@ -40,15 +40,30 @@ ISMCTS_DEV uint64_t global_timer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+// Atomics on the node pool and the result arrays.  All of them name the GLOBAL state space: through a generic pointer
+// the compiler adds a run-time test for shared memory and a compare-and-swap loop for that case to every 64-bit
+// atomic, and turns an atomicAdd() whose result is dropped into an ATOM rather than a fire-and-forget RED.
+ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { asm volatile("red.global.add.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 // Warp vote over all 32 lanes (every lane of a warp runs the search loop, see lane_search.cuh).
 ISMCTS_DEV bool warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 // Shared-tree (tree-parallel) primitives: slot reservation, child publication, counters.
-ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value) { return atomicCAS(p, expect, value); }
-ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
-ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { atomicOr((unsigned long long*)p, (unsigned long long)v); }
-ISMCTS_DEV void atomic_add_f64(double* p, double v) { atomicAdd(p, v); }
-ISMCTS_DEV void fence_device() { __threadfence(); }
+ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value)
+{
+    uint32_t old;
+    asm volatile("atom.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(expect), "r"(value) : "memory");
+    return old;
+}
+ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+ISMCTS_DEV void red_add_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+// Publishes: everything this thread wrote before is visible to a thread that sees the bit (release at GPU scope — a
+// MEMBAR, unlike __threadfence() no invalidation of the SM's whole L1, which every lane's local memory lives in).
+ISMCTS_DEV void atomic_or_u64_release(uint64_t* p, uint64_t v) { asm volatile("red.release.gpu.global.or.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+ISMCTS_DEV void atomic_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
 ISMCTS_DEV void store_u32_release(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p)
 {
@@ -58,6 +73,8 @@ ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p)
 }
 // Starts bringing the line at p into L2 (no register, no wait).
 ISMCTS_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// A table in global memory nobody writes during the kernel (ln): the read-only path through L1.
+ISMCTS_DEV double load_f64_readonly(const double* p) { return __ldg(p); }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return __ldcg(p); }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
 // Fire-and-forget 64-bit reduction (SASS RED.E.ADD.64): no return value, no scoreboard wait.
@@ -88,12 +105,13 @@ ISMCTS_DEV uint32_t atomic_cas_u32(uint32_t* p, uint32_t expect, uint32_t value)
     return old;
 }
 ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t old = *p; *p += v; return old; }
-ISMCTS_DEV void atomic_or_u64(uint64_t* p, uint64_t v) { *p |= v; }
+ISMCTS_DEV void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
+ISMCTS_DEV void atomic_or_u64_release(uint64_t* p, uint64_t v) { *p |= v; }
 ISMCTS_DEV void atomic_add_f64(double* p, double v) { *p = ISMCTS_DADD(*p, v); }
-ISMCTS_DEV void fence_device() {}
 ISMCTS_DEV void store_u32_release(uint32_t* p, uint32_t v) { *p = v; }
 ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p) { return *p; }
 ISMCTS_DEV void prefetch_l2(const void*) {}
+ISMCTS_DEV double load_f64_readonly(const double* p) { return *p; }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return *p; }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }

@@ -279,16 +279,43 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             const double* const ln = P.ln_table;
             const double exploration = P.exploration;
             const uint32_t ln_last = P.ln_count - 1u;                 // (never reached: budget_left())
+#if defined(ISMCTS_PIPELINED_SELECT)
+            // (experiment: the slot of the next child in flight while this one is evaluated, as in select_child_shared)
+            Mask rest = legal;
+            uint32_t move = rest.pop_lowest();
+            uint32_t i = pool.home_slot(parent, move);
+            S c = load_slot(&pool.slots[i]);
+            for (;;) {
+                const uint32_t ci = pool.resolve(parent, move, i, c);
+                c.avail += 1;
+                const double ln_avail = load_f64_readonly(ln + (c.avail < ln_last ? c.avail : ln_last));
+                const bool more = rest.any();
+                uint32_t move_next = 0, i_next = 0;
+                S c_next = c;
+                if (more) {
+                    move_next = rest.pop_lowest();
+                    i_next = pool.home_slot(parent, move_next);
+                    c_next = load_slot(&pool.slots[i_next]);
+                }
+                pool.slots[ci].avail = c.avail;
+                const double u = ismcts_ucb_value(c.score2, c.visits, ln_avail, exploration);
+                if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
+                if (!more) break;
+                move = move_next; i = i_next; c = c_next;
+            }
+            return best;
+#else
             for (Mask rest = legal; rest.any();) {
                 const uint32_t move = rest.pop_lowest();
                 S c;
                 const uint32_t ci = pool.find(parent, move, c);
                 c.avail += 1;
                 pool.slots[ci].avail = c.avail;
-                const double u = ismcts_ucb_value(c.score2, c.visits, ln[c.avail < ln_last ? c.avail : ln_last], exploration);
+                const double u = ismcts_ucb_value(c.score2, c.visits, load_f64_readonly(ln + (c.avail < ln_last ? c.avail : ln_last)), exploration);
                 if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
             }
             return best;
+#endif
         } else {
             // EXP3::operator(), exp3.h:57-95: p_i = eps_t + (1 - K eps_t) exp(eps_{t-1} s_i) / sum_j exp(eps_{t-1} s_j),
             // stored in the nodes, then one sample.  Children are taken in ascending move order.
@@ -416,7 +443,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     ISMCTS_DEV void count_visit(uint32_t slot)
     {
         if constexpr (!kExp3) red_add_u64(reinterpret_cast<uint64_t*>(&tree.slots[slot]), 1u);
-        else atomic_add_u32(&tree.slots[slot].visits, 1u);
+        else red_add_u32(&tree.slots[slot].visits, 1u);
     }
 
     // UCB1 on a node whose children other lanes update (selectChild as in select_child()).
@@ -427,16 +454,38 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             for (Mask rest = legal; rest.any();) tree.prefetch(parent, rest.pop_lowest());
             double best_u = -1.0;
             uint32_t best_created = 0xFFFFFFFFu, best = 0;
-            for (Mask rest = legal; rest.any();) {
-                const uint32_t m = rest.pop_lowest();
-                S c;
-                const uint32_t ci = tree.find(parent, m, c);
-                atomic_add_u32(&tree.slots[ci].avail, 1u);                 // markAvailable, ucb1.h:71-72
-                const uint32_t avail = c.avail + 1u < P.ln_count ? c.avail + 1u : P.ln_count - 1u;
-                const double u = ismcts_ucb_value(c.score2, c.visits, P.ln_table[avail], P.exploration);
+            const TreePool<S> pool = tree;
+            const double* const ln = P.ln_table;
+            const double exploration = P.exploration;
+            const uint32_t ln_last = P.ln_count - 1u;
+            // The children one after the other, two loads ahead of the arithmetic: while the value of a child is
+            // computed its ln() (a table of tens of thousands of entries for a deep tree: an L2 access that depends
+            // on the slot just read) and the slot of the NEXT child are in flight.  Evaluated strictly one after the
+            // other, a level cost two dependent L2 round trips per child — 57 % of this kernel's long-scoreboard
+            // stalls (profiles/r02_hybrid.md).
+            Mask rest = legal;
+            uint32_t m = rest.pop_lowest();
+            uint32_t i = pool.home_slot(parent, m);
+            S c = load_slot(&pool.slots[i]);
+            for (;;) {
+                const uint32_t ci = pool.resolve(parent, m, i, c);
+                const uint32_t avail = c.avail + 1u < ln_last ? c.avail + 1u : ln_last;
+                const double ln_avail = load_f64_readonly(ln + avail);
+                const bool more = rest.any();
+                uint32_t m_next = 0, i_next = 0;
+                S c_next = c;
+                if (more) {
+                    m_next = rest.pop_lowest();
+                    i_next = pool.home_slot(parent, m_next);
+                    c_next = load_slot(&pool.slots[i_next]);
+                }
+                red_add_u32(&pool.slots[ci].avail, 1u);                    // markAvailable, ucb1.h:71-72
+                const double u = ismcts_ucb_value(c.score2, c.visits, ln_avail, exploration);
                 if (u > best_u || (u == best_u && c.created < best_created)) {
                     best_u = u; best_created = c.created; best = ci; chosen_move = m; chosen_player = c.player;
                 }
+                if (!more) break;
+                m = m_next; i = i_next; c = c_next;
             }
             return best;
         } else {
@@ -483,8 +532,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                                 next = tree.find_or_insert_shared(node[t], move, who, node_counter);
                                 // count the visit before the child becomes visible: a published child has visits >= 1
                                 count_visit(next);
-                                fence_device();
-                                Mask::set_shared(&tree.slots[node[t]].child_mask, move);
+                                Mask::set_shared(&tree.slots[node[t]].child_mask, move);   // (a release)
                             }
                             node[t] = next;
                         }

@@ -122,6 +122,23 @@ struct TreePool {
         }
     }
 
+    // find() in two halves, for callers that keep the load of one child in flight while they work on another:
+    // home_slot() is where the search for the child starts, resolve() finishes it from the contents of that
+    // slot (loaded by the caller), looking further only if the home slot holds another node.
+    ISMCTS_DEV uint32_t home_slot(uint32_t parent, uint32_t move) const { return home(slot_make_key(parent, move)); }
+    ISMCTS_DEV uint32_t resolve(uint32_t parent, uint32_t move, uint32_t i, Slot& contents) const
+    {
+        const uint32_t key = slot_make_key(parent, move);
+        if (i >= roots && contents.key == key) return i;
+        for (;;) {
+            i = (i + 1u) & mask;
+            if (i >= roots) {
+                contents = load_slot(&slots[i]);
+                if (contents.key == key) return i;
+            }
+        }
+    }
+
     // Starts loading the home slot of the child of `parent` for `move`: a descent looks its children up
     // one after the other, and without this their DRAM latencies add up.
     ISMCTS_DEV void prefetch(uint32_t parent, uint32_t move) const { prefetch_l2(&slots[home(slot_make_key(parent, move))]); }
@@ -129,8 +146,8 @@ struct TreePool {
     // Shared tree (tree parallelisation): the child of `parent` for `move`, created if no lane has
     // created it yet (Node::addChild under the node mutex, node.h:44-48,121-126, without the
     // mutex).  A slot is reserved by a compare-and-swap on its key; the winner fills in the
-    // fields nobody else writes and then PUBLISHES the node by storing its creation index (never 0 for a
-    // child: the counter starts at the number of roots) behind a fence; a lane that finds the key
+    // fields nobody else writes and then PUBLISHES the node by a release store of its creation index (never 0
+    // for a child: the counter starts at the number of roots); a lane that finds the key
     // reserved waits for that index, so nobody reads the player, the availability or the probability of
     // a node that is still being filled in.  The availability starts as an atomic increment of the
     // zeroed field: increments of other lanes commute with it.  `counter` numbers the nodes of the
@@ -143,11 +160,10 @@ struct TreePool {
             if (i >= roots) {
                 const uint32_t old = atomic_cas_u32(&slots[i].key, 0u, key);
                 if (old == 0u) {
-                    if constexpr (!Slot::kExp3) atomic_add_u32(&slots[i].avail, 1u);   // ucb1.h:51
+                    if constexpr (!Slot::kExp3) red_add_u32(&slots[i].avail, 1u);      // ucb1.h:51
                     else slots[i].prob = 1.0;                                          // exp3.h:42
                     slots[i].player = player;
                     const uint32_t index = atomic_add_u32(counter, 1u);
-                    fence_device();
                     store_u32_release(&slots[i].created, index);
                     return i;
                 }
