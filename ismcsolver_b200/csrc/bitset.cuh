@@ -22,6 +22,7 @@ struct Mask64 {
     // (a release: what the lane wrote to the child before is visible to whoever sees the bit)
     ISMCTS_DEV static Mask64 load_shared(const Mask64* p) { return Mask64{load_u64_cg(&p->w)}; }
     ISMCTS_DEV static void set_shared(Mask64* p, uint32_t b) { atomic_or_u64_release(&p->w, (uint64_t)1 << b); }
+    ISMCTS_DEV static bool test_shared_acquire(const Mask64* p, uint32_t b) { return (load_u64_acquire(&p->w) >> b) & 1u; }
 };
 
 struct Mask256 {
@@ -67,6 +68,7 @@ struct Mask256 {
         return Mask256{{load_u64_cg(&p->w[0]), load_u64_cg(&p->w[1]), load_u64_cg(&p->w[2]), load_u64_cg(&p->w[3])}};
     }
     ISMCTS_DEV static void set_shared(Mask256* p, uint32_t b) { atomic_or_u64_release(&p->w[b >> 6], (uint64_t)1 << (b & 63u)); }
+    ISMCTS_DEV static bool test_shared_acquire(const Mask256* p, uint32_t b) { return (load_u64_acquire(&p->w[b >> 6]) >> (b & 63u)) & 1u; }
     ISMCTS_DEV Mask256 minus(const Mask256& o) const
     {
         return Mask256{{w[0] & ~o.w[0], w[1] & ~o.w[1], w[2] & ~o.w[2], w[3] & ~o.w[3]}};

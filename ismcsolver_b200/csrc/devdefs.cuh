@@ -64,11 +64,11 @@ ISMCTS_DEV void red_add_u32(uint32_t* p, uint32_t v) { asm volatile("red.global.
 // MEMBAR, unlike __threadfence() no invalidation of the SM's whole L1, which every lane's local memory lives in).
 ISMCTS_DEV void atomic_or_u64_release(uint64_t* p, uint64_t v) { asm volatile("red.release.gpu.global.or.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
 ISMCTS_DEV void atomic_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
-ISMCTS_DEV void store_u32_release(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p)
+// (the rare path of a lane that waits for another lane's publication)
+ISMCTS_DEV uint64_t load_u64_acquire(const uint64_t* p)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // Starts bringing the line at p into L2 (no register, no wait).
@@ -108,8 +108,7 @@ ISMCTS_DEV uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { const uint32_t old
 ISMCTS_DEV void red_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 ISMCTS_DEV void atomic_or_u64_release(uint64_t* p, uint64_t v) { *p |= v; }
 ISMCTS_DEV void atomic_add_f64(double* p, double v) { *p = ISMCTS_DADD(*p, v); }
-ISMCTS_DEV void store_u32_release(uint32_t* p, uint32_t v) { *p = v; }
-ISMCTS_DEV uint32_t load_u32_acquire(const uint32_t* p) { return *p; }
+ISMCTS_DEV uint64_t load_u64_acquire(const uint64_t* p) { return *p; }
 ISMCTS_DEV void prefetch_l2(const void*) {}
 ISMCTS_DEV double load_f64_readonly(const double* p) { return *p; }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }

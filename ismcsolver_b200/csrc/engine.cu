@@ -157,7 +157,6 @@ struct ismcts_ctx {
     void* prepared = nullptr;    size_t prepared_bytes = 0;
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
     uint32_t* play_out = nullptr; size_t play_bytes = 0;
-    uint32_t* counters = nullptr; size_t counters_bytes = 0; // shared trees: nodes created per tree
     uint64_t* start_ns = nullptr;                             // time mode: device clock at launch (prepare_kernel)
     uint32_t* queue = nullptr;                                // persistent grid: next tree to claim
     std::vector<std::pair<const void*, uint32_t>> resident;   // blocks of one resident wave, per search kernel
@@ -248,7 +247,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
-    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->counters); cudaFree(ctx->start_ns); cudaFree(ctx->queue);
+    cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->start_ns); cudaFree(ctx->queue);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -553,8 +552,6 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     if (recycle) CUDA_TRY(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(uint32_t), ctx->stream));
     if (shared) {
-        rc = ensure(ctx, ctx->counters, ctx->counters_bytes, (size_t)trees * sizeof(uint32_t));
-        if (rc) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(d_iters, 0, (size_t)trees * sizeof(uint64_t), ctx->stream));
     }
 
@@ -569,7 +566,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
     P.playout_out = nullptr;
-    P.lanes_per_tree = width; P.node_counters = ctx->counters;
+    P.lanes_per_tree = width;
     P.start_ns = ctx->start_ns;
     P.unit_queue = recycle ? ctx->queue : nullptr;
 

@@ -60,7 +60,6 @@ struct SearchParams {
     uint32_t* playout_out;   // playout-only launches: one packed result per thread
     // tree parallelisation: `lanes_per_tree` lanes search ONE tree together (1 = private trees)
     uint32_t lanes_per_tree;
-    uint32_t* node_counters; // [n_positions * trees] nodes created per shared tree (root included)
     // time mode: the device clock when the search was launched (written by prepare_kernel): ONE deadline for
     // all lanes, whichever wave of blocks they run in (null: every lane starts its own clock)
     const uint64_t* start_ns;
@@ -147,7 +146,8 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     uint64_t deadline;
     uint32_t first_iteration; // index of this lane's first iteration (playout kernel: the playout id)
     uint32_t iteration_stride; // shared tree: the lanes of a tree interleave their iteration ids
-    uint32_t* node_counter;   // shared tree: nodes created so far (all lanes)
+    uint32_t my_nodes;        // shared tree: nodes this lane has created; its share of the table is max_nodes / lanes
+    uint32_t created_seq;     // shared tree: nodes this lane has created in the current iteration
     uint32_t tree_players;    // MO: bit p = player p has a tree (the players of the root position)
 
     ISMCTS_DEV explicit Lane(const SearchParams& p) : P(p) {}
@@ -166,7 +166,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     {
         rng.begin_iteration(first_iteration + done * iteration_stride);
         game().start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
-        depth = 0; plies = 0;
+        depth = 0; plies = 0; created_seq = 0;
         if (kMulti) {
             for (uint32_t t = 0; t < kTrees; ++t) { node[t] = t; node_children[t] = load_slot(&tree.slots[t]).child_mask; }
         } else {
@@ -178,7 +178,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     ISMCTS_DEV bool budget_left() const
     {
         if (kTree && !kShared && tree.count + kTrees > P.max_nodes) return false;
-        if (kShared && load_u32_cg(node_counter) + P.lanes_per_tree * kTrees > P.max_nodes) return false;
+        if (kShared && (uint64_t)(my_nodes + kTrees) * P.lanes_per_tree + kTrees > P.max_nodes) return false;
         if (P.iterations > 0 || !kTree) return done < quota;
         // time mode: the availability of a node grows by one per iteration even when the tree has stopped
         // growing (a root with one legal move), and ln() is a table: stop before its end
@@ -279,32 +279,6 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             const double* const ln = P.ln_table;
             const double exploration = P.exploration;
             const uint32_t ln_last = P.ln_count - 1u;                 // (never reached: budget_left())
-#if defined(ISMCTS_PIPELINED_SELECT)
-            // (experiment: the slot of the next child in flight while this one is evaluated, as in select_child_shared)
-            Mask rest = legal;
-            uint32_t move = rest.pop_lowest();
-            uint32_t i = pool.home_slot(parent, move);
-            S c = load_slot(&pool.slots[i]);
-            for (;;) {
-                const uint32_t ci = pool.resolve(parent, move, i, c);
-                c.avail += 1;
-                const double ln_avail = load_f64_readonly(ln + (c.avail < ln_last ? c.avail : ln_last));
-                const bool more = rest.any();
-                uint32_t move_next = 0, i_next = 0;
-                S c_next = c;
-                if (more) {
-                    move_next = rest.pop_lowest();
-                    i_next = pool.home_slot(parent, move_next);
-                    c_next = load_slot(&pool.slots[i_next]);
-                }
-                pool.slots[ci].avail = c.avail;
-                const double u = ismcts_ucb_value(c.score2, c.visits, ln_avail, exploration);
-                if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
-                if (!more) break;
-                move = move_next; i = i_next; c = c_next;
-            }
-            return best;
-#else
             for (Mask rest = legal; rest.any();) {
                 const uint32_t move = rest.pop_lowest();
                 S c;
@@ -315,7 +289,6 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                 if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
             }
             return best;
-#endif
         } else {
             // EXP3::operator(), exp3.h:57-95: p_i = eps_t + (1 - K eps_t) exp(eps_{t-1} s_i) / sum_j exp(eps_{t-1} s_j),
             // stored in the nodes, then one sample.  Children are taken in ascending move order.
@@ -529,10 +502,19 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                                 next = chosen;
                                 count_visit(next);
                             } else {
-                                next = tree.find_or_insert_shared(node[t], move, who, node_counter);
+                                // Creation order within a tree = (iteration, node of that iteration): unique without a
+                                // counter the lanes would have to share (a second atomic round trip per expansion).
+                                bool won;
+                                next = tree.find_or_insert_shared(node[t], move, who, ((rng.c1 + 1u) << 8) | (created_seq & 0xFFu), won);
                                 // count the visit before the child becomes visible: a published child has visits >= 1
                                 count_visit(next);
-                                Mask::set_shared(&tree.slots[node[t]].child_mask, move);   // (a release)
+                                if (won) {
+                                    ++created_seq; ++my_nodes;
+                                    Mask::set_shared(&tree.slots[node[t]].child_mask, move);   // publishes the child (a release)
+                                } else {
+                                    // another lane is creating this child: wait until it has published it
+                                    while (!Mask::test_shared_acquire(&tree.slots[node[t]].child_mask, move)) {}
+                                }
                             }
                             node[t] = next;
                         }
@@ -628,7 +610,7 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
     lane.path = path;
     lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
-    lane.iteration_stride = 1; lane.node_counter = nullptr;
+    lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0;
     lane.root_children = Mask::none();
     uint32_t tree_index = 0;
     if (valid) {
@@ -652,7 +634,6 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
         }
         if (kShared) {
             lane.first_iteration = lane_in_tree; lane.iteration_stride = width;
-            lane.node_counter = P.node_counters + tree_index;
         }
         if (lane.budget_left()) lane.start_iteration();
     }
@@ -689,7 +670,6 @@ ISMCTS_DEV void init_shared_root(const SearchParams& P, uint32_t index, uint32_t
     TreePool<Slot> tree;
     tree.bind(reinterpret_cast<Slot*>(P.pool) + ((size_t)index << P.log2cap), P.log2cap, n_roots);
     tree.init_roots();
-    P.node_counters[index] = n_roots;
 }
 
 // Root children of tree `index` -> per-position sums (RootParallel::compileVisitCounts,
@@ -733,7 +713,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
     lane.path = nullptr;
     lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
-    lane.iteration_stride = 1; lane.node_counter = nullptr;
+    lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0;
     lane.root_children = Mask::none();
     if (valid) {
         const uint32_t pos = gtid / per_position;

@@ -145,14 +145,14 @@ struct TreePool {
 
     // Shared tree (tree parallelisation): the child of `parent` for `move`, created if no lane has
     // created it yet (Node::addChild under the node mutex, node.h:44-48,121-126, without the
-    // mutex).  A slot is reserved by a compare-and-swap on its key; the winner fills in the
-    // fields nobody else writes and then PUBLISHES the node by a release store of its creation index (never 0
-    // for a child: the counter starts at the number of roots); a lane that finds the key
-    // reserved waits for that index, so nobody reads the player, the availability or the probability of
-    // a node that is still being filled in.  The availability starts as an atomic increment of the
-    // zeroed field: increments of other lanes commute with it.  `counter` numbers the nodes of the
-    // tree in creation order.  The caller publishes the child in the parent's child_mask afterwards.
-    ISMCTS_DEV uint32_t find_or_insert_shared(uint32_t parent, uint32_t move, uint32_t player, uint32_t* counter)
+    // mutex).  A slot is reserved by a compare-and-swap on its key.  The lane that wins (`won`) fills in the
+    // fields nobody else writes; the caller counts its visit and then PUBLISHES the child with a release on the
+    // parent's child_mask, so that whoever sees the bit sees the whole node.  A lane that finds the key reserved
+    // by another (`won` = false) gets the slot too — its visit is a reduction on a field that started at zero —
+    // but must wait for that bit before it reads anything else of the node.  The availability starts as an
+    // increment of the zeroed field: increments of other lanes commute with it.  `created`: the node's place
+    // in the creation order of its tree (never 0 for a child).
+    ISMCTS_DEV uint32_t find_or_insert_shared(uint32_t parent, uint32_t move, uint32_t player, uint32_t created, bool& won)
     {
         const uint32_t key = slot_make_key(parent, move);
         uint32_t i = home(key);
@@ -163,14 +163,11 @@ struct TreePool {
                     if constexpr (!Slot::kExp3) red_add_u32(&slots[i].avail, 1u);      // ucb1.h:51
                     else slots[i].prob = 1.0;                                          // exp3.h:42
                     slots[i].player = player;
-                    const uint32_t index = atomic_add_u32(counter, 1u);
-                    store_u32_release(&slots[i].created, index);
+                    slots[i].created = created;
+                    won = true;
                     return i;
                 }
-                if (old == key) {                             // another lane was first
-                    while (load_u32_acquire(&slots[i].created) == 0u) {}
-                    return i;
-                }
+                if (old == key) { won = false; return i; }    // another lane was first
             }
             i = (i + 1u) & mask;
         }

@@ -255,7 +255,6 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     std::memset((void*)table.data(), 0, table.size() * sizeof(Slot));
     const std::vector<double> ln = ln_table(iterations + 300);
     std::vector<uint64_t> v(Game::kMoveStride), s2(Game::kMoveStride), a(Game::kMoveStride), it(1);
-    uint32_t counter = 0;
     typename Game::Prepared prepared;
     prepare_root<Game>(root, &prepared);
     SearchParams P;
@@ -264,7 +263,7 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     P.seed = seed; P.exploration = 0.7; P.pool = table.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
     P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
     P.visits = v.data(); P.score2 = s2.data(); P.avail = a.data(); P.iters_done = it.data();
-    P.lanes_per_tree = width; P.node_counters = &counter;
+    P.lanes_per_tree = width;
     init_shared_root<Slot>(P, 0, n_roots);
     WarpScratch<Game> ws(width);
     FiberWarp warp(width);
