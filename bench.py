@@ -44,9 +44,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--positions", type=int, default=64, help="root positions per step (batch)")
-    ap.add_argument("--trees", type=int, default=2368, help="trees per position per GPU")
-    ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (tree parallelisation with virtual loss inside every tree); 0/1 = one lane per tree")
+    ap.add_argument("--positions", type=int, default=0, help="root positions per step (batch); 0 = eight waves of blocks")
+    ap.add_argument("--trees", type=int, default=0,
+                    help="trees per position per GPU; 0 = the host's hardware threads, i.e. the trees the reference's "
+                         "RootParallel builds on this box (execution.h:160-167,181-189)")
+    ap.add_argument("--lanes", type=int, default=128,
+                    help="lanes per tree: every tree is searched by a block of lanes with virtual loss; 1 = one lane per tree")
+    ap.add_argument("--wide-trees", type=int, default=2368, help="extra leg `wide`: private trees per position (one lane each)")
+    ap.add_argument("--wide-positions", type=int, default=1024)
     ap.add_argument("--iterations", type=int, default=ITERATIONS_PER_DECISION, help="iterations per decision per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (position stream, MO+EXP3, ...)")
@@ -298,9 +303,12 @@ def b200_arm(args):
             barrier()
             return max_over_ranks(time.perf_counter() - t0)
 
-    B, T = args.positions, args.trees
+    T = args.trees or host_cores()
+    lanes = max(1, args.lanes)
+    resident_blocks = 148 * 8
+    B = args.positions or (max(1, 8 * resident_blocks * 128 // (T * lanes)) if lanes > 1 else 1024)
     iterations = args.iterations * world                      # weak scaling: every GPU adds its own 1M per decision
-    main = Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T * world, iterations, lanes=args.lanes)
+    main = Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T * world, iterations, lanes=lanes)
     assert main.trees == T
 
     # -------- device-resident timing
@@ -334,7 +342,7 @@ def b200_arm(args):
                     "iterations_per_decision": leg.iterations, **more}
         pos_states = position_stream(capi, B)
         extra["position_stream"] = leg_line(
-            Leg(pos_states, T * world, iterations),
+            Leg(pos_states, T * world, iterations, lanes=lanes),
             workload="KW4 mid-game roots: deal i + d ~ U{0..60} random plies (SURVEY 8d), SO-ISMCTS root-parallel",
             mean_players_alive=float(np.mean([bin(s.alive_mask).count("1") for s in pos_states])))
         extra["mo_exp3"] = leg_line(
@@ -343,8 +351,14 @@ def b200_arm(args):
             workload="KW4 MOSolver<Card, RootParallel, EXP3> (BASELINE config 4): one tree per player, trees sharded over the ranks")
         if T % world == 0:
             extra["strong_scaling"] = leg_line(
-                Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T, args.iterations),
+                Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(B)], T, args.iterations, lanes=lanes),
                 workload=f"the N=1 job (1M iterations per decision over {T} trees) split over {world} GPU(s)")
+        # the throughput geometry: many private trees per decision, one lane each (profiles/r02_head_to_head.md: equal
+        # playing strength, the reference's decision on 16 of 17 decisive golden positions)
+        extra["wide"] = leg_line(
+            Leg([capi.kw_deal(DEAL_SEED, i, 4) for i in range(args.wide_positions)], args.wide_trees * world, iterations),
+            workload=f"1M iterations per decision over {args.wide_trees} private trees of "
+                     f"{args.iterations // args.wide_trees} iterations, one lane per tree, persistent grid")
         # one decision at a time through the host-buffer call, as SOSolver<Card, CudaRootParallel>{1M}(game) issues it
         single = Leg([capi.kw_deal(DEAL_SEED, 0, 4)], args.single_trees * world, iterations)
         s_sec = single.e2e_timed(5, 2, first_step=200)

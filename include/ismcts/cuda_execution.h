@@ -31,6 +31,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace ISMCTS
@@ -134,6 +135,13 @@ public:
     }
     std::vector<int> const &devices() const { return m_devices; }
 
+    /// Root parallel: lanes that search each tree together, with virtual loss (default 128, one block of the kernel;
+    /// capped so that every lane keeps at least minIterationsPerLane iterations).  1: every tree is searched
+    /// sequentially by one lane, exactly as a thread of the reference's RootParallel does, and a seeded search is
+    /// reproducible bit for bit; with more lanes the interleaving inside a tree is the hardware's.
+    void setLanesPerTree(unsigned int lanes) { m_lanesPerTree = std::max(lanes, 1u); }
+    unsigned int lanesPerTree() const { return m_lanesPerTree; }
+
     /// How many of the searched trees currentTrees() materialises on the host (default 8).
     void setMaterialisedTrees(unsigned int count) { m_materialised = count; }
 
@@ -146,9 +154,7 @@ protected:
     /// Fewest iterations a tree gets when the number of trees is chosen automatically.  Spreading a
     /// small budget over many trees leaves every root child with one visit (solvertest.cpp:131-138
     /// expects a decision from 16 iterations), so small budgets use one tree.
-    static constexpr std::size_t minIterationsPerTree = 256;
-    /// One resident wave of the search kernel on a B200: 148 SMs x 8 CTAs x 128 lanes.
-    static constexpr unsigned int fullWave = 148 * 8 * 128;
+    static constexpr std::size_t minIterationsPerTree = 1024;
 
     CudaExecutionPolicy(std::size_t iterationCount, unsigned int parallelism, bool sharedTree)
         : m_parallelism{parallelism}, m_sharedTree{sharedTree}
@@ -164,14 +170,27 @@ protected:
         setIterationTime(iterationTime);
     }
 
+    /// Root parallel with the number of trees left open: as many trees as the reference's RootParallel builds by
+    /// default — one per hardware thread of the host (execution.h:160-167,181-189) — so that the search has the
+    /// reference's geometry (a 1M-iteration decision on a 16-core host: 16 trees of 62,500 iterations, whose
+    /// decisions agree with the reference's, profiles/r02_head_to_head.md), but not more than the budget feeds.
     unsigned int treesFor(std::size_t iterations) const
     {
         if (m_sharedTree)
             return 1;
+        unsigned int const host = std::max(1u, std::thread::hardware_concurrency());
         if (iterations == 0)
-            return fullWave / 4;  // time mode: every tree iterates until the deadline
-        std::size_t const trees = iterations / minIterationsPerTree;
-        return static_cast<unsigned int>(std::min<std::size_t>(std::max<std::size_t>(trees, 1), fullWave));
+            return host;  // time mode: every tree iterates until the deadline
+        return static_cast<unsigned int>(std::min<std::size_t>(std::max<std::size_t>(iterations / minIterationsPerTree, 1), host));
+    }
+
+    /// Root parallel: the lanes that search one tree (setLanesPerTree), capped like the lanes of tree parallelisation.
+    unsigned int lanesPerTreeFor(std::size_t iterations, unsigned int trees) const
+    {
+        if (iterations == 0)
+            return m_lanesPerTree;
+        std::size_t const cap = iterations / trees / minIterationsPerLane;
+        return static_cast<unsigned int>(std::max<std::size_t>(1, std::min<std::size_t>(m_lanesPerTree, cap)));
     }
 
     bool sharedTree() const { return m_sharedTree; }
@@ -235,8 +254,9 @@ protected:
         desc.seed = m_seed;
         desc.exploration = exploration;
         desc.dump_tree = 0xFFFFFFFFu;
-        desc.flags = m_sharedTree ? (ISMCTS_FLAG_SHARED_TREE | (lanesFor(m_iterCount) << ISMCTS_FLAG_LANES_SHIFT)) : 0;
-        if (m_materialised > 0 && count == 1)
+        unsigned int const lanes = m_sharedTree ? lanesFor(m_iterCount) : lanesPerTreeFor(m_iterCount, treesTotal);
+        desc.flags = (m_sharedTree || lanes > 1) ? (ISMCTS_FLAG_SHARED_TREE | (lanes << ISMCTS_FLAG_LANES_SHIFT)) : 0;
+        if (m_materialised > 0 && count == 1 && desc.flags == 0)
             desc.flags |= ISMCTS_FLAG_KEEP_TREES;   // currentTrees() reads trees back after the search
 
         std::vector<std::uint64_t> visits(count * stride), score2(count * stride), avail(count * stride), iters(count * treesTotal);
@@ -297,15 +317,17 @@ private:
     bool m_seedFixed {false};
     std::vector<int> m_devices {0};
     std::vector<std::unique_ptr<detail::Context>> m_contexts;
+    unsigned int m_lanesPerTree {128};
     unsigned int m_materialised {8};
     unsigned int m_lastTreesOnFirstDevice {0};
     detail::RootStatistics m_last;
     std::vector<detail::RootStatistics> m_lastBatch;
 };
 
-/// Root parallelisation on the GPU: `numTrees` independent trees (0 = chosen from the budget),
-/// one per lane; the decision sums the root visits per move over all trees
-/// (RootParallel, execution.h:181-232).
+/// Root parallelisation on the GPU: `numTrees` independent trees (0 = one per hardware thread of the host, as the
+/// reference's default, fewer for small budgets), each searched by a block of lanes (setLanesPerTree); the
+/// decision sums the root visits per move over all trees (RootParallel, execution.h:181-232).  The throughput
+/// geometry of bench.py's `extra.wide` leg is CudaRootParallel{1000000, 2368} with setLanesPerTree(1).
 class CudaRootParallel : public CudaExecutionPolicy
 {
 public:

@@ -42,15 +42,35 @@
 
 /* UCB1 value, utility.h:96-99 with X = score/visits (ucb1.h:36-39):
  *   score/visits + C * sqrt(ln(available) / visits)
- * score2 = 2*score (rewards are multiples of 1/2), ln_avail = ln(available). */
-ISMCTS_HD double ismcts_ucb_value(uint32_t score2, uint32_t visits, double ln_avail, double exploration)
+ * evaluated from three factors that depend on ONE integer each,
+ *   (score2 / 2) * [1 / visits]  +  C * ([sqrt(ln(available))] * [1 / sqrt(visits)]),
+ * score2 = 2*score (rewards are multiples of 1/2).  The bracketed factors are the table entries below: the
+ * kernels read them from tables the host builds with these very functions, the oracle calls the functions —
+ * the same bits on both sides, and a child evaluation on the GPU is two table look-ups, three multiplications
+ * and an addition instead of two double-precision divisions and a square root (which were 8 % of the
+ * instructions of a search with deep trees, profiles/r02_hybrid.md).  The value differs from the reference's
+ * expression by a few units in the last place (a deviation like that of any other libm); the order of the
+ * children it induces is what matters, and is pinned against the reference statistically (tests/test_ref_stats.py,
+ * tests/test_gpu_geometry.py). */
+ISMCTS_HD double ismcts_ucb_value(uint32_t score2, double inv_visits, double inv_sqrt_visits, double sqrt_ln_avail,
+                                  double exploration)
 {
-    const double v = (double)visits;
-    /* 0 / v is exactly 0: many nodes have no win yet, and a zero numerator takes the slow path of the GPU's division */
-    const double x = score2 ? ISMCTS_DDIV(ISMCTS_DMUL((double)score2, 0.5), v) : 0.0;
-    const double e = ISMCTS_DMUL(exploration, ISMCTS_DSQRT(ISMCTS_DDIV(ln_avail, v)));
+    /* 0 * x is exactly 0: many nodes have no win yet */
+    const double x = score2 ? ISMCTS_DMUL(ISMCTS_DMUL((double)score2, 0.5), inv_visits) : 0.0;
+    const double e = ISMCTS_DMUL(exploration, ISMCTS_DMUL(sqrt_ln_avail, inv_sqrt_visits));
     return ISMCTS_DADD(x, e);
 }
+
+/* The table entries (host code: log() is libm's; division and square root are IEEE's, rounded once).  Entry 0 of
+ * the visit factors is never used: a child that can be selected has been visited. */
+#if defined(__CUDACC__)
+#define ISMCTS_HOST_ONLY __host__ static inline
+#else
+#define ISMCTS_HOST_ONLY static inline
+#endif
+ISMCTS_HOST_ONLY double ismcts_tab_inv_visits(uint32_t v) { return v ? 1.0 / (double)v : 0.0; }
+ISMCTS_HOST_ONLY double ismcts_tab_inv_sqrt_visits(uint32_t v) { return v ? 1.0 / sqrt((double)v) : 0.0; }
+ISMCTS_HOST_ONLY double ismcts_tab_sqrt_ln(uint32_t a) { return a ? sqrt(log((double)a)) : 0.0; }
 
 /* exp(x) for x <= 0 (callers subtract the maximum first), relative error
  * about 2e-16, from exactly-rounded operations only. */

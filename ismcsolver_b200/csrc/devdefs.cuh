@@ -75,6 +75,11 @@ ISMCTS_DEV uint64_t load_u64_acquire(const uint64_t* p)
 ISMCTS_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 // A table in global memory nobody writes during the kernel (ln): the read-only path through L1.
 ISMCTS_DEV double load_f64_readonly(const double* p) { return __ldg(p); }
+template <class T> ISMCTS_DEV T load_factors_readonly(const T* p)
+{
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return T{v.x, v.y};
+}
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return __ldcg(p); }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
 // Fire-and-forget 64-bit reduction (SASS RED.E.ADD.64): no return value, no scoreboard wait.
@@ -111,6 +116,7 @@ ISMCTS_DEV void atomic_add_f64(double* p, double v) { *p = ISMCTS_DADD(*p, v); }
 ISMCTS_DEV uint64_t load_u64_acquire(const uint64_t* p) { return *p; }
 ISMCTS_DEV void prefetch_l2(const void*) {}
 ISMCTS_DEV double load_f64_readonly(const double* p) { return *p; }
+template <class T> ISMCTS_DEV T load_factors_readonly(const T* p) { return *p; }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return *p; }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }

@@ -152,7 +152,8 @@ struct ismcts_ctx {
 
     // device buffers, grown on demand
     void* pool = nullptr;        size_t pool_bytes = 0;
-    double* ln_table = nullptr;  uint32_t ln_count = 0;
+    double* ln_table = nullptr;  uint32_t ln_count = 0;     // EXP3's ln(); entries of the two UCB1 tables
+    UcbVisitFactors* visit_tab = nullptr; double* sqrt_ln_tab = nullptr;
     void* roots = nullptr;       size_t roots_bytes = 0;
     void* prepared = nullptr;    size_t prepared_bytes = 0;
     uint64_t* out = nullptr;     size_t out_bytes = 0;   // visits | score2 | avail | iters
@@ -246,7 +247,7 @@ void ismcts_destroy(ismcts_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->roots); cudaFree(ctx->prepared);
+    cudaFree(ctx->pool); cudaFree(ctx->ln_table); cudaFree(ctx->visit_tab); cudaFree(ctx->sqrt_ln_tab); cudaFree(ctx->roots); cudaFree(ctx->prepared);
     cudaFree(ctx->out); cudaFree(ctx->play_out); cudaFree(ctx->start_ns); cudaFree(ctx->queue);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -374,18 +375,34 @@ static int validate_roots(ismcts_ctx* ctx, uint32_t game, const void* roots, uin
     return ISMCTS_OK;
 }
 
-// Builds ln(i), i < count, with the host libm (the oracle uses the same libm, so
-// UCB values agree bit for bit; CUDA's log() does not).
+// The tables the bandits read (include/ismcts_detmath.h), built with the host libm — the oracle uses the same libm
+// and the same expressions, so UCB values agree bit for bit; CUDA's log() does not.  ln(K), K < kLnSmall, for EXP3,
+// once; the UCB1 factors {1 / v, 1 / sqrt(v)} and sqrt(ln(a)) for v, a < count, regrown on demand.
 static int ensure_ln_table(ismcts_ctx* ctx, uint32_t count)
 {
+    if (!ctx->ln_table) {
+        std::vector<double> host(kLnSmall);
+        host[0] = 0.0;
+        for (uint32_t i = 1; i < kLnSmall; ++i) host[i] = std::log((double)i);
+        CUDA_TRY(ctx, cudaMalloc((void**)&ctx->ln_table, (size_t)kLnSmall * sizeof(double)));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->ln_table, host.data(), (size_t)kLnSmall * sizeof(double), cudaMemcpyHostToDevice));
+    }
     if (count <= ctx->ln_count) return ISMCTS_OK;
     count = std::max<uint32_t>(count, 4096);
-    std::vector<double> host(count);
-    host[0] = 0.0;
-    for (uint32_t i = 1; i < count; ++i) host[i] = std::log((double)i);
-    if (ctx->ln_table) { CUDA_TRY(ctx, cudaFree(ctx->ln_table)); ctx->ln_table = nullptr; ctx->ln_count = 0; }
-    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->ln_table, (size_t)count * sizeof(double)));
-    CUDA_TRY(ctx, cudaMemcpy(ctx->ln_table, host.data(), (size_t)count * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<UcbVisitFactors> by_visits(count);
+    std::vector<double> sqrt_ln(count);
+    for (uint32_t i = 0; i < count; ++i) {
+        by_visits[i].inv = ismcts_tab_inv_visits(i);
+        by_visits[i].inv_sqrt = ismcts_tab_inv_sqrt_visits(i);
+        sqrt_ln[i] = ismcts_tab_sqrt_ln(i);
+    }
+    if (ctx->visit_tab) { CUDA_TRY(ctx, cudaFree(ctx->visit_tab)); ctx->visit_tab = nullptr; }
+    if (ctx->sqrt_ln_tab) { CUDA_TRY(ctx, cudaFree(ctx->sqrt_ln_tab)); ctx->sqrt_ln_tab = nullptr; }
+    ctx->ln_count = 0;
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->visit_tab, (size_t)count * sizeof(UcbVisitFactors)));
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->sqrt_ln_tab, (size_t)count * sizeof(double)));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->visit_tab, by_visits.data(), (size_t)count * sizeof(UcbVisitFactors), cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->sqrt_ln_tab, sqrt_ln.data(), (size_t)count * sizeof(double), cudaMemcpyHostToDevice));
     ctx->ln_count = count;
     return ISMCTS_OK;
 }
@@ -564,6 +581,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.pool = ctx->pool; P.log2cap = log2cap;
     P.max_nodes = (uint32_t)std::min<uint64_t>(((uint64_t)1 << (log2cap - 1)), (uint64_t)per_lane * (ctx->ln_count - 2));
     P.ln_table = ctx->ln_table; P.ln_count = ctx->ln_count;
+    P.visit_tab = ctx->visit_tab; P.sqrt_ln_tab = ctx->sqrt_ln_tab;
     P.visits = d_visits; P.score2 = d_score2; P.avail = d_avail; P.iters_done = d_iters;
     P.playout_out = nullptr;
     P.lanes_per_tree = width;

@@ -37,6 +37,9 @@
 
 namespace ismcts {
 
+struct alignas(16) UcbVisitFactors { double inv, inv_sqrt; };
+constexpr uint32_t kLnSmall = 4096;   // entries of the ln() table EXP3 reads (a node has at most 256 children)
+
 struct SearchParams {
     const void* prepared;    // n_positions Game::Prepared records (prepare_kernel)
     uint32_t n_positions;
@@ -51,7 +54,11 @@ struct SearchParams {
     void* pool;              // [n_positions * trees] tables of (1 << log2cap) slots, zeroed
     uint32_t log2cap;
     uint32_t max_nodes;      // a tree stops iterating before exceeding this many nodes
-    const double* ln_table;  // ln(i) for i < ln_count, built on the host (bit-exact with the oracle)
+    const double* ln_table;  // EXP3: ln(K) for K < kLnSmall children, built on the host (bit-exact with the oracle)
+    // UCB1 (include/ismcts_detmath.h: ismcts_ucb_value): {1 / v, 1 / sqrt(v)} for v < ln_count visits and sqrt(ln(a)) for
+    // a < ln_count availabilities, built on the host
+    const UcbVisitFactors* visit_tab;
+    const double* sqrt_ln_tab;
     uint32_t ln_count;
     uint64_t* visits;        // [n_positions * stride] root-child sums (compileVisitCounts, execution.h:219-231)
     uint64_t* score2;
@@ -276,16 +283,18 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             chosen.created = 0xFFFFFFFFu;
             // copies: what is read through `this` or P would be read again after every store to a node
             const TreePool<S> pool = tree;
-            const double* const ln = P.ln_table;
+            const UcbVisitFactors* const by_visits = P.visit_tab;
+            const double* const sqrt_ln = P.sqrt_ln_tab;
             const double exploration = P.exploration;
-            const uint32_t ln_last = P.ln_count - 1u;                 // (never reached: budget_left())
+            const uint32_t last = P.ln_count - 1u;                    // (never reached: budget_left())
             for (Mask rest = legal; rest.any();) {
                 const uint32_t move = rest.pop_lowest();
                 S c;
                 const uint32_t ci = pool.find(parent, move, c);
                 c.avail += 1;
                 pool.slots[ci].avail = c.avail;
-                const double u = ismcts_ucb_value(c.score2, c.visits, load_f64_readonly(ln + (c.avail < ln_last ? c.avail : ln_last)), exploration);
+                const UcbVisitFactors f = load_factors_readonly(by_visits + (c.visits < last ? c.visits : last));
+                const double u = ismcts_ucb_value(c.score2, f.inv, f.inv_sqrt, load_f64_readonly(sqrt_ln + (c.avail < last ? c.avail : last)), exploration);
                 if (u > best_u || (u == best_u && c.created < chosen.created)) { best_u = u; best = ci; chosen = c; chosen_move = move; }
             }
             return best;
@@ -428,11 +437,12 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             double best_u = -1.0;
             uint32_t best_created = 0xFFFFFFFFu, best = 0;
             const TreePool<S> pool = tree;
-            const double* const ln = P.ln_table;
+            const UcbVisitFactors* const by_visits = P.visit_tab;
+            const double* const sqrt_ln = P.sqrt_ln_tab;
             const double exploration = P.exploration;
-            const uint32_t ln_last = P.ln_count - 1u;
+            const uint32_t last = P.ln_count - 1u;
             // The children one after the other, two loads ahead of the arithmetic: while the value of a child is
-            // computed its ln() (a table of tens of thousands of entries for a deep tree: an L2 access that depends
+            // computed its table factors (tables of tens of thousands of entries for a deep tree: L2 accesses that depend
             // on the slot just read) and the slot of the NEXT child are in flight.  Evaluated strictly one after the
             // other, a level cost two dependent L2 round trips per child — 57 % of this kernel's long-scoreboard
             // stalls (profiles/r02_hybrid.md).
@@ -442,8 +452,9 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             S c = load_slot(&pool.slots[i]);
             for (;;) {
                 const uint32_t ci = pool.resolve(parent, m, i, c);
-                const uint32_t avail = c.avail + 1u < ln_last ? c.avail + 1u : ln_last;
-                const double ln_avail = load_f64_readonly(ln + avail);
+                const uint32_t avail = c.avail + 1u < last ? c.avail + 1u : last;
+                const double sqrt_ln_avail = load_f64_readonly(sqrt_ln + avail);
+                const UcbVisitFactors f = load_factors_readonly(by_visits + (c.visits < last ? c.visits : last));
                 const bool more = rest.any();
                 uint32_t m_next = 0, i_next = 0;
                 S c_next = c;
@@ -453,7 +464,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                     c_next = load_slot(&pool.slots[i_next]);
                 }
                 red_add_u32(&pool.slots[ci].avail, 1u);                    // markAvailable, ucb1.h:71-72
-                const double u = ismcts_ucb_value(c.score2, c.visits, ln_avail, exploration);
+                const double u = ismcts_ucb_value(c.score2, f.inv, f.inv_sqrt, sqrt_ln_avail, exploration);
                 if (u > best_u || (u == best_u && c.created < best_created)) {
                     best_u = u; best_created = c.created; best = ci; chosen_move = m; chosen_player = c.player;
                 }

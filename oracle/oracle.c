@@ -995,7 +995,8 @@ static int otree_untried(const otree* t, uint32_t node, const uint16_t* legal, i
 
 double orc_ucb(uint32_t score2, uint32_t visits, uint32_t avail, double exploration)
 {
-    return ismcts_ucb_value(score2, visits, log((double)avail), exploration);
+    return ismcts_ucb_value(score2, ismcts_tab_inv_visits(visits), ismcts_tab_inv_sqrt_visits(visits),
+                            ismcts_tab_sqrt_ln(avail), exploration);
 }
 
 void orc_exp3_probabilities(const double* scores, const uint32_t* visits, uint32_t K, double* p_out)

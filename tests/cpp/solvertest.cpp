@@ -21,6 +21,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <thread>
 
 using namespace ISMCTS;
 using namespace std::chrono_literals;
@@ -391,6 +392,8 @@ int main(int argc, char **argv)
             pomRoots.push_back(games.back().get());
         }
         SOSolver<Card, CudaRootParallel> batch {20000};
+        CHECK(batch.lanesPerTree() == 128);
+        batch.setLanesPerTree(1);     // one lane per tree: a seeded search is reproducible bit for bit
         batch.setSeed(7);
         auto const moves = batch(roots);
         CHECK(moves.size() == roots.size());
@@ -401,6 +404,7 @@ int main(int argc, char **argv)
         }
         auto const first = batch.lastBatchStatistics().front();
         SOSolver<Card, CudaRootParallel> single {20000};
+        single.setLanesPerTree(1);
         single.setSeed(7);
         CHECK(single(*roots.front()) == moves.front());
         CHECK(single.lastStatistics().visits == first.visits);
@@ -414,6 +418,14 @@ int main(int argc, char **argv)
         for (std::size_t g = 0; g < roots.size(); ++g)
             CHECK(isValid(*roots[g], treeMoves[g]));
         CHECK(batch(std::vector<Game<Card> const *>{}).empty());
+        // the default geometry: one tree per host thread, a block of lanes on each (virtual loss inside a tree)
+        SOSolver<Card, CudaRootParallel> blocks {200000};
+        CHECK(blocks.numThreads() == std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 200000 / 1024));
+        auto const blockMoves = blocks(roots);
+        for (std::size_t g = 0; g < roots.size(); ++g) {
+            CHECK(isValid(*roots[g], blockMoves[g]));
+            CHECK(blocks.lastBatchStatistics()[g].iterations() == 200000);
+        }
         // a budget that takes more trees than the GPU holds lanes (persistent grid) through the C++ layer
         SOSolver<Card, CudaRootParallel> wide {400000, 20000};
         wide.setSeed(3);
@@ -432,6 +444,8 @@ int main(int argc, char **argv)
             devices.push_back(d);
         KnockoutWhist game {4, 42};
         SOSolver<Card, CudaRootParallel> one {100000, 64}, many {100000, 64};
+        one.setLanesPerTree(1);
+        many.setLanesPerTree(1);
         one.setSeed(11);
         many.setSeed(11);
         many.setDevices(devices);
@@ -442,6 +456,8 @@ int main(int argc, char **argv)
         CHECK(one.lastStatistics().available == many.lastStatistics().available);
         CHECK(many.lastStatistics().iterations() == 100000);
         MOSolver<Card, CudaRootParallel, EXP3> moOne {30000, 32}, moMany {30000, 32};
+        moOne.setLanesPerTree(1);
+        moMany.setLanesPerTree(1);
         moOne.setSeed(5);
         moMany.setSeed(5);
         moMany.setDevices(devices);

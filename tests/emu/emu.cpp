@@ -113,11 +113,26 @@ FiberWarp* FiberWarp::active_ = nullptr;
 
 std::vector<double> ln_table(size_t n)
 {
-    std::vector<double> ln(n);
+    std::vector<double> ln(std::max<size_t>(n, kLnSmall));
     ln[0] = 0.0;
-    for (size_t i = 1; i < n; ++i) ln[i] = std::log((double)i);
+    for (size_t i = 1; i < ln.size(); ++i) ln[i] = std::log((double)i);
     return ln;
 }
+
+// The UCB1 tables of the engine (engine.cu: ensure_ln_table), installed in P.
+struct UcbTables {
+    std::vector<UcbVisitFactors> by_visits;
+    std::vector<double> sqrt_ln;
+    explicit UcbTables(size_t n) : by_visits(n), sqrt_ln(n)
+    {
+        for (size_t i = 0; i < n; ++i) {
+            by_visits[i].inv = ismcts_tab_inv_visits((uint32_t)i);
+            by_visits[i].inv_sqrt = ismcts_tab_inv_sqrt_visits((uint32_t)i);
+            sqrt_ln[i] = ismcts_tab_sqrt_ln((uint32_t)i);
+        }
+    }
+    void install(SearchParams& P) const { P.visit_tab = by_visits.data(); P.sqrt_ln_tab = sqrt_ln.data(); P.ln_count = (uint32_t)sqrt_ln.size(); }
+};
 
 // One table -> the node records of the tree rooted at slot `root_slot`, in creation order.
 template <class Slot>
@@ -211,7 +226,9 @@ int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos,
     P.prepared = &prepared; P.n_positions = 1; P.trees = width; P.trees_total = first_tree + width; P.tree_base = first_tree;
     P.pos_base = pos; P.iterations = iterations * P.trees_total; P.seed = seed; P.exploration = exploration;
     P.pool = tables.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
-    P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
+    P.ln_table = ln.data();
+    const UcbTables ucb(iterations + 300);
+    ucb.install(P);
     P.visits = v.data(); P.score2 = s.data(); P.avail = a.data(); P.iters_done = it.data();
     P.lanes_per_tree = 1;
     WarpScratch<Game> ws(width);
@@ -261,7 +278,9 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     std::memset(&P, 0, sizeof P);
     P.prepared = &prepared; P.n_positions = 1; P.trees = 1; P.trees_total = 1; P.iterations = iterations;
     P.seed = seed; P.exploration = 0.7; P.pool = table.data(); P.log2cap = log2cap; P.max_nodes = 1u << (log2cap - 1);
-    P.ln_table = ln.data(); P.ln_count = (uint32_t)ln.size();
+    P.ln_table = ln.data();
+    const UcbTables ucb(iterations + 300);
+    ucb.install(P);
     P.visits = v.data(); P.score2 = s2.data(); P.avail = a.data(); P.iters_done = it.data();
     P.lanes_per_tree = width;
     init_shared_root<Slot>(P, 0, n_roots);
