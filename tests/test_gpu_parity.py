@@ -500,46 +500,21 @@ def test_tree_parallel_lanes_cap_keeps_the_decision(engine):
     """Tree parallelisation at 1M iterations on the empty 9x9 board (k = 5): with the lanes capped at
     iterations / 128 (cuda_execution.h: lanesFor) all of eight independent searches play the centre, as the
     sequential search does (profiles/r02_tree_parallel_quality.md); with 151,552 lanes in flight — 6.6 iterations
-    per lane, what round 1 benchmarked — most of them do not."""
+    per lane, what round 1 benchmarked — the search has lost its focus: the most visited move holds less than half
+    the share of the visits it holds at the cap (measured 0.06 against 0.26; sequential 0.40) and some of the
+    searches decide otherwise (which ones depends on how the hardware interleaves the lanes)."""
     iterations, seeds, centre = 1_000_000, 8, 40
     roots = capi.pack_states([capi.mnk_init(9, 9, 5)] * seeds)
 
-    def decisions(lanes):
+    def search(lanes):
         res = engine.search(engine.make_desc(capi.GAME_MNK, seeds, 1, iterations=iterations, seed=20262,
                                              flags=_shared_flags(lanes)), roots)
         assert (res["iterations_done"].sum(axis=1) == iterations).all()
-        return [int(b) for b in res["best_move"]]
+        share = (res["visits"].max(axis=1) / res["visits"].sum(axis=1)).mean()
+        return [int(b) for b in res["best_move"]], float(share)
 
-    capped = decisions(iterations // 128 // 32 * 32)
+    capped, capped_share = search(iterations // 128 // 32 * 32)
     assert capped == [centre] * seeds, capped
-    flooded = decisions(151552)
-    assert sum(b == centre for b in flooded) <= seeds // 2, flooded
-
-
-def test_search_multi_equals_one_context(engine):
-    """ismcts_search_multi shards the trees of a request over several contexts (one per device on a multi-GPU box;
-    here several contexts on the same device, which exercises the same sharding, threading and summing) and returns
-    what one context returns."""
-    import torch
-    n_pos, trees, iterations = 3, 50, 50 * 120 + 7
-    states = [_midgame(61, i, i * 8) for i in range(n_pos)]
-    roots = capi.pack_states(states)
-    desc = engine.make_desc(capi.GAME_KW, n_pos, trees, iterations=iterations, seed=99)
-    one = engine.search(desc, roots)
-    devices = list(range(torch.cuda.device_count()))
-    others = [capi.Engine(d) for d in (devices[1:] if len(devices) > 1 else [0, 0])]
-    try:
-        many = engine.search_multi(others, desc, roots)
-    finally:
-        for e in others:
-            e.close()
-    for k in ("visits", "score2", "avail", "iterations_done", "best_move"):
-        assert (one[k] == many[k]).all(), k
-    mo = engine.make_desc(capi.GAME_KW, n_pos, 9, iterations=9 * 300, seed=5, solver=capi.SOLVER_MO, policy=capi.POLICY_EXP3)
-    others = [capi.Engine(0)]
-    try:
-        a, b = engine.search(mo, roots), engine.search_multi(others, mo, roots)
-    finally:
-        others[0].close()
-    for k in ("visits", "score2", "avail", "iterations_done", "best_move"):
-        assert (a[k] == b[k]).all(), k
+    assert capped_share >= 0.15, capped_share
+    _, flooded_share = search(151552)
+    assert flooded_share <= 0.5 * capped_share, (flooded_share, capped_share)
