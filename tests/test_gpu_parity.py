@@ -518,3 +518,38 @@ def test_tree_parallel_lanes_cap_keeps_the_decision(engine):
     assert capped_share >= 0.15, capped_share
     _, flooded_share = search(151552)
     assert flooded_share <= 0.5 * capped_share, (flooded_share, capped_share)
+
+
+def test_malformed_root_records_are_rejected(engine):
+    """Everything a kernel indexes with is checked on the host before a search or a playout: a record
+    with a player, a trick entry, a hand or a board out of range fails with ISMCTS_ERR_INVALID and names the position."""
+    good = capi.kw_deal(1, 1, 4)
+
+    def broken(**fields):
+        s = capi.KwState.from_buffer_copy(bytes(good))
+        for k, v in fields.items():
+            setattr(s, k, v)
+        return s
+
+    cases = [broken(num_players=8), broken(num_players=1), broken(player=4), broken(dealer=7), broken(alive_mask=0),
+             broken(alive_mask=0b10001), broken(trump=4), broken(tricks_left=8), broken(trick_len=5)]
+    s = capi.KwState.from_buffer_copy(bytes(good)); s.hands[0] = (1 << 8) - 1; cases.append(s)          # eight cards
+    s = capi.KwState.from_buffer_copy(bytes(good)); s.hands[1] |= 1 << 60; cases.append(s)               # a card that does not exist
+    s = capi.KwState.from_buffer_copy(bytes(good)); s.hands[5] = 1; cases.append(s)                      # a player that does not exist
+    s = capi.KwState.from_buffer_copy(bytes(good)); s.trick_len = 1; s.trick_player[0] = 6; cases.append(s)
+    for i, bad in enumerate(cases):
+        roots = capi.pack_states([good, bad])
+        with pytest.raises(capi.EngineError) as e:
+            engine.search(engine.make_desc(capi.GAME_KW, 2, 2, iterations=20, seed=1), roots)
+        assert e.value.code == capi.ERR_INVALID and "position 1" in str(e.value), (i, str(e.value))
+        with pytest.raises(capi.EngineError):
+            engine.playouts(capi.GAME_KW, roots, 2, 4, seed=1)
+    board = capi.mnk_init(3, 3, 3)
+    board.m, board.n = 20, 20                                                                            # 400 cells
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(capi.GAME_MNK, 1, 1, iterations=10), capi.pack_states([board]))
+    # unknown flag bits, and lanes = 0 with a shared tree
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=10, flags=16), capi.pack_states([good]))
+    with pytest.raises(capi.EngineError):
+        engine.search(engine.make_desc(capi.GAME_KW, 1, 1, iterations=10, flags=capi.FLAG_SHARED_TREE), capi.pack_states([good]))
