@@ -387,12 +387,21 @@ def b200_arm(args):
                                if world > 1 else "1M iterations per decision"),
                 "iterations_per_decision": iterations, "positions_per_step": B,
                 "trees_per_position": T * world, "iterations_per_tree": iterations / (T * world),
-                "wave_width": 1, "deal_seed": hex(DEAL_SEED), "exploration": 0.7,
-                "parallelism": f"root-parallel trees sharded over {world} GPU(s), NCCL all-reduce of root arrays"
-                               if world > 1 else "root-parallel, one tree per thread",
-                "grid": "persistent: warps claim 32 trees at a time and reuse their node tables"
-                        if B * T > 148 * 8 * 128 else "one tree per lane, one wave",
-                "l2": "the node tables in use (about 5 GB) are far larger than the 126 MB L2; every tree starts from a zeroed table",
+                "trees_source": ("the hardware threads of this box's host: the trees the reference's RootParallel builds here "
+                                 "(execution.h:160-167,181-189), and what `--impl reference` runs") if not args.trees else "--trees",
+                "lanes_per_tree": lanes, "iterations_per_lane": iterations / (T * world) / lanes,
+                "wave_width": lanes, "deal_seed": hex(DEAL_SEED), "exploration": 0.7,
+                "parallelism": ("root-parallel trees, each searched by a block of lanes with virtual loss"
+                                if lanes > 1 else "root-parallel, one lane per tree")
+                               + (f"; trees sharded over {world} GPUs, NCCL all-reduce of root arrays" if world > 1 else ""),
+                "grid": ("one block per tree, %d waves of blocks" % max(1, B * T * lanes // (148 * 8 * 128))) if lanes > 1
+                        else ("persistent: warps claim 32 trees at a time and reuse their node tables"
+                              if B * T > 148 * 8 * 128 else "one tree per lane, one wave"),
+                "l2": "the node tables in use (%.0f GB) are far larger than the 126 MB L2; every tree starts from a zeroed table"
+                      % ((B * T * (32 << max(4, (2 * (iterations // (T * world) + 2 + lanes) - 1).bit_length())) / 2**30)
+                         if lanes > 1 else 4.97),
+                "geometry_evidence": "profiles/r02_head_to_head.md, tests/test_gpu_geometry.py: decisions equal the unmodified "
+                                     "reference's on 17 of 17 decisive golden positions; `extra.wide` is round 1's geometry",
             },
             "search_kernel_ms": search_ms,
             "iterations_done_per_step": per_launch_iters,
