@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (position stream, MO+EXP3, ...)")
     ap.add_argument("--mo-trees", type=int, default=4736, help="extra leg MO+EXP3: lanes (sets of trees) per position")
-    ap.add_argument("--single-trees", type=int, default=3906, help="extra leg single decision: trees (CudaRootParallel's own choice for 1M)")
+    ap.add_argument("--single-trees", type=int, default=3906, help="extra leg single decision with --lanes 1: private trees")
     return ap.parse_args()
 
 
@@ -360,11 +360,15 @@ def b200_arm(args):
             workload=f"1M iterations per decision over {args.wide_trees} private trees of "
                      f"{args.iterations // args.wide_trees} iterations, one lane per tree, persistent grid")
         # one decision at a time through the host-buffer call, as SOSolver<Card, CudaRootParallel>{1M}(game) issues it
-        single = Leg([capi.kw_deal(DEAL_SEED, 0, 4)], args.single_trees * world, iterations)
+        single_lanes = max(1, min(iterations // (T * world) // 128, 148 * 8 * 128 // (T * world))) if lanes > 1 else 1
+        single = Leg([capi.kw_deal(DEAL_SEED, 0, 4)], (T if lanes > 1 else args.single_trees) * world, iterations, lanes=single_lanes)
         s_sec = single.e2e_timed(5, 2, first_step=200)
         extra["single_decision"] = {"value": iterations * 5 / s_sec, "unit": UNIT, "ms_per_decision": 1e3 * s_sec / 5,
-                                    "trees": single.trees_total, "iterations_per_decision": iterations,
-                                    "workload": "ONE position per call, host buffers (ismcts_search), wall clock"}
+                                    "trees": single.trees_total, "lanes_per_tree": single_lanes,
+                                    "iterations_per_decision": iterations,
+                                    "workload": "ONE position per call, host buffers (ismcts_search), wall clock: what "
+                                                "SOSolver<Card, CudaRootParallel>{1M}(game) issues (lanes per tree capped at "
+                                                "iterations / trees / 128)"}
 
     if rank == 0:
         peaks = {}

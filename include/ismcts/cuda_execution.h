@@ -135,11 +135,13 @@ public:
     }
     std::vector<int> const &devices() const { return m_devices; }
 
-    /// Root parallel: lanes that search each tree together, with virtual loss (default 128, one block of the kernel;
-    /// capped so that every lane keeps at least minIterationsPerLane iterations).  1: every tree is searched
-    /// sequentially by one lane, exactly as a thread of the reference's RootParallel does, and a seeded search is
-    /// reproducible bit for bit; with more lanes the interleaving inside a tree is the hardware's.
-    void setLanesPerTree(unsigned int lanes) { m_lanesPerTree = std::max(lanes, 1u); }
+    /// Root parallel: lanes that search each tree together, with virtual loss.  0 (default): chosen per search — a
+    /// block of 128 when the positions of the call fill the GPU, more when they do not (a single 1M-iteration
+    /// decision: 488 lanes on each of its 16 trees), never so many that a lane keeps fewer than
+    /// minIterationsPerLane iterations.  1: every tree is searched sequentially by one lane, exactly as a thread of
+    /// the reference's RootParallel does, and a seeded search is reproducible bit for bit; with more lanes the
+    /// interleaving inside a tree is the hardware's.
+    void setLanesPerTree(unsigned int lanes) { m_lanesPerTree = lanes; }
     unsigned int lanesPerTree() const { return m_lanesPerTree; }
 
     /// How many of the searched trees currentTrees() materialises on the host (default 8).
@@ -184,13 +186,19 @@ protected:
         return static_cast<unsigned int>(std::min<std::size_t>(std::max<std::size_t>(iterations / minIterationsPerTree, 1), host));
     }
 
+    /// One resident wave of the search kernel on a B200: 148 SMs x 8 blocks x 128 lanes.
+    static constexpr std::size_t residentLanes = 148 * 8 * 128;
+
     /// Root parallel: the lanes that search one tree (setLanesPerTree), capped like the lanes of tree parallelisation.
-    unsigned int lanesPerTreeFor(std::size_t iterations, unsigned int trees) const
+    unsigned int lanesPerTreeFor(std::size_t iterations, unsigned int trees, std::size_t positions) const
     {
+        std::size_t lanes = m_lanesPerTree;
+        if (lanes == 0)   // a block per tree, or what it takes to fill the GPU with the positions at hand
+            lanes = std::max<std::size_t>(128, residentLanes / std::max<std::size_t>(1, positions * trees));
         if (iterations == 0)
-            return m_lanesPerTree;
+            return static_cast<unsigned int>(std::min<std::size_t>(lanes, 1024));
         std::size_t const cap = iterations / trees / minIterationsPerLane;
-        return static_cast<unsigned int>(std::max<std::size_t>(1, std::min<std::size_t>(m_lanesPerTree, cap)));
+        return static_cast<unsigned int>(std::max<std::size_t>(1, std::min<std::size_t>(lanes, cap)));
     }
 
     bool sharedTree() const { return m_sharedTree; }
@@ -254,7 +262,7 @@ protected:
         desc.seed = m_seed;
         desc.exploration = exploration;
         desc.dump_tree = 0xFFFFFFFFu;
-        unsigned int const lanes = m_sharedTree ? lanesFor(m_iterCount) : lanesPerTreeFor(m_iterCount, treesTotal);
+        unsigned int const lanes = m_sharedTree ? lanesFor(m_iterCount) : lanesPerTreeFor(m_iterCount, treesTotal, count);
         desc.flags = (m_sharedTree || lanes > 1) ? (ISMCTS_FLAG_SHARED_TREE | (lanes << ISMCTS_FLAG_LANES_SHIFT)) : 0;
         if (m_materialised > 0 && count == 1 && desc.flags == 0)
             desc.flags |= ISMCTS_FLAG_KEEP_TREES;   // currentTrees() reads trees back after the search
@@ -317,7 +325,7 @@ private:
     bool m_seedFixed {false};
     std::vector<int> m_devices {0};
     std::vector<std::unique_ptr<detail::Context>> m_contexts;
-    unsigned int m_lanesPerTree {128};
+    unsigned int m_lanesPerTree {0};
     unsigned int m_materialised {8};
     unsigned int m_lastTreesOnFirstDevice {0};
     detail::RootStatistics m_last;

@@ -163,6 +163,7 @@ struct ismcts_ctx {
     std::vector<std::pair<const void*, uint32_t>> resident;   // blocks of one resident wave, per search kernel
 
     int min_blocks = 8;          // resident CTAs per SM the SO/UCB1 Knockout Whist kernel is compiled for; ISMCTS_MIN_BLOCKS
+    int min_blocks_mo = 4;       // ... the MO/EXP3 Knockout Whist kernel; ISMCTS_MIN_BLOCKS_MO
 
     // geometry of the last search (for ismcts_dump_tree)
     uint32_t last_log2cap = 0, last_lanes = 0 /* tables */, last_game = 0, last_solver = 0, last_policy = 0;
@@ -238,6 +239,7 @@ int ismcts_create(int device, ismcts_ctx** out)
         return fail(nullptr, ISMCTS_ERR_CUDA, "cannot allocate device memory");
     }
     if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS")) ctx->min_blocks = std::atoi(v);
+    if (const char* v = std::getenv("ISMCTS_MIN_BLOCKS_MO")) ctx->min_blocks_mo = std::atoi(v);
     *out = ctx;
     return ISMCTS_OK;
 }
@@ -481,6 +483,12 @@ static KernelSet choose_kernels(const ismcts_ctx* ctx, const ismcts_search_desc*
     }
     if (so) return kernel_set<Game, SlotExp<Mask>, kSO, false, 4>();
     if (ucb) return kernel_set<Game, SlotUcb<Mask>, kMO, false, 4>();
+    if constexpr (Game::kGameId == ISMCTS_GAME_KW) {
+        // BASELINE config 4 (Knockout Whist, MO-ISMCTS, EXP3) at several register budgets (ISMCTS_MIN_BLOCKS_MO)
+        const bool max4 = (d->flags & ISMCTS_FLAG_KW_MAX4) != 0;
+        if (ctx->min_blocks_mo == 6) return kernel_set<Game, SlotExp<Mask>, kMO, false, 6>();
+        if (ctx->min_blocks_mo == 8) return max4 ? kernel_set<KwGame4, SlotExp<Mask>, kMO, false, 8, Game>() : kernel_set<Game, SlotExp<Mask>, kMO, false, 8>();
+    }
     return kernel_set<Game, SlotExp<Mask>, kMO, false, 4>();
 }
 

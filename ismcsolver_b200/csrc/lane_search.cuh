@@ -148,7 +148,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     uint32_t phase, depth, plies;
     uint32_t node[kTrees];   // the cursor of every tree
     Mask node_children[kTrees];
-    Mask root_children;      // SO: children of the root (saves its reload every iteration)
+    Mask root_children[kTrees]; // private trees: children of the root(s) (saves their reload every iteration)
     uint32_t done, quota;
     uint64_t deadline;
     uint32_t first_iteration; // index of this lane's first iteration (playout kernel: the playout id)
@@ -175,9 +175,14 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
         game().start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
         depth = 0; plies = 0; created_seq = 0;
         if (kMulti) {
-            for (uint32_t t = 0; t < kTrees; ++t) { node[t] = t; node_children[t] = load_slot(&tree.slots[t]).child_mask; }
+            // (private trees: the lane is the only writer of its roots' masks; shared trees re-read masks at every level)
+            for (uint32_t t = 0; t < kTrees; ++t) {
+                node[t] = t;
+                if constexpr (kShared) node_children[t] = load_slot(&tree.slots[t]).child_mask;
+                else node_children[t] = root_children[t];
+            }
         } else {
-            node[0] = 0; node_children[0] = root_children;   // (shared tree: masks are re-read at every level)
+            node[0] = 0; node_children[0] = root_children[0];
         }
         phase = kTree ? kSelect : kRollout;
     }
@@ -384,7 +389,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                         } else {
                             const Mask grown = node_children[t].with(move);
                             tree.slots[node[t]].child_mask = grown;
-                            if (!kMulti && node[t] == 0) root_children = grown;
+                            if (node[t] < kTrees) root_children[node[t]] = grown;
                             node[t] = tree.insert(node[t], move, who, tree.count);
                             node_children[t] = Mask::none();
                         }
@@ -622,7 +627,7 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
     lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
     lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0;
-    lane.root_children = Mask::none();
+    for (uint32_t t = 0; t < L::kTrees; ++t) lane.root_children[t] = Mask::none();
     uint32_t tree_index = 0;
     if (valid) {
         const uint32_t width = kShared ? P.lanes_per_tree : 1u;
@@ -725,7 +730,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
     lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
     lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0;
-    lane.root_children = Mask::none();
+    lane.root_children[0] = Mask::none();
     if (valid) {
         const uint32_t pos = gtid / per_position;
         lane.first_iteration = gtid % per_position;

@@ -392,7 +392,7 @@ int main(int argc, char **argv)
             pomRoots.push_back(games.back().get());
         }
         SOSolver<Card, CudaRootParallel> batch {20000};
-        CHECK(batch.lanesPerTree() == 128);
+        CHECK(batch.lanesPerTree() == 0);     // chosen per search
         batch.setLanesPerTree(1);     // one lane per tree: a seeded search is reproducible bit for bit
         batch.setSeed(7);
         auto const moves = batch(roots);
