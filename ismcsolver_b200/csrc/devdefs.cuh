@@ -82,6 +82,7 @@ template <class T> ISMCTS_DEV T load_factors_readonly(const T* p)
 }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return __ldcg(p); }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+ISMCTS_DEV double load_f64_cg(const double* p) { return __ldcg(p); }
 // Fire-and-forget 64-bit reduction (SASS RED.E.ADD.64): no return value, no scoreboard wait.
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v)
 {
@@ -119,6 +120,7 @@ ISMCTS_DEV double load_f64_readonly(const double* p) { return *p; }
 template <class T> ISMCTS_DEV T load_factors_readonly(const T* p) { return *p; }
 ISMCTS_DEV uint32_t load_u32_cg(const uint32_t* p) { return *p; }
 ISMCTS_DEV uint64_t load_u64_cg(const uint64_t* p) { return *p; }
+ISMCTS_DEV double load_f64_cg(const double* p) { return *p; }
 ISMCTS_DEV void atomic_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 ISMCTS_DEV void red_add_u64(uint64_t* p, uint64_t v) { *p += v; }
 #endif

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem + Game::kHandWords * kBlock) + threadIdx.x;
     Game::init_block(threadIdx.x, blockDim.x);
     __syncthreads();
-    uint32_t path[kKind == kSO && !Slot::kExp3 ? Game::kMaxDepth : 1];
+    uint32_t path[Lane<Game, Slot, kKind, kShared>::kPathWords];   // (local memory: only the levels a descent reaches are touched)
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t units = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
     if constexpr (kShared) {

@@ -139,6 +139,11 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     static constexpr bool kExp3 = Slot::kExp3;
     // MO-ISMCTS: one tree per player (mosolver.h:31-34); the root of player p's tree is slot p
     static constexpr uint32_t kTrees = kMulti ? Game::kMaxPlayers : 1;
+    // The descent records the nodes it passes (slot | player << 24; one entry per tree and level) for the
+    // backpropagation: private trees of every kind, and shared SO trees with UCB1.  The other shared trees walk
+    // the parent links instead.
+    static constexpr bool kPathed = kTree && (!kShared || (!kMulti && !kExp3));
+    static constexpr uint32_t kPathWords = kPathed ? Game::kMaxDepth * kTrees : 1;
 
     const SearchParams& P;
     LaneRng rng;
@@ -212,8 +217,9 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     ISMCTS_DEV static void update_exp(S* s, uint32_t r2, double prob)
     {
         if constexpr (S::kExp3) {
-            s->visits += 1;
-            s->score = ISMCTS_DADD(s->score, ISMCTS_DDIV(ISMCTS_DMUL((double)r2, 0.5), prob));
+            // (reductions: an IEEE addition each, performed where the node lives — nothing of the node is loaded)
+            red_add_u32(&s->visits, 1u);
+            atomic_add_f64(&s->score, ISMCTS_DDIV(ISMCTS_DMUL((double)r2, 0.5), prob));
         }
     }
 
@@ -248,13 +254,23 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                 }
                 for (; i < depth; ++i) update_node(path[i] & 0xFFFFFFu, path[i] >> 24, 1.0);
             } else {
-                // walk the parent links (the key of a node holds its parent's slot)
-                for (uint32_t t = 0; t < kTrees; ++t) {
-                    uint32_t n = node[t];
-                    while (n >= tree.roots) {
-                        const Slot s = load_slot(&tree.slots[n]);
-                        update_node(n, s.player, slot_prob(s));
-                        n = slot_parent_of(s.key);
+                // MO-ISMCTS and EXP3 on private trees: the recorded path of every tree, level by level.  Round 1 walked
+                // the parent links (load a node, find its parent in the key, load that ...): a chain of dependent
+                // loads per tree, the largest single source of stalls of the MO kernel (profiles/r02_extra_benches.md).
+                // Here the probabilities of a level's nodes (EXP3) are loaded together and the updates are reductions.
+                for (uint32_t i = 0; i < depth; ++i) {
+                    const uint32_t* const level = path + i * kTrees;
+                    double prob[kTrees];
+#pragma unroll
+                    for (uint32_t t = 0; t < kTrees; ++t) {
+                        const uint32_t n = level[t] & 0xFFFFFFu;
+                        prob[t] = 1.0;
+                        if constexpr (kExp3) { if (n >= tree.roots) prob[t] = load_prob(&tree.slots[n]); }
+                    }
+#pragma unroll
+                    for (uint32_t t = 0; t < kTrees; ++t) {
+                        const uint32_t n = level[t] & 0xFFFFFFu;
+                        if (n >= tree.roots) update_node(n, level[t] >> 24, prob[t]);
                     }
                 }
             }
@@ -275,6 +291,10 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     }
 
     template <class S> ISMCTS_DEV static double slot_prob(const S& s) { if constexpr (S::kExp3) return s.prob; else return 1.0; }
+    template <class S> ISMCTS_DEV static double load_prob(const S* s)
+    {
+        if constexpr (S::kExp3) return load_f64_cg(&s->prob); else return 1.0;
+    }
 
     // Node::selectChild + UCB1::operator(), node.h:58-72, ucb1.h:69-76: every legal
     // child becomes available, then the first maximum in creation order.
@@ -378,14 +398,19 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                     chosen.child_mask = Mask::none();
                     if (expand) move = untried.kth(draw_expansion(untried.count(), ahead));  // expand, sosolver.h:63-71
                     else chosen_slot = select_child(node[a], legal, chosen, move);
+                    // the reward is credited from the point of view of the player stored in the node (ucb1.h:53-56),
+                    // which is the mover when the node was created — in games where the same move can be made by
+                    // different players in different determinisations (phantom m,n,k) not necessarily today's mover
+                    uint32_t* const level = path + depth * kTrees;
                     for (uint32_t t = 0; t < kTrees; ++t) {
-                        if (kMulti && !((tree_players >> t) & 1u)) continue;
+                        if (kMulti && !((tree_players >> t) & 1u)) { level[t] = t; continue; }   // (a root: no update)
+                        uint32_t stored = who;
                         if (t == a && !expand) {
-                            node[t] = chosen_slot; node_children[t] = chosen.child_mask;
+                            node[t] = chosen_slot; node_children[t] = chosen.child_mask; stored = chosen.player;
                         } else if (node_children[t].test(move)) {         // MO: the child exists in this tree
                             Slot c;
                             node[t] = tree.find(node[t], move, c);
-                            node_children[t] = c.child_mask;
+                            node_children[t] = c.child_mask; stored = c.player;
                         } else {
                             const Mask grown = node_children[t].with(move);
                             tree.slots[node[t]].child_mask = grown;
@@ -393,11 +418,9 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                             node[t] = tree.insert(node[t], move, who, tree.count);
                             node_children[t] = Mask::none();
                         }
+                        level[t] = node[t] | (stored << 24);
                     }
-                    // the reward is credited from the point of view of the player stored in the node (ucb1.h:53-56),
-                    // which is the mover when the node was created — in games where the same move can be made by
-                    // different players in different determinisations (phantom m,n,k) not necessarily today's mover
-                    if (!kMulti && !kExp3) path[depth++] = node[0] | ((expand ? who : chosen.player) << 24);
+                    ++depth;
                 }
             }
             warp_sync();

@@ -170,7 +170,8 @@ struct WarpScratch {
     std::vector<uint32_t> ring, path;
     explicit WarpScratch(uint32_t w)
         : blocked(kWordsPerWarp * ((w + kBlockLanes - 1) / kBlockLanes)),
-          ring((size_t)LaneRng::kRingWords * w), path((size_t)Game::kMaxDepth * w) {}
+          ring((size_t)LaneRng::kRingWords * w), path((size_t)kPathWords * w) {}
+    static constexpr size_t kPathWords = (size_t)Game::kMaxDepth * Game::kMaxPlayers;   // (enough for every kind of lane)
 };
 
 // Game::prepare with the scratch of one lane installed.
@@ -237,7 +238,7 @@ int search_t(const void* root, uint64_t iterations, uint64_t seed, uint32_t pos,
     warp.run([&](uint32_t lane) {
         lane_tree_search<Game, Slot, kKind, false>(P, lane, true, ws.blocked.data() + (lane / kBlockLanes) * WarpScratch<Game>::kWordsPerWarp,
                                                    kBlockLanes, lane % kBlockLanes, ws.ring.data() + lane, width,
-                                                   ws.path.data() + (size_t)lane * Game::kMaxDepth);
+                                                   ws.path.data() + (size_t)lane * WarpScratch<Game>::kPathWords);
     });
     for (uint32_t i = 0; i < width; ++i) if (it[i] != iterations) return 6;
     return dump_table(tables.data() + cap * dump, cap, L::kTrees, kKind == kMO ? player : 0, nodes, capacity, count);
@@ -290,7 +291,7 @@ int shared_search_t(const void* root, uint64_t iterations, uint32_t width, uint6
     warp.run([&](uint32_t lane) {
         lane_tree_search<Game, Slot, kKind, true>(P, lane, true, ws.blocked.data() + (lane / kBlockLanes) * WarpScratch<Game>::kWordsPerWarp,
                                                   kBlockLanes, lane % kBlockLanes, ws.ring.data() + lane, width,
-                                                  ws.path.data() + (size_t)lane * Game::kMaxDepth);
+                                                  ws.path.data() + (size_t)lane * WarpScratch<Game>::kPathWords);
     });
     *done_out = it[0];
     return dump_table(table.data(), table.size(), n_roots, kKind == kMO ? player : 0, nodes, capacity, count);
