@@ -346,7 +346,7 @@ def b200_arm(args):
             workload="KW4 mid-game roots: deal i + d ~ U{0..60} random plies (SURVEY 8d), SO-ISMCTS root-parallel",
             mean_players_alive=float(np.mean([bin(s.alive_mask).count("1") for s in pos_states])))
         extra["mo_exp3"] = leg_line(
-            Leg(main_states(capi, 16), args.mo_trees * world, iterations,
+            Leg(main_states(capi, 32), args.mo_trees * world, iterations,
                 solver=capi.SOLVER_MO, policy=capi.POLICY_EXP3),
             workload="KW4 MOSolver<Card, RootParallel, EXP3> (BASELINE config 4): one tree per player, trees sharded over the ranks")
         if T % world == 0:
