@@ -305,6 +305,11 @@ def b200_arm(args):
 
     T = args.trees or host_cores()
     lanes = max(1, args.lanes)
+    if lanes > 1:
+        # never fewer than 128 iterations per lane (profiles/r02_tree_parallel_quality.md): on a host with very many
+        # threads the trees are small and get fewer lanes
+        cap = args.iterations // T // 128
+        lanes = max(1, min(lanes, cap // 32 * 32 if cap >= 32 else cap))
     resident_blocks = 148 * 8
     B = args.positions or (max(1, 8 * resident_blocks * 128 // (T * lanes)) if lanes > 1 else 1024)
     iterations = args.iterations * world                      # weak scaling: every GPU adds its own 1M per decision
