@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 nvidia-smi -L | head -3
 python -m pytest tests/test_cpp_conformance.py tests/test_gpu_parity.py -m gpu -q -k "devices or search_multi or conformance or lanes_cap" > $O/r02_pytest_2gpu.log 2>&1; tail -5 $O/r02_pytest_2gpu.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 nvidia-smi -L | wc -l; nproc
 show() { python - "$1" <<'PY'

@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU session: tests, persistent-grid sweep, full bench, tree-parallel quality, ncu capture.
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python -m pytest tests -m gpu -q > $O/r02_pytest_b.log 2>&1; tail -15 $O/r02_pytest_b.log
 for P in 64 128 256 512 1024; do

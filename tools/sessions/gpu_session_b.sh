@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python tools/geometry_agreement.py --geometries 16,2368,16x128,16x148,64x32 --out $O/r02_geometry.jsonl > $O/r02_geometry.log 2>&1; cut -c1-700 $O/r02_geometry.log
 python tools/extra_bench.py kw-hybrid > $O/r02_hybrid.jsonl 2> $O/r02_hybrid.err; cat $O/r02_hybrid.jsonl | cut -c100-400

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python tools/extra_bench.py kw-hybrid --hybrid 16x128,16x148,64x32,148x8 > $O/r02_c_hybrid.jsonl 2> $O/r02_c_hybrid.err; cut -c100-420 $O/r02_c_hybrid.jsonl
 ISMCTS_MIN_BLOCKS=4 python tools/extra_bench.py kw-hybrid --hybrid 16x128 > $O/r02_c_hybrid_mb4.jsonl 2>&1; cut -c100-420 $O/r02_c_hybrid_mb4.jsonl

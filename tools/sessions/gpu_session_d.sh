@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python -m pytest tests -m gpu -q -x > $O/r02_pytest_e.log 2>&1; tail -4 $O/r02_pytest_e.log
 for cfg in "64 2368 0" "1024 2368 0" "74 16 128" "296 16 128" "592 16 128" "592 64 32"; do

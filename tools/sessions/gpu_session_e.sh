@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python -m pytest tests -m gpu -q -x > $O/r02_pytest_f.log 2>&1; tail -4 $O/r02_pytest_f.log
 run() { # name, lib, args...

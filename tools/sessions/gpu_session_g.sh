@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python -m pytest tests -m gpu -q > $O/r02_pytest_h.log 2>&1; tail -6 $O/r02_pytest_h.log
 run() { name=$1; shift

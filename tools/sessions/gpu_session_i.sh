@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 for MB in 4 6 8; do
   ISMCTS_MIN_BLOCKS_MO=$MB python tools/extra_bench.py kw-mo-exp3 > $O/r02_i_mo_mb$MB.jsonl 2> $O/r02_i_mo_mb$MB.err

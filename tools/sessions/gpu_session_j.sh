@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.." || exit 1
+cd "$(dirname "$0")/../.." || exit 1
 O=gpurun_out
 python tools/extra_bench.py kw-mo-exp3 --reference > $O/r02_j_mo.jsonl 2> $O/r02_j_mo.err; cut -c100-300 $O/r02_j_mo.jsonl
 python -m pytest tests -m gpu -q > $O/r02_pytest_k.log 2>&1; tail -5 $O/r02_pytest_k.log
