@@ -200,9 +200,12 @@ int ismcts_set_stream(ismcts_ctx* ctx, void* cuda_stream);
  * all devices.  Time mode (iterations == 0): every tree iterates until
  * `time_ns` nanoseconds have passed on the device clock (utility.h:51-60).
  */
-/* Tree parallelisation (TreeParallel, execution.h:169-179): the `trees` trees of a position are ONE
- * shared tree searched by `lanes` iterations in flight with virtual loss; lanes in bits 8..31 (the rest of
- * the word: bits 3..7 must be zero). */
+/* Tree parallelisation (TreeParallel, execution.h:169-179), alone or inside root parallelisation: EACH of the
+ * `trees` trees of a position is searched by `lanes` lanes together — iterations in flight on one tree, with virtual
+ * loss; lanes in bits 8..31 (bits 3..7 must be zero).  trees = 1: the reference's TreeParallel.  trees = 16, lanes = 128:
+ * the geometry of the reference's RootParallel on a 16-thread host with a block of lanes on every tree (what bench.py
+ * measures).  Keep iterations / trees / lanes >= 128 (profiles/r02_tree_parallel_quality.md).  With lanes = 1 the search
+ * equals the sequential one bit for bit; with more the interleaving inside a tree is the hardware's. */
 #define ISMCTS_FLAG_SHARED_TREE 1u
 #define ISMCTS_FLAG_LANES_SHIFT 8
 /* Knockout Whist: the caller guarantees that no position has more than four players, which lets the

@@ -160,6 +160,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     uint32_t iteration_stride; // shared tree: the lanes of a tree interleave their iteration ids
     uint32_t my_nodes;        // shared tree: nodes this lane has created; its share of the table is max_nodes / lanes
     uint32_t created_seq;     // shared tree: nodes this lane has created in the current iteration
+    uint32_t mask_known;      // shared SO tree: node_children[0] holds the child mask of the cursor (descend_shared)
     uint32_t tree_players;    // MO: bit p = player p has a tree (the players of the root position)
 
     ISMCTS_DEV explicit Lane(const SearchParams& p) : P(p) {}
@@ -178,7 +179,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
     {
         rng.begin_iteration(first_iteration + done * iteration_stride);
         game().start(prep);                                        // cloneAndRandomise, sosolver.h:46 / mosolver.h:60
-        depth = 0; plies = 0; created_seq = 0;
+        depth = 0; plies = 0; created_seq = 0; mask_known = 0;
         if (kMulti) {
             // (private trees: the lane is the only writer of its roots' masks; shared trees re-read masks at every level)
             for (uint32_t t = 0; t < kTrees; ++t) {
@@ -458,7 +459,8 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
 
     // UCB1 on a node whose children other lanes update (selectChild as in select_child()).
     template <class S>
-    ISMCTS_DEV uint32_t select_child_shared(uint32_t parent, const Mask& legal, uint32_t& chosen_move, uint32_t& chosen_player)
+    ISMCTS_DEV uint32_t select_child_shared(uint32_t parent, const Mask& legal, uint32_t& chosen_move, uint32_t& chosen_player,
+                                            Mask& chosen_children)
     {
         if constexpr (!S::kExp3) {
             for (Mask rest = legal; rest.any();) tree.prefetch(parent, rest.pop_lowest());
@@ -495,6 +497,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                 const double u = ismcts_ucb_value(c.score2, f.inv, f.inv_sqrt, sqrt_ln_avail, exploration);
                 if (u > best_u || (u == best_u && c.created < best_created)) {
                     best_u = u; best_created = c.created; best = ci; chosen_move = m; chosen_player = c.player;
+                    chosen_children = c.child_mask;
                 }
                 if (!more) break;
                 m = m_next; i = i_next; c = c_next;
@@ -506,6 +509,7 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
             S chosen;
             const uint32_t ci = select_child(parent, legal, chosen, chosen_move);
             chosen_player = chosen.player;
+            chosen_children = chosen.child_mask;
             return ci;
         }
     }
@@ -528,12 +532,18 @@ struct Lane : LaneGameStore<Game, game_home_in_scratch<Game>(0)> {
                     } else {
                         const uint32_t who = game().current_player();
                         const uint32_t a = kMulti ? who : 0;                  // the deciding tree
-                        const Mask kids = Mask::load_shared(&tree.slots[node[a]].child_mask); // other lanes add children
+                        // The children of the cursor: other lanes add children, so the mask is read from the node — except
+                        // (SO) right after a selection, which has just read the chosen child's slot, mask included: a
+                        // mask a few hundred cycles old instead of one more dependent round trip per level.  A child
+                        // added since then is found by find_or_insert_shared() when this lane tries to create it.
+                        const Mask kids = (!kMulti && mask_known) ? node_children[0] : Mask::load_shared(&tree.slots[node[a]].child_mask);
                         const Mask untried = legal.minus(kids);
                         expand = untried.any();
                         uint32_t chosen = 0, stored = who;
+                        Mask chosen_children = Mask::none();
                         if (expand) move = untried.kth(draw_expansion(untried.count(), ahead));
-                        else chosen = select_child_shared<Slot>(node[a], legal, move, stored);
+                        else chosen = select_child_shared<Slot>(node[a], legal, move, stored, chosen_children);
+                        if constexpr (!kMulti) { node_children[0] = chosen_children; mask_known = !expand; }
                         for (uint32_t t = 0; t < kTrees; ++t) {
                             if (kMulti && !((tree_players >> t) & 1u)) continue;
                             uint32_t next;
@@ -649,7 +659,7 @@ ISMCTS_DEV void lane_tree_search_on(Lane<Game, Slot, kKind, kShared>& lane, cons
     lane.path = path;
     lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 0; lane.deadline = 0; lane.first_iteration = 0;
-    lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0;
+    lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0; lane.mask_known = 0;
     for (uint32_t t = 0; t < L::kTrees; ++t) lane.root_children[t] = Mask::none();
     uint32_t tree_index = 0;
     if (valid) {
@@ -752,7 +762,7 @@ ISMCTS_DEV void lane_playout(const SearchParams& P, uint32_t gtid, bool valid, u
     lane.path = nullptr;
     lane.game().bind(scratch, scratch_stride, column);
     lane.phase = kDone; lane.done = 0; lane.quota = 1; lane.deadline = 0; lane.first_iteration = 0;
-    lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0;
+    lane.iteration_stride = 1; lane.my_nodes = 0; lane.created_seq = 0; lane.mask_known = 0;
     lane.root_children[0] = Mask::none();
     if (valid) {
         const uint32_t pos = gtid / per_position;
