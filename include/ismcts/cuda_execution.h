@@ -40,7 +40,7 @@ namespace ISMCTS
 /// Thrown for engine failures (no device, CUDA errors, capacity); illegal moves keep std::out_of_range.
 struct CudaError : std::runtime_error
 {
-    CudaError(int code, std::string const &what) : std::runtime_error{what}, code{code} {}
+    CudaError(int errorCode, std::string const &what) : std::runtime_error{what}, code{errorCode} {}
     int code;
 };
 
