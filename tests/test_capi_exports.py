@@ -76,3 +76,31 @@ def test_mnk_helpers_match_oracle(engine_lib):
                 mv = int(rnd.choice(la))
                 assert O.lib().orc_mnk_apply(C.byref(a), mv) == capi.mnk_apply(b, mv) == 0
                 assert bytes(a) == bytes(b)
+
+
+def _build_abi_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_example")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "c", "abi_example.c"), "-L" + os.path.join(root, "ismcsolver_b200"),
+                    "-lismcts_b200", "-Wl,-rpath," + os.path.join(root, "ismcsolver_b200")], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_links(engine_lib, tmp_path):
+    """include/ismcts_b200.h compiles as C11 with -Werror and a C program links against the library; without a device
+    it is told so (ISMCTS_ERR_NO_DEVICE) instead of silently computing on the CPU."""
+    import subprocess
+    exe = _build_abi_example(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "no device" in out.stdout or "kernels launched" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_searches_on_the_gpu(engine_lib, tmp_path):
+    import subprocess
+    out = subprocess.run([_build_abi_example(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("position ") == 4 and "kernels launched" in out.stdout
