@@ -80,16 +80,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) search_kernel(SearchParams
     const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t units = P.n_positions * P.trees * (kShared ? P.lanes_per_tree : 1u);
     if constexpr (kShared) {
-        if (P.block_owns_tree) {
-            // block = tree: zero the tree's table (streaming stores, 2 KB per instruction of the block) and write its roots;
-            // the zeroing then overlaps with the searches of the blocks already under way instead of preceding the launch
-            uint4* const first = reinterpret_cast<uint4*>(reinterpret_cast<Slot*>(P.pool) + ((size_t)blockIdx.x << P.log2cap));
-            const size_t words = (sizeof(Slot) / sizeof(uint4)) << P.log2cap;
-            for (size_t i = threadIdx.x; i < words; i += kBlock) __stcs(first + i, make_uint4(0, 0, 0, 0));
-            __syncthreads();
-            if (threadIdx.x == 0) init_shared_root<Slot>(P, blockIdx.x, kKind == kMO ? Game::kMaxPlayers : 1u);
-            __syncthreads();
-        }
         lane_tree_search<Game, Slot, kKind, true>(P, gtid, gtid < units, smem, kBlock, threadIdx.x, ring, kBlock, path, gtid);
     } else {
         const uint32_t lane = threadIdx.x & 31u;
@@ -585,9 +575,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     rc = ensure_ln_table(ctx, (uint32_t)std::min<uint64_t>(max_it + 3 + (shared ? (uint64_t)width + 1 : 0), 0x7FFFFFFFull));
     if (rc) return rc;
 
-    // (recycled tables are zeroed by their warps, the table of a tree searched by one block by that block)
-    const bool block_owns_tree = shared && width == (uint32_t)kBlock;
-    if (!recycle && !block_owns_tree) CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, pool_need, ctx->stream));
+    if (!recycle) CUDA_TRY(ctx, cudaMemsetAsync(ctx->pool, 0, pool_need, ctx->stream));   // (recycled tables are zeroed by their warps)
     CUDA_TRY(ctx, cudaMemsetAsync(d_visits, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_score2, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(d_avail, 0, (size_t)d->n_positions * stride * sizeof(uint64_t), ctx->stream));
@@ -611,7 +599,6 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.lanes_per_tree = width;
     P.start_ns = ctx->start_ns;
     P.unit_queue = recycle ? ctx->queue : nullptr;
-    P.block_owns_tree = block_owns_tree ? 1u : 0u;
 
     ctx->last_log2cap = log2cap; ctx->last_lanes = recycle ? 0 : trees; ctx->last_game = d->game;
     ctx->last_solver = d->solver; ctx->last_policy = d->policy;
@@ -621,7 +608,7 @@ extern "C" int ismcts_search_device(ismcts_ctx* ctx, const ismcts_search_desc* d
     P.prepared = ctx->prepared;
     void* args[] = {&P};
     const uint32_t tgrid = (trees + 127) / 128;
-    if (shared && !block_owns_tree) {
+    if (shared) {
         uint32_t n_roots = kernels.roots_per_table;
         void* init_args[] = {&P, &n_roots};
         rc = launch(ctx, kernels.init_shared, tgrid, 128, 0, init_args);

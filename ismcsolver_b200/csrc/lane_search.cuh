@@ -73,9 +73,6 @@ struct SearchParams {
     // private trees, count mode, more trees than resident lanes: the warps of a persistent grid claim 32 trees at a
     // time from this counter and reuse their tables (null: lane = tree, one pass)
     uint32_t* unit_queue;
-    // shared trees searched by exactly one block of lanes each (lanes_per_tree == block size): the block zeroes its
-    // tree's table and writes its root(s) itself before it starts (no memset of the pool, no set-up kernel)
-    uint32_t block_owns_tree;
 };
 
 // Iterations of one tree in count mode: the reference drains one shared counter
